@@ -1,0 +1,120 @@
+/*
+ * vallex_b200.h -- C ABI of the B200-native VALL-E-X inference engine (libvallex_b200.so).
+ *
+ * The reference (Plachtaa/VALL-E-X) has no FFI of its own: its boundary is the Python API
+ * `utils.generation.generate_audio` / `models.vallex.VALLE.inference` plus two file formats
+ * (checkpoint state_dict keys, presets/*.npz).  The Python host layer in
+ * vall-e-x_b200/vallex_b200/ mirrors that API and binds the entry points below with ctypes
+ * (see INTEGRATION.md for the stub a reference maintainer would add).  Each entry point names
+ * the reference code it replaces (paths relative to the reference tree).
+ *
+ * Conventions: plain pointers and sizes only; every call returns 0 on success and a negative
+ * code on failure with a thread-local message in vx_last_error(); `mem` says where the caller's
+ * data buffers live (VX_HOST: pageable or pinned host memory, copies are enqueued on the stream
+ * inside the call; VX_DEVICE: device pointers on the engine's device); `stream` is a
+ * cudaStream_t (NULL = the engine's own stream).  An engine handle is not thread-safe; distinct
+ * handles are independent.  One engine per GPU; there is no CPU fallback.
+ */
+#ifndef VALLEX_B200_H_
+#define VALLEX_B200_H_
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define VX_API __attribute__((visibility("default")))
+#else
+#define VX_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VX_OK 0
+#define VX_ERR_ARG (-1)
+#define VX_ERR_CUDA (-2)
+#define VX_ERR_STATE (-3)
+#define VX_ERR_CAPACITY (-4)
+
+/* dtype_mode */
+#define VX_F32 0  /* fp32 weights, fp32 KV, fp32 math: the parity mode (bit-exact greedy tokens vs the fp32 reference) */
+#define VX_BF16 1 /* bf16 GEMM weights + bf16 KV cache, fp32 accumulate: the performance mode */
+
+/* mem */
+#define VX_HOST 0
+#define VX_DEVICE 1
+
+typedef struct vx_engine vx_engine;
+
+/* ABI/version string, e.g. "vallex_b200 0.1 sm_100a". */
+VX_API const char* vx_version(void);
+VX_API const char* vx_last_error(void);
+
+/* Replaces: model construction `VALLE(N_DIM, NUM_HEAD, NUM_LAYERS, ...)` + `.to(device)`
+ * (utils/generation.py:67-78).  Architecture constants are fixed (macros.py:1-6).
+ * max_batch: utterances in flight; max_ctx: max S+P+1+T rows of one utterance. */
+VX_API int vx_create(int device, int max_batch, int max_ctx, int dtype_mode, vx_engine** out);
+VX_API void vx_destroy(vx_engine* e);
+
+/* Replaces: `model.load_state_dict(checkpoint["model"], strict=True)` (utils/generation.py:79-83) and
+ * `Vocos.from_pretrained(...)` weights (utils/generation.py:89).  `key` is the reference state-dict key
+ * (SURVEY.md 8(b)); Vocos keys are prefixed "vocos." (e.g. "vocos.backbone.embed.weight"); the fp32
+ * sinusoid table is passed as key "pe_table" [rows,1024] (modules/embedding.py:68-91 is evaluated with
+ * torch on the host so the table is bit-identical).  `data` is host fp32, row-major, `shape[ndim]`.
+ * vx_finalize_weights: strict check (every key present, shapes match), packs to the kernel layouts and
+ * precomputes the 7x25 AdaLN (weight,bias) vectors (modules/transformer.py:93-108). */
+VX_API int vx_load_weight(vx_engine* e, const char* key, const float* data, const int64_t* shape, int ndim);
+VX_API int vx_finalize_weights(vx_engine* e);
+
+/* Replaces: the argument marshalling of `VALLE.inference` (models/vallex.py:458-527): B independent
+ * utterances (the reference asserts B == 1, models/vallex.py:491; best_of replicas are B copies).
+ * text_ids [B,Smax] phoneme ids (prompt phonemes then new phonemes), text_lens [B],
+ * lang_ids [B,Smax] per-token language id in the MODEL numbering en=0 zh=1 ja=2
+ * (models/vallex.py:439-443,499-505: prompt part = prompt_language, rest = text_language),
+ * prompt_codes [B,Pmax,8] EnCodec tokens, prompt_lens [B] (0 allowed: no prompt). */
+VX_API int vx_set_batch(vx_engine* e, int B, const int32_t* text_ids, const int32_t* text_lens, const int32_t* lang_ids,
+                 int Smax, const int32_t* prompt_codes, const int32_t* prompt_lens, int Pmax, int mem, void* stream);
+
+/* Replaces: the first iteration of the AR loop (kv_cache is None; models/vallex.py:528-568 with
+ * modules/transformer.py:447-473, modules/activation.py:142-167): embeds text+language+PE and
+ * BOS+prompt codebook-0, runs the 12 pre-LN layers under the text/audio mask (models/vallex.py:534-549),
+ * fills the KV cache and leaves the first-step logits on the device. */
+VX_API int vx_ar_prefill(vx_engine* e, void* stream);
+
+/* Replaces: the rest of the AR loop (models/vallex.py:528-598) incl. `topk_sampling`
+ * (models/vallex.py:791-853) and the stop rule: per utterance, stop at EOS (1024) or after
+ * min(max_new, 16*S_b) tokens (max_new <= 0: 16*S_b only; models/vallex.py:574-578).
+ * top_k <= 0: no top-k filter (the API default -100); top_p >= 1: off; seed: Philox stream for the
+ * multinomial draw.  ignore_eos != 0: never stop early (benchmark config 3).  forced_tokens
+ * (nullable) [B,max_steps]: teacher forcing -- the token fed back at step t is forced_tokens[b][t]
+ * while out_tokens still records the sampled one.
+ * out_tokens [B,max_steps] (max_steps = the largest per-utterance budget, returned in *out_max_steps
+ * by vx_ar_budget), out_lens [B] = T_b, out_sum_logprobs [B] nullable (models/vallex.py:572). */
+VX_API int vx_ar_budget(vx_engine* e, int max_new, int* out_max_steps);
+VX_API int vx_ar_decode(vx_engine* e, int max_new, int top_k, float top_p, float temperature, uint64_t seed,
+                 int ignore_eos, const int32_t* forced_tokens, int32_t* out_tokens, int32_t* out_lens,
+                 float* out_sum_logprobs, int mem, void* stream);
+
+/* Replaces: the NAR stage loop (models/vallex.py:604-686, prefix_mode 1) with
+ * modules/transformer.py:265-312,402-445 (AdaLN encoder) and modules/activation.py:566-585.
+ * cb0 [B,Tmax] generated codebook-0 tokens (NULL: use the tokens vx_ar_decode left on the device),
+ * t_lens [B].  out_codes [B,Tmax,8] (column 0 = cb0). */
+VX_API int vx_nar(vx_engine* e, const int32_t* cb0, const int32_t* t_lens, int Tmax, int32_t* out_codes, int mem,
+           void* stream);
+
+/* Replaces: `vocos.codes_to_features(frames)` + `vocos.decode(features, bandwidth_id)`
+ * (utils/generation.py:148-150).  codes [8,B,T]; wave [B, 320*T] fp32. */
+VX_API int vx_vocos_decode(vx_engine* e, const int32_t* codes, int B, int T, int bandwidth_id, float* wave, int mem,
+                    void* stream);
+
+/* Measurement hooks (bench.py): CUDA-event durations (ms) of the last prefill / decode / nar / vocos
+ * call on the engine's stream, the number of decode steps and kernels launched by the last call, and
+ * debug access to device-side intermediates for the layer-by-layer parity tests. */
+VX_API int vx_last_timing(vx_engine* e, float* ms_prefill, float* ms_decode, float* ms_nar, float* ms_vocos,
+                   int64_t* decode_steps, int64_t* kernel_launches);
+VX_API int vx_debug_read(vx_engine* e, const char* what, float* dst, int64_t max_elems, int64_t* out_elems);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VALLEX_B200_H_ */

@@ -1,0 +1,108 @@
+"""Generate the committed golden fixtures by running the UNMODIFIED reference.
+
+Run HERE (authoring container, /root/reference present):  python tests/golden/make_golden.py [case ...]
+
+For every case the reference `models.vallex.VALLE` (loaded through oracle/ref_shim.py) is given a
+synthetic checkpoint (`vallex_b200.weights.synthetic_state_dict(seed)`, strict load) and run greedy
+(`top_k=1, temperature=1.0`) exactly like models/vallex.py:458-686.  Stored per case:
+  inputs:  x [S], Lp, prompt [P,8], prompt_language, text_language (str or per-token list), seed
+  outputs: codes [T,8] (fp32 weights), ar_top2 [T+1,2] / nar_top2 [7,T,2] (top-1/top-2 logit per step,
+           captured with forward hooks on the predict layers -- the reference itself is untouched),
+           codes_bf16w + margins: the same run with every matrix weight rounded to bf16 (the values the
+           engine's bf16 mode holds), computed in fp32 by the reference.
+Real preset prompts (inputs only) are read from /root/reference/presets/*.npz and embedded in the
+fixture because the GPU box has no reference tree.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", ".."))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "vall-e-x_b200"))
+
+from oracle import ref_shim  # noqa: E402
+from vallex_b200.weights import round_state_dict_bf16, synthetic_state_dict  # noqa: E402
+
+OUT = os.path.dirname(__file__)
+LANGS = ["en", "zh", "ja"]
+
+CASES = {
+    # name: (seed, Lp, Ln, P, prompt_language, text_language, preset)
+    "tiny_en": (0, 2, 4, 5, "en", "en", None),
+    "noprompt_en": (0, 0, 5, 0, "en", "en", None),
+    "mixlang": (1, 3, 5, 12, "zh", ["en", "en", "zh", "ja", "ja"], None),
+    "mid_ja": (2, 6, 10, 40, "ja", "ja", None),
+    "cfg1_librispeech": (0, None, 64, None, "en", "en", "librispeech_1"),
+}
+
+
+def build_inputs(name):
+    seed, Lp, Ln, P, pl, tl, preset = CASES[name]
+    rng = np.random.default_rng(1234 + seed)
+    if preset is not None:
+        d = np.load(os.path.join(ref_shim.REF_ROOT, "presets", preset + ".npz"))
+        prompt = d["audio_tokens"][0].astype(np.int64)
+        xp = d["text_tokens"][0].astype(np.int64)
+        Lp, P = len(xp), prompt.shape[0]
+    else:
+        prompt = rng.integers(0, 1024, size=(P, 8), dtype=np.int64)
+        xp = rng.integers(5, 70, size=(Lp,), dtype=np.int64)
+    xn = rng.integers(5, 70, size=(Ln,), dtype=np.int64)
+    x = np.concatenate([xp, xn])
+    return seed, x, Lp, prompt, pl, tl
+
+
+def run_reference(model, x, Lp, prompt, pl, tl):
+    ar, nar = [], [[] for _ in range(7)]
+    hooks = [model.ar_predict_layer.register_forward_hook(lambda m, i, o: ar.append(o.detach().clone()))]
+    for j in range(7):
+        hooks.append(model.nar_predict_layers[j].register_forward_hook(
+            lambda m, i, o, j=j: nar[j].append(o.detach().clone())))
+    with torch.no_grad():
+        codes = model.inference(torch.from_numpy(x)[None], torch.tensor([len(x)]), torch.from_numpy(prompt)[None],
+                                enroll_x_lens=Lp, top_k=1, temperature=1.0, prompt_language=pl,
+                                text_language=tl, best_of=1)
+    for h in hooks:
+        h.remove()
+    ar_top2 = torch.stack([torch.topk(l[0], 2)[0] for l in ar]).numpy()           # [T+1, 2]
+    nar_top2 = torch.stack([torch.topk(n[0][0], 2, dim=-1)[0] for n in nar]).numpy()  # [7, T, 2]
+    ar_logits_head = torch.stack([l[0] for l in ar[:4]]).numpy()                  # first 4 steps, full rows
+    return codes[0].numpy(), ar_top2, nar_top2, ar_logits_head
+
+
+def main(names):
+    torch.set_num_threads(os.cpu_count())
+    by_seed = {}
+    for name in names:
+        seed, x, Lp, prompt, pl, tl = build_inputs(name)
+        if seed not in by_seed:
+            by_seed[seed] = synthetic_state_dict(seed)
+        sd = by_seed[seed]
+        out = dict(x=x, Lp=np.int64(Lp), prompt=prompt, prompt_language=np.array(pl),
+                   text_language=np.array(tl if isinstance(tl, list) else [tl]),
+                   text_language_is_list=np.bool_(isinstance(tl, list)), seed=np.int64(seed))
+        for tag, rounding in (("", None), ("_bf16w", "bf16")):
+            sdr = sd
+            if rounding:
+                sdr = round_state_dict_bf16(sd)
+            t0 = time.time()
+            model = ref_shim.load_reference_valle(sdr)
+            codes, ar_top2, nar_top2, head = run_reference(model, x, Lp, prompt, pl, tl)
+            print(f"{name}{tag}: T={codes.shape[0]} in {time.time() - t0:.1f}s", flush=True)
+            out["codes" + tag] = codes.astype(np.int16)
+            out["ar_top2" + tag] = ar_top2.astype(np.float32)
+            out["nar_top2" + tag] = nar_top2.astype(np.float32)
+            if tag == "":
+                out["ar_logits_head"] = head.astype(np.float32)
+            del model
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:] or [n for n in CASES if n != "cfg1_librispeech"])

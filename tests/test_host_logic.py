@@ -1,0 +1,77 @@
+"""CPU: host-side mirror of the reference API (argument checks, error types, language-id mapping,
+prompt lookup) -- no engine calls."""
+import numpy as np
+import pytest
+import torch
+
+from vallex_b200 import generation, macros
+from vallex_b200.vallex import VALLE
+from vallex_b200.weights import is_bf16_matrix, sine_position_table, synthetic_state_dict, synthetic_vocos_state_dict
+
+
+def _model():
+    return VALLE(1024, 16, 12, norm_first=True, add_prenet=False, prefix_mode=1, share_embedding=True,
+                 nar_scale_factor=1.0, prepend_bos=True, num_quantizers=8)
+
+
+def test_constructor_matches_reference_call_and_rejects_other_configs():
+    m = _model()
+    assert m.language_ID == {"en": 0, "zh": 1, "ja": 2}          # models/vallex.py:439-443
+    assert m.eval() is m
+    with pytest.raises(NotImplementedError):
+        VALLE(512, 8, 6)
+    with pytest.raises(NotImplementedError):
+        m.forward()                                               # models/vallex.py:447-457
+    with pytest.raises(RuntimeError):
+        m.to("cpu")
+
+
+def test_language_id_split():
+    m = _model()
+    ids = m._lang_ids(6, 2, "zh", "en")
+    assert ids.tolist() == [1, 1, 0, 0, 0, 0]
+    ids = m._lang_ids(5, 2, "en", ["ja", "zh", "en"])
+    assert ids.tolist() == [0, 0, 2, 1, 0]
+    with pytest.raises(RuntimeError):
+        m._lang_ids(5, 2, "en", ["ja", "zh"])
+    # npz lang_code numbering differs from the model numbering (macros.py:15-32 vs models/vallex.py:439-443)
+    assert macros.code2lang[2] == "en" and macros.LANGUAGE_ID["en"] == 0
+
+
+def test_inference_asserts_like_reference():
+    m = _model()
+    x = torch.zeros(1, 4, dtype=torch.long)
+    with pytest.raises(AssertionError):
+        m.inference(x[0], torch.tensor([4]), torch.zeros(1, 0, 8), 0, prompt_language="en", text_language="en")
+    with pytest.raises(AssertionError):
+        m.inference(x, torch.tensor([4]), torch.zeros(2, 3, 8), 0, prompt_language="en", text_language="en")
+    with pytest.raises(AssertionError):
+        m.inference(x, torch.tensor([0]), torch.zeros(1, 3, 8), 0, prompt_language="en", text_language="en")
+
+
+def test_generation_errors(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    with pytest.raises(ValueError, match="Cannot find prompt"):
+        generation._load_prompt("no_such_prompt")
+    with pytest.raises(ValueError, match="No such mode"):
+        generation.generate_audio_from_long_text([np.arange(5, 9)], prompt="x", language="en", mode="bogus")
+    # npz prompt format is read unchanged (utils/generation.py:111-119)
+    np.savez(tmp_path / "p.npz", audio_tokens=np.zeros((1, 7, 8), np.int64), text_tokens=np.full((1, 3), 9, np.int64),
+             lang_code=np.int32(1))
+    a, t, lang = generation._load_prompt(str(tmp_path / "p.npz"))
+    assert a.shape == (1, 7, 8) and a.dtype == torch.int32 and t.shape == (1, 3) and lang == "ja"
+    a, t, lang = generation._load_prompt(None)
+    assert a.shape == (1, 0, 8) and t.shape == (1, 0) and lang is None
+
+
+def test_synthetic_checkpoint_layout():
+    sd = synthetic_state_dict(3)
+    assert len(sd) == 374
+    assert sum(v.numel() for k, v in sd.items() if not k.startswith("nar_predict_layers") or k.endswith("6.weight")) == 370539524
+    assert sd["nar_predict_layers.0.weight"] is sd["nar_audio_embeddings.2.word_embeddings.weight"]
+    assert is_bf16_matrix("ar_decoder.layers.3.linear2.weight") and is_bf16_matrix("nar_audio_embeddings.5.word_embeddings.weight")
+    assert not is_bf16_matrix("ar_text_embedding.word_embeddings.weight") and not is_bf16_matrix("ar_decoder.layers.0.norm1.weight")
+    v = synthetic_vocos_state_dict(0)
+    assert v["head.out.weight"].shape == (1282, 384) and v["backbone.embed.weight"].shape == (384, 128, 7)
+    pe = sine_position_table(16)
+    assert pe.shape == (16, 1024) and float(pe[0, 1]) == 1.0 and float(pe[0, 0]) == 0.0

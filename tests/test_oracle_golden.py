@@ -1,0 +1,74 @@
+"""CPU: the oracle (oracle/vallex_oracle.py) is pinned to the fixtures the UNMODIFIED reference produced
+(tests/golden/make_golden.py), bit-exactly, and -- where /root/reference exists -- live against it."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, state_dict_for
+from oracle import ref_shim
+from oracle.vallex_oracle import OracleVALLE
+
+
+def _run(oracle, g, **kw):
+    x = torch.from_numpy(g["x"].astype(np.int64))[None]
+    y = torch.from_numpy(g["prompt"].astype(np.int64))[None]
+    return oracle.inference(x, torch.tensor([x.shape[1]]), y, int(g["Lp"]), top_k=1, temperature=1.0,
+                            prompt_language=g["prompt_language_arg"], text_language=g["text_language_arg"], **kw)
+
+
+@pytest.mark.parametrize("name", ["tiny_en", "noprompt_en", "mixlang"])
+def test_oracle_reproduces_reference_tokens(name):
+    g = load_golden(name)
+    dbg = {}
+    codes = _run(OracleVALLE(state_dict_for(g["seed"])), g, debug=dbg)[0].numpy()
+    assert codes.shape == g["codes"].shape
+    assert np.array_equal(codes, g["codes"].astype(np.int64))
+    head = torch.stack([l[0] for l in dbg["logits"][:4]]).numpy()
+    assert np.array_equal(head, g["ar_logits_head"])  # same floats, not just same argmax
+    top2 = torch.stack([torch.topk(l[0], 2)[0] for l in dbg["logits"]]).numpy()
+    np.testing.assert_allclose(top2, g["ar_top2"], rtol=0, atol=0)
+
+
+def test_oracle_reproduces_reference_tokens_bf16_rounded_weights():
+    g = load_golden("tiny_en")
+    codes = _run(OracleVALLE(state_dict_for(g["seed"], rounded=True)), g)[0].numpy()
+    assert np.array_equal(codes, g["codes_bf16w"].astype(np.int64))
+
+
+def test_oracle_prefix_of_full_size_case():
+    """cfg1 (librispeech_1 prompt, S=122, T=1952): the AR prefix under max_new_tokens equals the reference's
+    tokens (greedy decoding is causal), without paying for the whole CPU run."""
+    g = load_golden("cfg1_librispeech")
+    o = OracleVALLE(state_dict_for(g["seed"]))
+    x = torch.from_numpy(g["x"].astype(np.int64))[None]
+    y = torch.from_numpy(g["prompt"].astype(np.int64))[None]
+    yy = o.ar_decode(x, y[..., 0], int(g["Lp"]), g["prompt_language_arg"], g["text_language_arg"], top_k=1,
+                     max_new_tokens=24)
+    assert g["codes"].shape == (16 * len(g["x"]), 8)  # the 16*S cap (models/vallex.py:577)
+    assert np.array_equal(yy[0, 1 + y.shape[1]:].numpy(), g["codes"][:24, 0].astype(np.int64))
+
+
+def test_golden_edge_cases_present():
+    assert load_golden("noprompt_en")["prompt"].shape == (0, 8)       # no prompt: P = 0, Lp = 0
+    assert bool(load_golden("mixlang")["text_language_is_list"])      # per-token language list
+    for n in ("tiny_en", "noprompt_en", "mixlang", "mid_ja"):
+        g = load_golden(n)
+        assert g["codes"].shape[0] == 16 * len(g["x"])                # random weights never emit EOS -> cap
+        assert g["codes"].min() >= 0 and g["codes"].max() < 1024
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not present (GPU box)")
+def test_oracle_live_against_reference():
+    g = load_golden("noprompt_en")
+    sd = state_dict_for(g["seed"])
+    ref = ref_shim.load_reference_valle(sd)
+    x = torch.from_numpy(g["x"].astype(np.int64))[None]
+    y = torch.from_numpy(g["prompt"].astype(np.int64))[None]
+    with torch.no_grad():
+        want = ref.inference(x, torch.tensor([x.shape[1]]), y, enroll_x_lens=int(g["Lp"]), top_k=1, temperature=1.0,
+                             prompt_language=g["prompt_language_arg"], text_language=g["text_language_arg"])
+    got = _run(OracleVALLE(sd), g)
+    assert torch.equal(want, got)
+    # the synthetic checkpoint has exactly the reference's key set / shapes (strict load above) and its
+    # tied tensors stay tied
+    assert set(ref.state_dict().keys()) == set(sd.keys())

@@ -1,0 +1,916 @@
+// vallex_b200 engine: C ABI (include/vallex_b200.h), weight ingestion, workspaces and the host-side
+// orchestration of the AR prefill / AR decode / NAR / Vocos kernel sequences.  One engine per GPU.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/vallex_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace vx;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return fail(VX_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e) + " @" + std::to_string(__LINE__)); \
+  } while (0)
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = __float2bfloat16_rn(in[i]);
+}
+__global__ void write_cb0_kernel(Batch bt, const int32_t* __restrict__ cb0, const int32_t* __restrict__ tl, int Tmax) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (threadIdx.x == 0 && blockIdx.x == 0) bt.T[b] = tl[b];
+  if (t < tl[b]) bt.y[(size_t)b * bt.ymax + 1 + bt.P[b] + t] = cb0[(size_t)b * Tmax + t];
+}
+
+struct Weight {
+  std::vector<int64_t> shape;
+  float* f32 = nullptr;  // device fp32 (always present until finalize may drop it for bf16 matrices)
+  bf16* b16 = nullptr;   // device bf16 copy (bf16 mode, GEMM matrices only)
+  size_t numel = 0;
+};
+
+struct Buf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct LayerW {
+  const void *qkv_w, *out_w, *ff1_w, *ff2_w;
+  const float *qkv_b, *out_b, *ff1_b, *ff2_b, *n1_g, *n1_b, *n2_g, *n2_b;
+  const float *ada1, *ada2;  // [7][2048] (NAR only)
+};
+
+}  // namespace
+
+struct vx_engine {
+  int device = 0, max_batch = 0, max_ctx = 0, mode = 0;
+  cudaStream_t own_stream = nullptr;
+  std::map<std::string, Weight> w;
+  bool finalized = false, has_vocos = false, has_valle = false;
+  LayerW ar[kL], nar[kL];
+  const float *ar_norm_g = nullptr, *ar_norm_b = nullptr, *nar_norm_g = nullptr, *nar_norm_b = nullptr;
+  const float* nar_norm_ada = nullptr;  // [7][2048]
+  float* ada_all = nullptr;             // [25][7][2048]
+  const void* ar_predict = nullptr;
+  const void* nar_predict[7] = {};
+  EmbTables nar_emb{};
+  const float* pe = nullptr;
+  int pe_rows = 0;
+  float* dft_basis = nullptr;  // [1280][1296]
+
+  // batch state
+  bool batch_set = false, prefilled = false, decoded = false;
+  int B = 0, Smax = 0, Pmax = 0, ymax = 0;
+  std::vector<int> hS, hP, hT, h_ar_row0;
+  int ar_rows = 0, ar_maxlen = 0;
+  Batch bt{};
+  Buf d_text, d_lang, d_prompt, d_S, d_P, d_ar_row0, d_nar_row0, d_T, d_ctx, d_y, d_budget, d_fin, d_slp, d_nact;
+  Buf x, xn, qkv, att, ffh, kc, vc;                 // prefill / NAR activations, KV cache
+  Buf xs, xsn, qkvs, atts, ffs, logits, part, tick;  // decode-step scratch
+  Buf lastmap, out_tok, forced, yemb, yrow0, trow0, tgtmap, nlog, codes, tl_dev, cb0_dev;
+  Buf v_codes, v_feat, v_col, v_x, v_h, v_ff, v_head, v_spec, v_frames, v_wave;
+  int32_t* h_pinned = nullptr;  // small pinned scratch for polling
+  int ctx_cap = 0;
+  size_t kv_layer_elems = 0;
+
+  float ms_prefill = 0, ms_decode = 0, ms_nar = 0, ms_vocos = 0;
+  int64_t decode_steps = 0, launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+int ensure(Buf& b, size_t bytes) {
+  if (bytes <= b.cap) return VX_OK;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+  const size_t want = (bytes + 255) & ~size_t(255);
+  cudaError_t err = cudaMalloc(&b.p, want);
+  if (err != cudaSuccess) return fail(VX_ERR_CUDA, std::string("cudaMalloc ") + std::to_string(want) + ": " + cudaGetErrorString(err));
+  b.cap = want;
+  return VX_OK;
+}
+#define ENS(buf, bytes)                        \
+  do {                                         \
+    int _r = ensure(buf, (size_t)(bytes));     \
+    if (_r != VX_OK) return _r;                \
+  } while (0)
+
+int copy_in(void* dst, const void* src, size_t bytes, int mem, cudaStream_t st) {
+  if (bytes == 0) return VX_OK;
+  CK(cudaMemcpyAsync(dst, src, bytes, mem == VX_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
+  return VX_OK;
+}
+int copy_out(void* dst, const void* src, size_t bytes, int mem, cudaStream_t st) {
+  if (bytes == 0) return VX_OK;
+  CK(cudaMemcpyAsync(dst, src, bytes, mem == VX_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+  return VX_OK;
+}
+
+size_t kv_esize(const vx_engine* e) { return e->mode == VX_BF16 ? 2 : 4; }
+
+const Weight* findw(vx_engine* e, const std::string& k) {
+  auto it = e->w.find(k);
+  return it == e->w.end() ? nullptr : &it->second;
+}
+
+bool is_gemm_matrix(const std::string& k) {
+  auto ends = [&](const char* s) {
+    const size_t n = strlen(s);
+    return k.size() >= n && k.compare(k.size() - n, n, s) == 0;
+  };
+  if (k.rfind("vocos.", 0) == 0) return false;
+  if (ends("self_attn.in_proj_weight") || ends("self_attn.out_proj.weight") || ends("linear1.weight") ||
+      ends("linear2.weight"))
+    return true;
+  if (k == "ar_predict_layer.weight") return true;
+  if (k.rfind("nar_predict_layers.", 0) == 0) return true;
+  for (int j = 2; j < 8; ++j)
+    if (k == "nar_audio_embeddings." + std::to_string(j) + ".word_embeddings.weight") return true;
+  return false;
+}
+
+// matrix pointer in the engine's GEMM storage type
+const void* mat(vx_engine* e, const std::string& k) {
+  const Weight* w = findw(e, k);
+  if (!w) return nullptr;
+  return (e->mode == VX_BF16 && w->b16) ? (const void*)w->b16 : (const void*)w->f32;
+}
+const float* vec(vx_engine* e, const std::string& k) {
+  const Weight* w = findw(e, k);
+  return w ? w->f32 : nullptr;
+}
+
+struct Req {
+  std::string key;
+  std::vector<int64_t> shape;
+};
+
+std::vector<Req> required_keys() {
+  std::vector<Req> r;
+  auto add = [&](const std::string& k, std::vector<int64_t> s) { r.push_back({k, s}); };
+  add("ar_text_embedding.word_embeddings.weight", {kTextVocab, kD});
+  add("nar_text_embedding.word_embeddings.weight", {kTextVocab, kD});
+  add("ar_audio_embedding.word_embeddings.weight", {kVocab + 2, kD});
+  add("ar_text_position.alpha", {1});
+  add("ar_audio_position.alpha", {1});
+  add("nar_text_position.alpha", {1});
+  add("nar_audio_position.alpha", {1});
+  add("ar_decoder.norm.weight", {kD});
+  add("ar_decoder.norm.bias", {kD});
+  add("ar_predict_layer.weight", {kVocab + 1, kD});
+  add("ar_language_embedding.word_embeddings.weight", {3, kD});
+  add("nar_language_embedding.word_embeddings.weight", {3, kD});
+  add("nar_audio_embeddings.0.word_embeddings.weight", {kVocab + 1, kD});
+  for (int j = 1; j < kNQ; ++j) add("nar_audio_embeddings." + std::to_string(j) + ".word_embeddings.weight", {kVocab, kD});
+  for (int j = 0; j < kNQ - 1; ++j) {
+    add("nar_predict_layers." + std::to_string(j) + ".weight", {kVocab, kD});
+    add("nar_stage_embeddings." + std::to_string(j) + ".word_embeddings.weight", {1, kD});
+  }
+  for (int which = 0; which < 2; ++which) {
+    for (int i = 0; i < kL; ++i) {
+      const std::string p = std::string(which ? "nar" : "ar") + "_decoder.layers." + std::to_string(i);
+      add(p + ".self_attn.in_proj_weight", {3 * kD, kD});
+      add(p + ".self_attn.in_proj_bias", {3 * kD});
+      add(p + ".self_attn.out_proj.weight", {kD, kD});
+      add(p + ".self_attn.out_proj.bias", {kD});
+      add(p + ".linear1.weight", {kFF, kD});
+      add(p + ".linear1.bias", {kFF});
+      add(p + ".linear2.weight", {kD, kFF});
+      add(p + ".linear2.bias", {kD});
+      for (const char* n : {".norm1", ".norm2"}) {
+        if (which) {
+          add(p + n + ".project_layer.weight", {2 * kD, kD});
+          add(p + n + ".project_layer.bias", {2 * kD});
+          add(p + n + ".norm.weight", {kD});
+          add(p + n + ".norm.bias", {kD});
+        } else {
+          add(p + n + ".weight", {kD});
+          add(p + n + ".bias", {kD});
+        }
+      }
+    }
+  }
+  add("nar_decoder.norm.project_layer.weight", {2 * kD, kD});
+  add("nar_decoder.norm.project_layer.bias", {2 * kD});
+  add("nar_decoder.norm.norm.weight", {kD});
+  add("nar_decoder.norm.norm.bias", {kD});
+  return r;
+}
+
+std::vector<Req> vocos_keys() {
+  std::vector<Req> r;
+  auto add = [&](const std::string& k, std::vector<int64_t> s) { r.push_back({"vocos." + k, s}); };
+  add("feature_extractor.codebook_weights", {16 * 1024, 128});
+  add("backbone.embed.weight", {384, 128, 7});
+  add("backbone.embed.bias", {384});
+  add("backbone.norm.scale.weight", {4, 384});
+  add("backbone.norm.shift.weight", {4, 384});
+  for (int i = 0; i < 8; ++i) {
+    const std::string p = "backbone.convnext." + std::to_string(i);
+    add(p + ".dwconv.weight", {384, 1, 7});
+    add(p + ".dwconv.bias", {384});
+    add(p + ".norm.scale.weight", {4, 384});
+    add(p + ".norm.shift.weight", {4, 384});
+    add(p + ".pwconv1.weight", {1152, 384});
+    add(p + ".pwconv1.bias", {1152});
+    add(p + ".pwconv2.weight", {384, 1152});
+    add(p + ".pwconv2.bias", {384});
+    add(p + ".gamma", {384});
+  }
+  add("backbone.final_layer_norm.weight", {384});
+  add("backbone.final_layer_norm.bias", {384});
+  add("head.out.weight", {1282, 384});
+  add("head.out.bias", {1282});
+  add("head.istft.window", {1280});
+  return r;
+}
+
+cudaStream_t pick(vx_engine* e, void* stream) { return stream ? (cudaStream_t)stream : e->own_stream; }
+
+// C[M,N] = (LN?)(A) W^T + bias, choosing the GEMV (M<=8) or the tiled kernel.
+int linear(vx_engine* e, const float* A, int64_t lda, const void* W, int wt, const float* bias, float* C,
+           int64_t ldc, int64_t M, int N, int K, int epi, cudaStream_t st) {
+  if (M <= 8) launch_gemv(A, lda, W, wt, bias, C, ldc, (int)M, N, K, epi, nullptr, nullptr, st);
+  else launch_gemm(A, lda, W, wt, bias, C, ldc, M, N, K, epi, nullptr, st);
+  e->launches++;
+  return VX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vx_version(void) { return "vallex_b200 0.1 sm_100a"; }
+const char* vx_last_error(void) { return g_err.c_str(); }
+
+int vx_create(int device, int max_batch, int max_ctx, int dtype_mode, vx_engine** out) {
+  if (!out || max_batch < 1 || max_ctx < 8 || (dtype_mode != VX_F32 && dtype_mode != VX_BF16))
+    return fail(VX_ERR_ARG, "vx_create: bad arguments");
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(VX_ERR_ARG, "vx_create: no such CUDA device");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(VX_ERR_CUDA, "vx_create: this library only contains sm_100a code (B200 required)");
+  vx_engine* e = new vx_engine();
+  e->device = device;
+  e->max_batch = max_batch;
+  e->max_ctx = max_ctx;
+  e->mode = dtype_mode;
+  CK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&e->ev0));
+  CK(cudaEventCreate(&e->ev1));
+  CK(cudaMallocHost(&e->h_pinned, 4096));
+  *out = e;
+  return VX_OK;
+}
+
+void vx_destroy(vx_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : e->w) {
+    if (kv.second.f32) cudaFree(kv.second.f32);
+    if (kv.second.b16) cudaFree(kv.second.b16);
+  }
+  Buf* bufs[] = {&e->d_text, &e->d_lang, &e->d_prompt, &e->d_S, &e->d_P, &e->d_ar_row0, &e->d_nar_row0, &e->d_T,
+                 &e->d_ctx, &e->d_y, &e->d_budget, &e->d_fin, &e->d_slp, &e->d_nact, &e->x, &e->xn, &e->qkv, &e->att,
+                 &e->ffh, &e->kc, &e->vc, &e->xs, &e->xsn, &e->qkvs, &e->atts, &e->ffs, &e->logits, &e->part, &e->tick,
+                 &e->lastmap, &e->out_tok, &e->forced, &e->yemb, &e->yrow0, &e->trow0, &e->tgtmap, &e->nlog, &e->codes,
+                 &e->tl_dev, &e->cb0_dev, &e->v_codes, &e->v_feat, &e->v_col, &e->v_x, &e->v_h, &e->v_ff, &e->v_head,
+                 &e->v_spec, &e->v_frames, &e->v_wave};
+  for (Buf* b : bufs)
+    if (b->p) cudaFree(b->p);
+  if (e->ada_all) cudaFree(e->ada_all);
+  if (e->dft_basis) cudaFree(e->dft_basis);
+  if (e->h_pinned) cudaFreeHost(e->h_pinned);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  delete e;
+}
+
+int vx_load_weight(vx_engine* e, const char* key, const float* data, const int64_t* shape, int ndim) {
+  if (!e || !key || !data || !shape || ndim < 1 || ndim > 4) return fail(VX_ERR_ARG, "vx_load_weight: bad arguments");
+  CK(cudaSetDevice(e->device));
+  Weight wt;
+  wt.numel = 1;
+  for (int i = 0; i < ndim; ++i) {
+    wt.shape.push_back(shape[i]);
+    wt.numel *= (size_t)shape[i];
+  }
+  auto it = e->w.find(key);
+  if (it != e->w.end()) {
+    if (it->second.f32) cudaFree(it->second.f32);
+    if (it->second.b16) cudaFree(it->second.b16);
+    e->w.erase(it);
+  }
+  CK(cudaMalloc(&wt.f32, std::max<size_t>(wt.numel, 4) * sizeof(float)));
+  CK(cudaMemcpy(wt.f32, data, wt.numel * sizeof(float), cudaMemcpyHostToDevice));
+  e->w[key] = wt;
+  e->finalized = false;
+  return VX_OK;
+}
+
+int vx_finalize_weights(vx_engine* e) {
+  if (!e) return fail(VX_ERR_ARG, "vx_finalize_weights: null engine");
+  CK(cudaSetDevice(e->device));
+  cudaStream_t st = e->own_stream;
+  e->has_vocos = findw(e, "vocos.head.out.weight") != nullptr;
+  e->has_valle = false;
+  for (auto& kv : e->w)
+    if (kv.first.rfind("vocos.", 0) != 0 && kv.first != "pe_table") e->has_valle = true;
+  if (!e->has_valle && !e->has_vocos) return fail(VX_ERR_STATE, "vx_finalize_weights: no weights loaded");
+  if (e->has_valle) {
+    for (const Req& r : required_keys()) {
+      const Weight* w = findw(e, r.key);
+      if (!w) return fail(VX_ERR_STATE, "missing checkpoint key: " + r.key);
+      if (w->shape != r.shape) return fail(VX_ERR_ARG, "shape mismatch for checkpoint key: " + r.key);
+    }
+    const Weight* pe = findw(e, "pe_table");
+    if (!pe || pe->shape.size() != 2 || pe->shape[1] != kD) return fail(VX_ERR_STATE, "missing pe_table [rows,1024]");
+    e->pe = pe->f32;
+    e->pe_rows = (int)pe->shape[0];
+    if (e->pe_rows < e->max_ctx) return fail(VX_ERR_CAPACITY, "pe_table has fewer rows than max_ctx");
+  }
+  if (e->has_vocos)
+    for (const Req& r : vocos_keys()) {
+      const Weight* w = findw(e, r.key);
+      if (!w) return fail(VX_ERR_STATE, "missing checkpoint key: " + r.key);
+      if (w->shape != r.shape) return fail(VX_ERR_ARG, "shape mismatch for checkpoint key: " + r.key);
+    }
+
+  if (e->has_valle) {
+  // AdaLN (weight, bias) = project_layer(stage_embedding) for 25 norms x 7 stages, in fp32
+  // (modules/transformer.py:96-101).  Layout ada_all[norm][stage][2048].
+  if (!e->ada_all) CK(cudaMalloc(&e->ada_all, (size_t)25 * 7 * 2 * kD * sizeof(float)));
+  {
+    float* stage_rows = nullptr;  // [7][1024] gathered stage embeddings
+    CK(cudaMalloc(&stage_rows, 7 * kD * sizeof(float)));
+    for (int i = 0; i < 7; ++i)
+      CK(cudaMemcpyAsync(stage_rows + i * kD, vec(e, "nar_stage_embeddings." + std::to_string(i) + ".word_embeddings.weight"),
+                         kD * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    for (int n = 0; n < 25; ++n) {
+      std::string p = (n < 24) ? "nar_decoder.layers." + std::to_string(n / 2) + (n % 2 ? ".norm2" : ".norm1") : "nar_decoder.norm";
+      launch_gemv(stage_rows, kD, vec(e, p + ".project_layer.weight"), 0, vec(e, p + ".project_layer.bias"),
+                  e->ada_all + (size_t)n * 7 * 2 * kD, 2 * kD, 7, 2 * kD, kD, EPI_NONE, nullptr, nullptr, st);
+    }
+    CK(cudaStreamSynchronize(st));
+    CK(cudaFree(stage_rows));
+  }
+  // bf16 copies of the GEMM matrices (bf16 mode); the fp32 originals are released.
+  if (e->mode == VX_BF16) {
+    for (auto& kv : e->w) {
+      Weight& w = kv.second;
+      if (!is_gemm_matrix(kv.first) || w.b16) continue;
+      // tied tensors arrive under two keys with identical contents; each gets its own bf16 copy (6 MB total)
+      CK(cudaMalloc(&w.b16, w.numel * sizeof(bf16)));
+      f32_to_bf16_kernel<<<296, 256, 0, st>>>(w.f32, w.b16, w.numel);
+    }
+    CK(cudaStreamSynchronize(st));
+    for (auto& kv : e->w) {
+      Weight& w = kv.second;
+      if (w.b16 && w.f32) {
+        cudaFree(w.f32);
+        w.f32 = nullptr;
+      }
+    }
+  }
+  const int wt = e->mode;
+  (void)wt;
+  for (int which = 0; which < 2; ++which)
+    for (int i = 0; i < kL; ++i) {
+      const std::string p = std::string(which ? "nar" : "ar") + "_decoder.layers." + std::to_string(i);
+      LayerW& L = which ? e->nar[i] : e->ar[i];
+      L.qkv_w = mat(e, p + ".self_attn.in_proj_weight");
+      L.qkv_b = vec(e, p + ".self_attn.in_proj_bias");
+      L.out_w = mat(e, p + ".self_attn.out_proj.weight");
+      L.out_b = vec(e, p + ".self_attn.out_proj.bias");
+      L.ff1_w = mat(e, p + ".linear1.weight");
+      L.ff1_b = vec(e, p + ".linear1.bias");
+      L.ff2_w = mat(e, p + ".linear2.weight");
+      L.ff2_b = vec(e, p + ".linear2.bias");
+      if (which) {
+        L.n1_g = vec(e, p + ".norm1.norm.weight");
+        L.n1_b = vec(e, p + ".norm1.norm.bias");
+        L.n2_g = vec(e, p + ".norm2.norm.weight");
+        L.n2_b = vec(e, p + ".norm2.norm.bias");
+        L.ada1 = e->ada_all + (size_t)(2 * i) * 7 * 2 * kD;
+        L.ada2 = e->ada_all + (size_t)(2 * i + 1) * 7 * 2 * kD;
+      } else {
+        L.n1_g = vec(e, p + ".norm1.weight");
+        L.n1_b = vec(e, p + ".norm1.bias");
+        L.n2_g = vec(e, p + ".norm2.weight");
+        L.n2_b = vec(e, p + ".norm2.bias");
+        L.ada1 = L.ada2 = nullptr;
+      }
+    }
+  e->ar_norm_g = vec(e, "ar_decoder.norm.weight");
+  e->ar_norm_b = vec(e, "ar_decoder.norm.bias");
+  e->nar_norm_g = vec(e, "nar_decoder.norm.norm.weight");
+  e->nar_norm_b = vec(e, "nar_decoder.norm.norm.bias");
+  e->nar_norm_ada = e->ada_all + (size_t)24 * 7 * 2 * kD;
+  e->ar_predict = mat(e, "ar_predict_layer.weight");
+  for (int j = 0; j < 7; ++j) e->nar_predict[j] = mat(e, "nar_predict_layers." + std::to_string(j) + ".weight");
+  for (int j = 0; j < 8; ++j) {
+    const std::string k = "nar_audio_embeddings." + std::to_string(j) + ".word_embeddings.weight";
+    const Weight* w = findw(e, k);
+    e->nar_emb.bf[j] = (e->mode == VX_BF16 && w->b16) ? 1 : 0;
+    e->nar_emb.p[j] = e->nar_emb.bf[j] ? (const void*)w->b16 : (const void*)w->f32;
+  }
+  }
+  if (e->has_vocos && !e->dft_basis) {
+    // inverse real DFT as a contraction: frame[n] = sum_k spec_re[k]*Bc[n][k] + spec_im[k]*Bs[n][k]
+    // (torch.fft.irfft(n=1280, norm="backward"): imaginary parts of DC and Nyquist are ignored).
+    const int N = 1280, KB = 641, LD = 1296;
+    std::vector<float> h((size_t)N * LD, 0.f);
+    for (int n = 0; n < N; ++n)
+      for (int k = 0; k < KB; ++k) {
+        const double c = (k == 0 || k == KB - 1) ? 1.0 : 2.0;
+        const double ang = 2.0 * M_PI * (double)((int64_t)k * n % N) / (double)N;
+        h[(size_t)n * LD + k] = (float)(c * std::cos(ang) / N);
+        h[(size_t)n * LD + KB + k] = (k == 0 || k == KB - 1) ? 0.f : (float)(-c * std::sin(ang) / N);
+      }
+    CK(cudaMalloc(&e->dft_basis, h.size() * sizeof(float)));
+    CK(cudaMemcpy(e->dft_basis, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    // Conv1d(128->384,k=7) weight [co][ci][j] -> im2col layout [co][j*128+ci]
+    const Weight* cw = findw(e, "vocos.backbone.embed.weight");
+    std::vector<float> src(cw->numel), dst(cw->numel);
+    CK(cudaMemcpy(src.data(), cw->f32, cw->numel * sizeof(float), cudaMemcpyDeviceToHost));
+    for (int co = 0; co < 384; ++co)
+      for (int ci = 0; ci < 128; ++ci)
+        for (int j = 0; j < 7; ++j) dst[(size_t)co * 896 + j * 128 + ci] = src[((size_t)co * 128 + ci) * 7 + j];
+    Weight packed;
+    packed.shape = {384, 896};
+    packed.numel = cw->numel;
+    CK(cudaMalloc(&packed.f32, packed.numel * sizeof(float)));
+    CK(cudaMemcpy(packed.f32, dst.data(), packed.numel * sizeof(float), cudaMemcpyHostToDevice));
+    e->w["vocos.__embed_im2col"] = packed;
+  }
+  e->finalized = true;
+  return VX_OK;
+}
+
+int vx_set_batch(vx_engine* e, int B, const int32_t* text_ids, const int32_t* text_lens, const int32_t* lang_ids,
+                 int Smax, const int32_t* prompt_codes, const int32_t* prompt_lens, int Pmax, int mem, void* stream) {
+  if (!e || !e->finalized || !e->has_valle) return fail(VX_ERR_STATE, "vx_set_batch: VALL-E X weights not finalized");
+  if (B < 1 || B > e->max_batch || !text_ids || !text_lens || !lang_ids || !prompt_lens || Smax < 1 || Pmax < 0 ||
+      (Pmax > 0 && !prompt_codes))
+    return fail(VX_ERR_ARG, "vx_set_batch: bad arguments");
+  CK(cudaSetDevice(e->device));
+  cudaStream_t st = pick(e, stream);
+  e->hS.assign(B, 0);
+  e->hP.assign(B, 0);
+  if (mem == VX_HOST) {
+    for (int b = 0; b < B; ++b) { e->hS[b] = text_lens[b]; e->hP[b] = prompt_lens[b]; }
+  } else {
+    CK(cudaMemcpyAsync(e->hS.data(), text_lens, B * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(e->hP.data(), prompt_lens, B * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  e->h_ar_row0.assign(B, 0);
+  int rows = 0, maxlen = 0;
+  for (int b = 0; b < B; ++b) {
+    if (e->hS[b] < 1 || e->hS[b] > Smax) return fail(VX_ERR_ARG, "vx_set_batch: text_lens out of range (x_lens > 0 required, models/vallex.py:493)");
+    if (e->hP[b] < 0 || e->hP[b] > Pmax) return fail(VX_ERR_ARG, "vx_set_batch: prompt_lens out of range");
+    const int len = e->hS[b] + e->hP[b] + 1;
+    if (len >= e->max_ctx) return fail(VX_ERR_CAPACITY, "vx_set_batch: S+P+1 exceeds max_ctx");
+    e->h_ar_row0[b] = rows;
+    rows += len;
+    maxlen = std::max(maxlen, len);
+  }
+  e->B = B; e->Smax = Smax; e->Pmax = Pmax; e->ar_rows = rows; e->ar_maxlen = maxlen;
+  e->ymax = e->max_ctx + 1;
+  e->ctx_cap = e->max_ctx;
+  ENS(e->d_text, (size_t)B * Smax * 4);
+  ENS(e->d_lang, (size_t)B * Smax * 4);
+  ENS(e->d_prompt, (size_t)B * std::max(Pmax, 1) * kNQ * 4);
+  ENS(e->d_S, B * 4); ENS(e->d_P, B * 4); ENS(e->d_ar_row0, B * 4); ENS(e->d_nar_row0, B * 4);
+  ENS(e->d_T, B * 4); ENS(e->d_ctx, B * 4); ENS(e->d_budget, B * 4); ENS(e->d_fin, B * 4);
+  ENS(e->d_slp, B * 4); ENS(e->d_nact, 4);
+  ENS(e->d_y, (size_t)B * e->ymax * 4);
+  int r;
+  if ((r = copy_in(e->d_text.p, text_ids, (size_t)B * Smax * 4, mem, st))) return r;
+  if ((r = copy_in(e->d_lang.p, lang_ids, (size_t)B * Smax * 4, mem, st))) return r;
+  if (Pmax > 0 && (r = copy_in(e->d_prompt.p, prompt_codes, (size_t)B * Pmax * kNQ * 4, mem, st))) return r;
+  CK(cudaMemcpyAsync(e->d_S.p, e->hS.data(), B * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(e->d_P.p, e->hP.data(), B * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(e->d_ar_row0.p, e->h_ar_row0.data(), B * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));  // hS/hP/h_ar_row0 are reused by later calls
+  Batch& bt = e->bt;
+  bt.B = B; bt.Smax = Smax; bt.Pmax = std::max(Pmax, 1);
+  bt.text_ids = (const int32_t*)e->d_text.p; bt.lang_ids = (const int32_t*)e->d_lang.p;
+  bt.prompt = (const int32_t*)e->d_prompt.p;
+  bt.S = (const int32_t*)e->d_S.p; bt.P = (const int32_t*)e->d_P.p;
+  bt.ar_row0 = (const int32_t*)e->d_ar_row0.p; bt.nar_row0 = (const int32_t*)e->d_nar_row0.p;
+  bt.T = (int32_t*)e->d_T.p; bt.ctx = (int32_t*)e->d_ctx.p; bt.y = (int32_t*)e->d_y.p; bt.ymax = e->ymax;
+  bt.budget = (int32_t*)e->d_budget.p; bt.finished = (int32_t*)e->d_fin.p;
+  bt.sum_logprobs = (float*)e->d_slp.p; bt.n_active = (int32_t*)e->d_nact.p;
+  e->Pmax = Pmax;
+  e->batch_set = true; e->prefilled = false; e->decoded = false;
+  return VX_OK;
+}
+
+int vx_ar_prefill(vx_engine* e, void* stream) {
+  if (!e || !e->batch_set) return fail(VX_ERR_STATE, "vx_ar_prefill: no batch set");
+  CK(cudaSetDevice(e->device));
+  cudaStream_t st = pick(e, stream);
+  const int B = e->B, wt = e->mode;
+  const int64_t R = e->ar_rows;
+  const size_t kvb = kv_esize(e);
+  e->kv_layer_elems = (size_t)e->max_batch * kH * e->ctx_cap * kDH;
+  ENS(e->x, R * kD * 4); ENS(e->xn, R * kD * 4); ENS(e->qkv, R * 3 * kD * 4); ENS(e->att, R * kD * 4);
+  ENS(e->ffh, R * kFF * 4);
+  ENS(e->kc, e->kv_layer_elems * kL * kvb); ENS(e->vc, e->kv_layer_elems * kL * kvb);
+  ENS(e->xs, (size_t)B * kD * 4); ENS(e->xsn, (size_t)B * kD * 4); ENS(e->logits, (size_t)B * kARLogits * 4);
+  ENS(e->lastmap, B * 4);
+  CK(cudaEventRecord(e->ev0, st));
+  const Batch& bt = e->bt;
+  float* x = (float*)e->x.p; float* xn = (float*)e->xn.p; float* qkv = (float*)e->qkv.p;
+  float* att = (float*)e->att.p; float* ffh = (float*)e->ffh.p;
+  launch_init_y(bt, st);
+  launch_embed_text(bt, vec(e, "ar_text_embedding.word_embeddings.weight"), vec(e, "ar_language_embedding.word_embeddings.weight"),
+                    vec(e, "ar_text_position.alpha"), e->pe, bt.ar_row0, x, st);
+  launch_embed_audio_prefill(bt, vec(e, "ar_audio_embedding.word_embeddings.weight"), vec(e, "ar_audio_position.alpha"), e->pe, x, st);
+  e->launches += 3;
+  for (int l = 0; l < kL; ++l) {
+    const LayerW& L = e->ar[l];
+    launch_layernorm(x, nullptr, R, kD, L.n1_g, L.n1_b, nullptr, nullptr, 1e-5f, xn, st);
+    launch_gemm(xn, kD, L.qkv_w, wt, L.qkv_b, qkv, 3 * kD, R, 3 * kD, kD, EPI_NONE, nullptr, st);
+    launch_kv_scatter(bt, qkv, (char*)e->kc.p + (size_t)l * e->kv_layer_elems * kvb,
+                      (char*)e->vc.p + (size_t)l * e->kv_layer_elems * kvb, wt, e->ar_maxlen, e->ctx_cap, st);
+    launch_attn_full(bt, qkv, bt.ar_row0, 1, e->ar_maxlen, att, st);
+    launch_gemm(att, kD, L.out_w, wt, L.out_b, x, kD, R, kD, kD, EPI_RESIDUAL, nullptr, st);
+    launch_layernorm(x, nullptr, R, kD, L.n2_g, L.n2_b, nullptr, nullptr, 1e-5f, xn, st);
+    launch_gemm(xn, kD, L.ff1_w, wt, L.ff1_b, ffh, kFF, R, kFF, kD, EPI_RELU, nullptr, st);
+    launch_gemm(ffh, kFF, L.ff2_w, wt, L.ff2_b, x, kD, R, kD, kFF, EPI_RESIDUAL, nullptr, st);
+    e->launches += 8;
+  }
+  std::vector<int32_t> last(B);
+  for (int b = 0; b < B; ++b) last[b] = e->h_ar_row0[b] + e->hS[b] + e->hP[b];
+  memcpy(e->h_pinned, last.data(), B * 4);
+  CK(cudaMemcpyAsync(e->lastmap.p, e->h_pinned, B * 4, cudaMemcpyHostToDevice, st));
+  launch_layernorm(x, (const int32_t*)e->lastmap.p, B, kD, e->ar_norm_g, e->ar_norm_b, nullptr, nullptr, 1e-5f, (float*)e->xsn.p, st);
+  e->launches++;
+  linear(e, (float*)e->xsn.p, kD, e->ar_predict, wt, nullptr, (float*)e->logits.p, kARLogits, B, kARLogits, kD, EPI_NONE, st);
+  CK(cudaMemsetAsync(e->d_T.p, 0, B * 4, st));
+  CK(cudaMemsetAsync(e->d_fin.p, 0, B * 4, st));
+  CK(cudaMemsetAsync(e->d_slp.p, 0, B * 4, st));
+  CK(cudaEventRecord(e->ev1, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaEventElapsedTime(&e->ms_prefill, e->ev0, e->ev1));
+  CK(cudaGetLastError());
+  e->prefilled = true; e->decoded = false;
+  return VX_OK;
+}
+
+int vx_ar_budget(vx_engine* e, int max_new, int* out_max_steps) {
+  if (!e || !e->batch_set || !out_max_steps) return fail(VX_ERR_STATE, "vx_ar_budget: no batch set");
+  int m = 0;
+  for (int b = 0; b < e->B; ++b) {
+    int bud = 16 * e->hS[b];  // models/vallex.py:577
+    if (max_new > 0) bud = std::min(bud, max_new);
+    bud = std::min(bud, e->max_ctx - (e->hS[b] + e->hP[b] + 1) - 1);
+    m = std::max(m, bud);
+  }
+  *out_max_steps = m;
+  return VX_OK;
+}
+
+// One decode forward pass for the tokens just appended (all utterances at once).
+static int decode_forward(vx_engine* e, int nsplit, cudaStream_t st) {
+  const Batch& bt = e->bt;
+  const int B = e->B, wt = e->mode;
+  const size_t kvb = kv_esize(e);
+  float* xs = (float*)e->xs.p; float* xsn = (float*)e->xsn.p; float* qkvs = (float*)e->qkvs.p;
+  float* atts = (float*)e->atts.p; float* ffs = (float*)e->ffs.p;
+  launch_embed_audio_step(bt, vec(e, "ar_audio_embedding.word_embeddings.weight"), vec(e, "ar_audio_position.alpha"), e->pe, xs, st);
+  e->launches++;
+  const bool small = B <= 8;
+  for (int l = 0; l < kL; ++l) {
+    const LayerW& L = e->ar[l];
+    if (small) {
+      launch_gemv(xs, kD, L.qkv_w, wt, L.qkv_b, qkvs, 3 * kD, B, 3 * kD, kD, EPI_NONE, L.n1_g, L.n1_b, st);
+      e->launches++;
+    } else {
+      launch_layernorm(xs, nullptr, B, kD, L.n1_g, L.n1_b, nullptr, nullptr, 1e-5f, xsn, st);
+      launch_gemm(xsn, kD, L.qkv_w, wt, L.qkv_b, qkvs, 3 * kD, B, 3 * kD, kD, EPI_NONE, nullptr, st);
+      e->launches += 2;
+    }
+    launch_attn_decode(bt, qkvs, (char*)e->kc.p + (size_t)l * e->kv_layer_elems * kvb,
+                       (char*)e->vc.p + (size_t)l * e->kv_layer_elems * kvb, wt, e->ctx_cap, atts, (float*)e->part.p,
+                       (int32_t*)e->tick.p, nsplit, st);
+    e->launches++;
+    linear(e, atts, kD, L.out_w, wt, L.out_b, xs, kD, B, kD, kD, EPI_RESIDUAL, st);
+    if (small) {
+      launch_gemv(xs, kD, L.ff1_w, wt, L.ff1_b, ffs, kFF, B, kFF, kD, EPI_RELU, L.n2_g, L.n2_b, st);
+      e->launches++;
+    } else {
+      launch_layernorm(xs, nullptr, B, kD, L.n2_g, L.n2_b, nullptr, nullptr, 1e-5f, xsn, st);
+      launch_gemm(xsn, kD, L.ff1_w, wt, L.ff1_b, ffs, kFF, B, kFF, kD, EPI_RELU, nullptr, st);
+      e->launches += 2;
+    }
+    linear(e, ffs, kFF, L.ff2_w, wt, L.ff2_b, xs, kD, B, kD, kFF, EPI_RESIDUAL, st);
+  }
+  if (small) {
+    launch_gemv(xs, kD, e->ar_predict, wt, nullptr, (float*)e->logits.p, kARLogits, B, kARLogits, kD, EPI_NONE,
+                e->ar_norm_g, e->ar_norm_b, st);
+    e->launches++;
+  } else {
+    launch_layernorm(xs, nullptr, B, kD, e->ar_norm_g, e->ar_norm_b, nullptr, nullptr, 1e-5f, xsn, st);
+    launch_gemm(xsn, kD, e->ar_predict, wt, nullptr, (float*)e->logits.p, kARLogits, B, kARLogits, kD, EPI_NONE, nullptr, st);
+    e->launches += 2;
+  }
+  return VX_OK;
+}
+
+int vx_ar_decode(vx_engine* e, int max_new, int top_k, float top_p, float temperature, uint64_t seed, int ignore_eos,
+                 const int32_t* forced_tokens, int32_t* out_tokens, int32_t* out_lens, float* out_sum_logprobs, int mem,
+                 void* stream) {
+  if (!e || !e->prefilled) return fail(VX_ERR_STATE, "vx_ar_decode: call vx_ar_prefill first");
+  if (!(temperature > 0.f)) return fail(VX_ERR_ARG, "vx_ar_decode: temperature must be > 0");
+  CK(cudaSetDevice(e->device));
+  cudaStream_t st = pick(e, stream);
+  const int B = e->B;
+  int max_steps = 0;
+  vx_ar_budget(e, max_new, &max_steps);
+  if (max_steps < 1) return fail(VX_ERR_CAPACITY, "vx_ar_decode: no room for new tokens (max_ctx too small)");
+  std::vector<int32_t> bud(B);
+  int final_ctx = 0;
+  for (int b = 0; b < B; ++b) {
+    int v = 16 * e->hS[b];
+    if (max_new > 0) v = std::min(v, max_new);
+    v = std::min(v, e->max_ctx - (e->hS[b] + e->hP[b] + 1) - 1);
+    bud[b] = v;
+    final_ctx = std::max(final_ctx, e->hS[b] + e->hP[b] + 1 + v);
+  }
+  int nsplit = std::max(1, (2 * kSMs + B * kH - 1) / (B * kH));
+  nsplit = std::max(nsplit, (final_ctx + 2047) / 2048);
+  nsplit = std::min(nsplit, 64);
+  ENS(e->qkvs, (size_t)B * 3 * kD * 4); ENS(e->atts, (size_t)B * kD * 4); ENS(e->ffs, (size_t)B * kFF * 4);
+  ENS(e->part, (size_t)B * kH * nsplit * (kDH + 2) * 4); ENS(e->tick, (size_t)B * kH * 4);
+  ENS(e->out_tok, (size_t)B * max_steps * 4);
+  if (forced_tokens) {
+    ENS(e->forced, (size_t)B * max_steps * 4);
+    int r = copy_in(e->forced.p, forced_tokens, (size_t)B * max_steps * 4, mem, st);
+    if (r) return r;
+  }
+  memcpy(e->h_pinned, bud.data(), B * 4);
+  e->h_pinned[B] = B;
+  CK(cudaMemcpyAsync(e->d_budget.p, e->h_pinned, B * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(e->d_nact.p, e->h_pinned + B, 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(e->tick.p, 0, (size_t)B * kH * 4, st));
+  CK(cudaMemsetAsync(e->out_tok.p, 0, (size_t)B * max_steps * 4, st));
+  CK(cudaStreamSynchronize(st));  // h_pinned reused below
+  const int32_t* forced_dev = forced_tokens ? (const int32_t*)e->forced.p : nullptr;
+
+  // capture one iteration [sample -> forward] into a CUDA graph; kernels read all step state from the device
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  const int64_t launches_before = e->launches;
+  CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  launch_sample(e->bt, (const float*)e->logits.p, top_k, top_p, temperature, seed, 0, ignore_eos, forced_dev, max_steps,
+                (int32_t*)e->out_tok.p, max_steps, st);
+  e->launches++;
+  decode_forward(e, nsplit, st);
+  CK(cudaStreamEndCapture(st, &graph));
+  CK(cudaGraphInstantiate(&exec, graph, 0));
+  const int64_t per_iter = e->launches - launches_before;
+  e->launches = launches_before;
+
+  CK(cudaEventRecord(e->ev0, st));
+  int steps = 0;
+  const bool can_stop_early = !ignore_eos;
+  for (int s = 0; s < max_steps; ++s) {
+    if (s == max_steps - 1) {  // last token: sample only, the forward pass would be discarded
+      launch_sample(e->bt, (const float*)e->logits.p, top_k, top_p, temperature, seed, 0, ignore_eos, forced_dev,
+                    max_steps, (int32_t*)e->out_tok.p, max_steps, st);
+      e->launches++;
+      steps++;
+      break;
+    }
+    CK(cudaGraphLaunch(exec, st));
+    e->launches += per_iter;
+    steps++;
+    if (can_stop_early && (s % 32) == 31) {
+      CK(cudaMemcpyAsync(e->h_pinned, e->d_nact.p, 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if (e->h_pinned[0] <= 0) break;
+    }
+  }
+  CK(cudaEventRecord(e->ev1, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaEventElapsedTime(&e->ms_decode, e->ev0, e->ev1));
+  e->decode_steps = steps;
+  CK(cudaGraphExecDestroy(exec));
+  CK(cudaGraphDestroy(graph));
+  CK(cudaGetLastError());
+  int r;
+  if (out_tokens && (r = copy_out(out_tokens, e->out_tok.p, (size_t)B * max_steps * 4, mem, st))) return r;
+  if (out_lens && (r = copy_out(out_lens, e->d_T.p, B * 4, mem, st))) return r;
+  if (out_sum_logprobs && (r = copy_out(out_sum_logprobs, e->d_slp.p, B * 4, mem, st))) return r;
+  e->hT.assign(B, 0);
+  CK(cudaMemcpyAsync(e->hT.data(), e->d_T.p, B * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  e->decoded = true;
+  return VX_OK;
+}
+
+int vx_nar(vx_engine* e, const int32_t* cb0, const int32_t* t_lens, int Tmax, int32_t* out_codes, int mem,
+           void* stream) {
+  if (!e || !e->batch_set) return fail(VX_ERR_STATE, "vx_nar: no batch set");
+  if (!out_codes || Tmax < 0) return fail(VX_ERR_ARG, "vx_nar: bad arguments");
+  CK(cudaSetDevice(e->device));
+  cudaStream_t st = pick(e, stream);
+  const int B = e->B, wt = e->mode;
+  const Batch& bt = e->bt;
+  if (cb0) {
+    if (!t_lens) return fail(VX_ERR_ARG, "vx_nar: t_lens required with cb0");
+    ENS(e->tl_dev, B * 4); ENS(e->cb0_dev, (size_t)B * std::max(Tmax, 1) * 4);
+    int r;
+    if ((r = copy_in(e->tl_dev.p, t_lens, B * 4, mem, st))) return r;
+    if ((r = copy_in(e->cb0_dev.p, cb0, (size_t)B * Tmax * 4, mem, st))) return r;
+    e->hT.assign(B, 0);
+    CK(cudaMemcpyAsync(e->hT.data(), e->tl_dev.p, B * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int b = 0; b < B; ++b)
+      if (e->hT[b] < 0 || e->hT[b] > Tmax || e->hS[b] + e->hP[b] + e->hT[b] + 1 > e->max_ctx)
+        return fail(VX_ERR_CAPACITY, "vx_nar: t_lens out of range for max_ctx");
+    launch_init_y(bt, st);
+    if (Tmax > 0) write_cb0_kernel<<<dim3((Tmax + 255) / 256, B), 256, 0, st>>>(bt, (const int32_t*)e->cb0_dev.p, (const int32_t*)e->tl_dev.p, Tmax);
+    else CK(cudaMemsetAsync(e->d_T.p, 0, B * 4, st));
+    e->launches += 2;
+  } else if (!e->decoded) {
+    return fail(VX_ERR_STATE, "vx_nar: no codebook-0 tokens (pass cb0 or run vx_ar_decode)");
+  }
+  std::vector<int32_t> nrow0(B), yrow0(B), trow0(B);
+  int64_t R = 0, YR = 0, TR = 0;
+  int maxlen = 0, maxpt = 0, maxT = 0;
+  for (int b = 0; b < B; ++b) {
+    if (e->hT[b] > Tmax) return fail(VX_ERR_ARG, "vx_nar: Tmax smaller than a generated length");
+    nrow0[b] = (int32_t)R; yrow0[b] = (int32_t)YR; trow0[b] = (int32_t)TR;
+    const int pt = e->hP[b] + e->hT[b];
+    R += e->hS[b] + pt; YR += pt; TR += e->hT[b];
+    maxlen = std::max(maxlen, e->hS[b] + pt); maxpt = std::max(maxpt, pt); maxT = std::max(maxT, e->hT[b]);
+  }
+  std::vector<int32_t> tgt((size_t)std::max<int64_t>(TR, 1));
+  for (int b = 0; b < B; ++b)
+    for (int t = 0; t < e->hT[b]; ++t) tgt[trow0[b] + t] = nrow0[b] + e->hS[b] + e->hP[b] + t;
+  ENS(e->yrow0, B * 4); ENS(e->trow0, B * 4); ENS(e->tgtmap, tgt.size() * 4);
+  CK(cudaMemcpyAsync(e->d_nar_row0.p, nrow0.data(), B * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(e->yrow0.p, yrow0.data(), B * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(e->trow0.p, trow0.data(), B * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(e->tgtmap.p, tgt.data(), tgt.size() * 4, cudaMemcpyHostToDevice, st));
+  ENS(e->x, R * kD * 4); ENS(e->xn, R * kD * 4); ENS(e->qkv, R * 3 * kD * 4); ENS(e->att, R * kD * 4);
+  ENS(e->ffh, R * kFF * 4);
+  ENS(e->yemb, std::max<int64_t>(YR, 1) * kD * 4); ENS(e->nlog, std::max<int64_t>(TR, 1) * kVocab * 4);
+  ENS(e->codes, (size_t)B * std::max(Tmax, 1) * kNQ * 4);
+  CK(cudaStreamSynchronize(st));  // host vectors above go out of scope; x/xn may have been reallocated
+  CK(cudaEventRecord(e->ev0, st));
+  float* x = (float*)e->x.p; float* xn = (float*)e->xn.p; float* qkv = (float*)e->qkv.p;
+  float* att = (float*)e->att.p; float* ffh = (float*)e->ffh.p; float* yemb = (float*)e->yemb.p;
+  const int32_t* d_yrow0 = (const int32_t*)e->yrow0.p; const int32_t* d_trow0 = (const int32_t*)e->trow0.p;
+  CK(cudaMemsetAsync(e->codes.p, 0, (size_t)B * std::max(Tmax, 1) * kNQ * 4, st));
+  launch_nar_copy_cb0(bt, (int32_t*)e->codes.p, Tmax, st);
+  launch_nar_embed_init(bt, e->nar_emb, yemb, d_yrow0, maxpt, st);
+  e->launches += 2;
+  if (TR > 0) {
+    for (int stage = 0; stage < kNQ - 1; ++stage) {
+      launch_embed_text(bt, vec(e, "nar_text_embedding.word_embeddings.weight"), vec(e, "nar_language_embedding.word_embeddings.weight"),
+                        vec(e, "nar_text_position.alpha"), e->pe, bt.nar_row0, x, st);
+      launch_nar_build_x(bt, yemb, d_yrow0, vec(e, "nar_audio_position.alpha"), e->pe, x, maxpt, st);
+      e->launches += 2;
+      for (int l = 0; l < kL; ++l) {
+        const LayerW& L = e->nar[l];
+        const float* a1 = L.ada1 + (size_t)stage * 2 * kD;
+        const float* a2 = L.ada2 + (size_t)stage * 2 * kD;
+        launch_layernorm(x, nullptr, R, kD, L.n1_g, L.n1_b, a1, a1 + kD, 1e-5f, xn, st);
+        launch_gemm(xn, kD, L.qkv_w, wt, L.qkv_b, qkv, 3 * kD, R, 3 * kD, kD, EPI_NONE, nullptr, st);
+        launch_attn_full(bt, qkv, bt.nar_row0, 0, maxlen, att, st);
+        launch_gemm(att, kD, L.out_w, wt, L.out_b, x, kD, R, kD, kD, EPI_RESIDUAL, nullptr, st);
+        launch_layernorm(x, nullptr, R, kD, L.n2_g, L.n2_b, a2, a2 + kD, 1e-5f, xn, st);
+        launch_gemm(xn, kD, L.ff1_w, wt, L.ff1_b, ffh, kFF, R, kFF, kD, EPI_RELU, nullptr, st);
+        launch_gemm(ffh, kFF, L.ff2_w, wt, L.ff2_b, x, kD, R, kD, kFF, EPI_RESIDUAL, nullptr, st);
+        e->launches += 7;
+      }
+      const float* af = e->nar_norm_ada + (size_t)stage * 2 * kD;
+      launch_layernorm(x, (const int32_t*)e->tgtmap.p, TR, kD, e->nar_norm_g, e->nar_norm_b, af, af + kD, 1e-5f, xn, st);
+      e->launches++;
+      linear(e, xn, kD, e->nar_predict[stage], wt, nullptr, (float*)e->nlog.p, kVocab, TR, kVocab, kD, EPI_NONE, st);
+      launch_nar_argmax_update(bt, (const float*)e->nlog.p, d_trow0, stage, e->nar_emb, yemb, d_yrow0,
+                               (int32_t*)e->codes.p, Tmax, st);
+      e->launches++;
+    }
+  }
+  CK(cudaEventRecord(e->ev1, st));
+  int r;
+  if ((r = copy_out(out_codes, e->codes.p, (size_t)B * Tmax * kNQ * 4, mem, st))) return r;
+  CK(cudaStreamSynchronize(st));
+  CK(cudaEventElapsedTime(&e->ms_nar, e->ev0, e->ev1));
+  CK(cudaGetLastError());
+  return VX_OK;
+}
+
+int vx_vocos_decode(vx_engine* e, const int32_t* codes, int B, int T, int bandwidth_id, float* wave, int mem,
+                    void* stream) {
+  if (!e || !e->finalized || !e->has_vocos) return fail(VX_ERR_STATE, "vx_vocos_decode: Vocos weights not loaded");
+  if (!codes || !wave || B < 1 || T < 1 || bandwidth_id < 0 || bandwidth_id > 3) return fail(VX_ERR_ARG, "vx_vocos_decode: bad arguments");
+  CK(cudaSetDevice(e->device));
+  cudaStream_t st = pick(e, stream);
+  const int64_t R = (int64_t)B * T;
+  ENS(e->v_codes, (size_t)kNQ * R * 4); ENS(e->v_feat, R * 128 * 4); ENS(e->v_col, R * 896 * 4);
+  ENS(e->v_x, R * 384 * 4); ENS(e->v_h, R * 384 * 4); ENS(e->v_ff, R * 1152 * 4); ENS(e->v_head, R * 1282 * 4);
+  ENS(e->v_spec, R * 1296 * 4); ENS(e->v_frames, R * 1280 * 4); ENS(e->v_wave, R * 320 * 4);
+  CK(cudaEventRecord(e->ev0, st));
+  int r;
+  if ((r = copy_in(e->v_codes.p, codes, (size_t)kNQ * R * 4, mem, st))) return r;
+  auto V = [&](const std::string& k) { return vec(e, "vocos." + k); };
+  float* feat = (float*)e->v_feat.p; float* col = (float*)e->v_col.p; float* x = (float*)e->v_x.p;
+  float* h = (float*)e->v_h.p; float* ff = (float*)e->v_ff.p; float* head = (float*)e->v_head.p;
+  float* spec = (float*)e->v_spec.p; float* frames = (float*)e->v_frames.p; float* wv = (float*)e->v_wave.p;
+  launch_vocos_features((const int32_t*)e->v_codes.p, B, T, V("feature_extractor.codebook_weights"), feat, st);
+  launch_vocos_im2col7(feat, B, T, 128, col, st);
+  launch_gemm(col, 896, V("__embed_im2col"), 0, V("backbone.embed.bias"), x, 384, R, 384, 896, EPI_NONE, nullptr, st);
+  launch_layernorm(x, nullptr, R, 384, nullptr, nullptr, V("backbone.norm.scale.weight") + bandwidth_id * 384,
+                   V("backbone.norm.shift.weight") + bandwidth_id * 384, 1e-6f, x, st);
+  e->launches += 4;
+  for (int i = 0; i < 8; ++i) {
+    const std::string p = "backbone.convnext." + std::to_string(i);
+    launch_vocos_dwconv7(x, B, T, 384, V(p + ".dwconv.weight"), V(p + ".dwconv.bias"), h, st);
+    launch_layernorm(h, nullptr, R, 384, nullptr, nullptr, V(p + ".norm.scale.weight") + bandwidth_id * 384,
+                     V(p + ".norm.shift.weight") + bandwidth_id * 384, 1e-6f, h, st);
+    launch_gemm(h, 384, V(p + ".pwconv1.weight"), 0, V(p + ".pwconv1.bias"), ff, 1152, R, 1152, 384, EPI_GELU, nullptr, st);
+    launch_gemm(ff, 1152, V(p + ".pwconv2.weight"), 0, V(p + ".pwconv2.bias"), x, 384, R, 384, 1152, EPI_SCALE_RESIDUAL,
+                V(p + ".gamma"), st);
+    e->launches += 4;
+  }
+  launch_layernorm(x, nullptr, R, 384, V("backbone.final_layer_norm.weight"), V("backbone.final_layer_norm.bias"), nullptr,
+                   nullptr, 1e-6f, h, st);
+  launch_gemm(h, 384, V("head.out.weight"), 0, V("head.out.bias"), head, 1282, R, 1282, 384, EPI_NONE, nullptr, st);
+  launch_vocos_spectrum(head, R, spec, 1296, st);
+  launch_gemm(spec, 1296, e->dft_basis, 0, nullptr, frames, 1280, R, 1280, 1296, EPI_NONE, nullptr, st);
+  launch_vocos_overlap_add(frames, B, T, V("head.istft.window"), wv, st);
+  e->launches += 5;
+  if ((r = copy_out(wave, wv, (size_t)R * 320 * 4, mem, st))) return r;
+  CK(cudaEventRecord(e->ev1, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaEventElapsedTime(&e->ms_vocos, e->ev0, e->ev1));
+  CK(cudaGetLastError());
+  return VX_OK;
+}
+
+int vx_last_timing(vx_engine* e, float* ms_prefill, float* ms_decode, float* ms_nar, float* ms_vocos,
+                   int64_t* decode_steps, int64_t* kernel_launches) {
+  if (!e) return fail(VX_ERR_ARG, "vx_last_timing: null engine");
+  if (ms_prefill) *ms_prefill = e->ms_prefill;
+  if (ms_decode) *ms_decode = e->ms_decode;
+  if (ms_nar) *ms_nar = e->ms_nar;
+  if (ms_vocos) *ms_vocos = e->ms_vocos;
+  if (decode_steps) *decode_steps = e->decode_steps;
+  if (kernel_launches) *kernel_launches = e->launches;
+  return VX_OK;
+}
+
+int vx_debug_read(vx_engine* e, const char* what, float* dst, int64_t max_elems, int64_t* out_elems) {
+  if (!e || !what || !dst) return fail(VX_ERR_ARG, "vx_debug_read: bad arguments");
+  CK(cudaSetDevice(e->device));
+  const std::string k(what);
+  const void* src = nullptr;
+  int64_t n = 0;
+  if (k == "ar_logits") { src = e->logits.p; n = (int64_t)e->B * kARLogits; }
+  else if (k == "nar_logits") { src = e->nlog.p; int64_t tr = 0; for (int t : e->hT) tr += t; n = tr * kVocab; }
+  else if (k == "ar_prefill_x") { src = e->x.p; n = (int64_t)e->ar_rows * kD; }
+  else if (k == "ada_all") { src = e->ada_all; n = 25 * 7 * 2 * kD; }
+  else return fail(VX_ERR_ARG, "vx_debug_read: unknown item " + k);
+  if (!src) return fail(VX_ERR_STATE, "vx_debug_read: item not available yet");
+  n = std::min(n, max_elems);
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(dst, src, n * sizeof(float), cudaMemcpyDeviceToHost));
+  if (out_elems) *out_elems = n;
+  return VX_OK;
+}
+
+}  // extern "C"

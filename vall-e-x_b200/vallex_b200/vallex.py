@@ -1,0 +1,154 @@
+"""Drop-in for the reference's `models.vallex.VALLE` inference surface (models/vallex.py:400-686),
+backed by the B200 engine.  Same constructor call (utils/generation.py:67-78), `load_state_dict`
+with the reference's 374 checkpoint keys, `.eval()`, `.to(device)` and
+`.inference(x, x_lens, y, enroll_x_lens, top_k, temperature, prompt_language, text_language,
+best_of, length_penalty, return_worst) -> LongTensor[1,T,8]`, same asserts and error types.
+`forward` raises NotImplementedError exactly like the reference (models/vallex.py:447-457).
+"""
+from __future__ import annotations
+
+from collections import namedtuple
+from typing import Dict, List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from .engine import Engine
+from .macros import LANGUAGE_ID, N_DIM, NUM_AUDIO_TOKENS, NUM_HEAD, NUM_LAYERS, NUM_QUANTIZERS
+
+_IncompatibleKeys = namedtuple("_IncompatibleKeys", ["missing_keys", "unexpected_keys"])
+
+
+def _device_index(device) -> int:
+    d = torch.device(device) if not isinstance(device, torch.device) else device
+    if d.type != "cuda":
+        raise RuntimeError("vallex_b200 runs on CUDA (B200, sm_100a) only; there is no CPU path")
+    return 0 if d.index is None else d.index
+
+
+class VALLE:
+    def __init__(self, d_model: int, nhead: int, num_layers: int, norm_first: bool = True, add_prenet: bool = False,
+                 prefix_mode: int = 0, share_embedding: bool = True, nar_scale_factor: float = 1.0,
+                 prepend_bos: bool = True, num_quantizers: int = 8, *, dtype: str = "bf16", max_batch: int = 8,
+                 max_ctx: int = 6144, **kwargs):
+        cfg = (d_model, nhead, num_layers, norm_first, add_prenet, prefix_mode, share_embedding, nar_scale_factor,
+               prepend_bos, num_quantizers)
+        if cfg != (N_DIM, NUM_HEAD, NUM_LAYERS, True, False, 1, True, 1.0, True, NUM_QUANTIZERS):
+            raise NotImplementedError(
+                "the B200 engine implements the released VALL-E X configuration only "
+                "(utils/generation.py:67-78): VALLE(1024, 16, 12, norm_first=True, add_prenet=False, "
+                f"prefix_mode=1, share_embedding=True, nar_scale_factor=1.0, prepend_bos=True, num_quantizers=8); got {cfg}")
+        self.language_ID = dict(LANGUAGE_ID)
+        self.num_quantizers = num_quantizers
+        self.prefix_mode = prefix_mode
+        self._dtype, self._max_batch, self._max_ctx = dtype, max_batch, max_ctx
+        self._device = 0
+        self._sd: Optional[Dict[str, torch.Tensor]] = None
+        self._engine: Optional[Engine] = None
+        self.last_timing: dict = {}
+
+    # -- nn.Module-like surface ----------------------------------------------------------------
+    def load_state_dict(self, state_dict, strict: bool = True):
+        self._sd = {k: v for k, v in state_dict.items()}
+        if self._engine is not None:
+            self._engine.close()
+            self._engine = None
+        return _IncompatibleKeys([], [])
+
+    def eval(self):
+        return self
+
+    def to(self, device):
+        idx = _device_index(device)
+        if self._engine is not None and idx != self._device:
+            self._engine.close()
+            self._engine = None
+        self._device = idx
+        return self
+
+    def cuda(self, device=0):
+        return self.to(torch.device("cuda", device))
+
+    def forward(self, *args, **kwargs):
+        raise NotImplementedError
+
+    __call__ = forward
+
+    @property
+    def engine(self) -> Engine:
+        if self._engine is None:
+            if self._sd is None:
+                raise RuntimeError("load_state_dict() must be called before inference")
+            eng = Engine(self._device, self._max_batch, self._max_ctx, self._dtype)
+            eng.load_valle_state_dict(self._sd)  # strict: vx_finalize_weights rejects missing keys / bad shapes
+            vs = getattr(self, "_vocos_sd", None)
+            if vs is not None:
+                eng.load_vocos_state_dict(vs)
+            eng.finalize()
+            self._engine = eng
+        return self._engine
+
+    def attach_vocos(self, vocos_state_dict):
+        """Share this model's engine with the Vocos decoder (one engine per GPU)."""
+        self._vocos_sd = vocos_state_dict
+        if self._engine is not None:
+            self._engine.load_vocos_state_dict(vocos_state_dict)
+            self._engine.finalize()
+
+    # -- inference -----------------------------------------------------------------------------
+    def _lang_ids(self, S: int, Lp: int, prompt_language: str, text_language: Union[str, Sequence[str]]) -> np.ndarray:
+        ids = np.empty((S,), np.int32)
+        ids[:Lp] = self.language_ID[prompt_language]
+        if isinstance(text_language, str):
+            ids[Lp:] = self.language_ID[text_language]
+        else:
+            tl = [self.language_ID[t] for t in text_language]
+            if len(tl) == 1:
+                ids[Lp:] = tl[0]
+            else:
+                if len(tl) != S - Lp:  # the reference's broadcast would raise here too (models/vallex.py:505)
+                    raise RuntimeError(f"text_language has {len(tl)} entries for {S - Lp} text tokens")
+                ids[Lp:] = tl
+        return ids
+
+    def inference(self, x: torch.Tensor, x_lens: torch.Tensor, y: torch.Tensor, enroll_x_lens, top_k: int = -100,
+                  temperature: float = 1.0, prompt_language: str = None, text_language=None, best_of: int = 1,
+                  length_penalty: float = 1.0, return_worst: bool = False, *, max_new_tokens: int = 0,
+                  seed: int = 0, quiet: bool = False) -> torch.Tensor:
+        """models/vallex.py:458-686.  `max_new_tokens`, `seed`, `quiet` are engine extensions (keyword-only)."""
+        assert x.ndim == 2, x.shape
+        assert x_lens.ndim == 1, x_lens.shape
+        assert y.ndim == 3, y.shape
+        assert y.shape[0] == 1, y.shape
+        assert torch.all(x_lens > 0)
+        S = int(x_lens.max())
+        Lp = int(enroll_x_lens)
+        P = int(y.shape[1])
+        text = x[0, :S].detach().to("cpu").numpy().astype(np.int32)
+        prompt = y[0].detach().to("cpu").numpy().astype(np.int32).reshape(P, NUM_QUANTIZERS)
+        lang = self._lang_ids(S, Lp, prompt_language, text_language)
+        eng = self.engine
+        nb = int(best_of)
+        eng.set_batch([text] * nb, [lang] * nb, [prompt] * nb)
+        eng.ar_prefill()
+        t_pre = eng.timing()["ms_prefill"]
+        toks, lens, slp = eng.ar_decode(max_new=max_new_tokens, top_k=top_k, top_p=1.0, temperature=temperature, seed=seed)
+        if int(lens.max()) == 0 and P + 1 == P:  # unreachable with prepend_bos (models/vallex.py:579-582)
+            raise SyntaxError("well trained model shouldn't reach here.")
+        # choose the best / worst beam by sum_logprobs / len**length_penalty (models/vallex.py:583-594);
+        # len counts BOS + prompt + generated non-EOS tokens
+        length = (1 + P + lens).astype(np.float64)
+        avg = slp.astype(np.float64) / length ** length_penalty
+        pick = int(np.argmin(avg) if return_worst else np.argmax(avg))
+        T = int(lens[pick])
+        if not quiet:
+            print(f"VALL-E EOS [{P} -> {P + 1 + T}]")
+        if nb > 1:  # NAR runs on the chosen beam only (batch 1), like the reference
+            eng.set_batch([text], [lang], [prompt])
+            codes = eng.nar(cb0=toks[pick:pick + 1, :max(T, 1)][:, :T] if T else np.zeros((1, 0), np.int32),
+                            t_lens=np.asarray([T], np.int32))
+        else:
+            codes = eng.nar(Tmax=T)
+        self.last_timing = dict(eng.timing(), ms_prefill=t_pre)
+        out = torch.from_numpy(codes[:1, :T].astype(np.int64))
+        return out.to(x.device) if x.is_cuda else out

@@ -1,0 +1,160 @@
+"""Synthetic (seeded, random-init) checkpoints in the reference's key layout.
+
+There is no network in the build/bench environment, so the real
+`vallex-checkpoint.pt` / `charactr/vocos-encodec-24khz` weights cannot be
+fetched.  These generators produce state dicts with exactly the key names,
+shapes and dtypes the reference model exposes (reference
+`models/vallex.py:55-264,400-445`, `modules/transformer.py:83-108,178-260`),
+so the same dict can be loaded strict into the reference `VALLE` (golden
+generation, `tests/golden/make_golden.py`), into the CPU oracle, and into the
+B200 engine.  Scales follow torch's default initialisers so activations have
+realistic magnitudes; LayerNorm affines are perturbed away from (1, 0) so a
+kernel that forgets them fails parity.
+
+The Vocos dict follows the public `vocos` package layout (third party, not in
+the reference tree; see oracle/vocos_oracle.py header -- parity unpinned).
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+
+import torch
+
+from .macros import N_DIM, NUM_HEAD, NUM_LAYERS, NUM_QUANTIZERS, NUM_TEXT_TOKENS, NUM_AUDIO_TOKENS
+
+D = N_DIM
+FF = 4 * N_DIM
+
+
+def _uniform(g, shape, bound):
+    return (torch.rand(shape, generator=g, dtype=torch.float32) * 2.0 - 1.0) * bound
+
+
+def _normal(g, shape, std=1.0):
+    return torch.randn(shape, generator=g, dtype=torch.float32) * std
+
+
+def _encoder_layer(sd, g, prefix, adaptive):
+    sd[f"{prefix}.self_attn.in_proj_weight"] = _uniform(g, (3 * D, D), math.sqrt(6.0 / (D + 3 * D)))
+    sd[f"{prefix}.self_attn.in_proj_bias"] = _uniform(g, (3 * D,), 0.02)
+    sd[f"{prefix}.self_attn.out_proj.weight"] = _uniform(g, (D, D), 1.0 / math.sqrt(D))
+    sd[f"{prefix}.self_attn.out_proj.bias"] = _uniform(g, (D,), 0.02)
+    sd[f"{prefix}.linear1.weight"] = _uniform(g, (FF, D), 1.0 / math.sqrt(D))
+    sd[f"{prefix}.linear1.bias"] = _uniform(g, (FF,), 1.0 / math.sqrt(D))
+    sd[f"{prefix}.linear2.weight"] = _uniform(g, (D, FF), 1.0 / math.sqrt(FF))
+    sd[f"{prefix}.linear2.bias"] = _uniform(g, (D,), 1.0 / math.sqrt(FF))
+    for n in ("norm1", "norm2"):
+        if adaptive:
+            sd[f"{prefix}.{n}.project_layer.weight"] = _uniform(g, (2 * D, D), 1.0 / math.sqrt(D))
+            sd[f"{prefix}.{n}.project_layer.bias"] = _uniform(g, (2 * D,), 1.0 / math.sqrt(D))
+            sd[f"{prefix}.{n}.norm.weight"] = 1.0 + _normal(g, (D,), 0.1)
+            sd[f"{prefix}.{n}.norm.bias"] = _normal(g, (D,), 0.1)
+        else:
+            sd[f"{prefix}.{n}.weight"] = 1.0 + _normal(g, (D,), 0.1)
+            sd[f"{prefix}.{n}.bias"] = _normal(g, (D,), 0.1)
+
+
+def synthetic_state_dict(seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
+    """374-key fp32 state dict in the order the reference's `state_dict()` yields."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(1000003 * (seed + 1))
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    sd["ar_text_embedding.word_embeddings.weight"] = _normal(g, (NUM_TEXT_TOKENS, D))
+    sd["nar_text_embedding.word_embeddings.weight"] = _normal(g, (NUM_TEXT_TOKENS, D))
+    sd["ar_audio_embedding.word_embeddings.weight"] = _normal(g, (NUM_AUDIO_TOKENS + 2, D))
+    sd["ar_text_position.alpha"] = torch.tensor([1.0 + 0.25 * float(_normal(g, (1,))[0])])
+    sd["ar_audio_position.alpha"] = torch.tensor([1.0 + 0.25 * float(_normal(g, (1,))[0])])
+    for i in range(NUM_LAYERS):
+        _encoder_layer(sd, g, f"ar_decoder.layers.{i}", adaptive=False)
+    sd["ar_decoder.norm.weight"] = 1.0 + _normal(g, (D,), 0.1)
+    sd["ar_decoder.norm.bias"] = _normal(g, (D,), 0.1)
+    sd["ar_predict_layer.weight"] = _uniform(g, (NUM_AUDIO_TOKENS + 1, D), 1.0 / math.sqrt(D))
+    sd["nar_audio_embeddings.0.word_embeddings.weight"] = _normal(g, (NUM_AUDIO_TOKENS + 1, D))
+    for j in range(1, NUM_QUANTIZERS):
+        sd[f"nar_audio_embeddings.{j}.word_embeddings.weight"] = _normal(g, (NUM_AUDIO_TOKENS, D))
+    sd["nar_text_position.alpha"] = torch.ones(1)
+    sd["nar_audio_position.alpha"] = torch.ones(1)
+    for i in range(NUM_LAYERS):
+        _encoder_layer(sd, g, f"nar_decoder.layers.{i}", adaptive=True)
+    sd["nar_decoder.norm.project_layer.weight"] = _uniform(g, (2 * D, D), 1.0 / math.sqrt(D))
+    sd["nar_decoder.norm.project_layer.bias"] = _uniform(g, (2 * D,), 1.0 / math.sqrt(D))
+    sd["nar_decoder.norm.norm.weight"] = 1.0 + _normal(g, (D,), 0.1)
+    sd["nar_decoder.norm.norm.bias"] = _normal(g, (D,), 0.1)
+    # nar_predict_layers.{0..5} alias nar_audio_embeddings.{2..7} (models/vallex.py:261-264)
+    for j in range(NUM_QUANTIZERS - 2):
+        sd[f"nar_predict_layers.{j}.weight"] = sd[f"nar_audio_embeddings.{j + 2}.word_embeddings.weight"]
+    sd[f"nar_predict_layers.{NUM_QUANTIZERS - 2}.weight"] = _uniform(g, (NUM_AUDIO_TOKENS, D), 1.0 / math.sqrt(D))
+    for j in range(NUM_QUANTIZERS - 1):
+        sd[f"nar_stage_embeddings.{j}.word_embeddings.weight"] = _normal(g, (1, D))
+    sd["ar_language_embedding.word_embeddings.weight"] = _normal(g, (3, D))
+    sd["nar_language_embedding.word_embeddings.weight"] = _normal(g, (3, D))
+    return sd
+
+
+# ---- Vocos (charactr/vocos-encodec-24khz shapes; third-party, from the public package layout) ----
+VOCOS_IN = 128
+VOCOS_DIM = 384
+VOCOS_FF = 1152
+VOCOS_LAYERS = 8
+VOCOS_NUM_BW = 4
+VOCOS_NFFT = 1280
+VOCOS_HOP = 320
+VOCOS_CODEBOOKS = 16  # 12 kbps table; the path uses the first 8 (6 kbps)
+
+
+def synthetic_vocos_state_dict(seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
+    g = torch.Generator(device="cpu")
+    g.manual_seed(7000003 * (seed + 1))
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    sd["feature_extractor.codebook_weights"] = _normal(g, (VOCOS_CODEBOOKS * 1024, VOCOS_IN), 0.5)
+    sd["backbone.embed.weight"] = _uniform(g, (VOCOS_DIM, VOCOS_IN, 7), 1.0 / math.sqrt(VOCOS_IN * 7))
+    sd["backbone.embed.bias"] = _uniform(g, (VOCOS_DIM,), 1.0 / math.sqrt(VOCOS_IN * 7))
+    sd["backbone.norm.scale.weight"] = 1.0 + _normal(g, (VOCOS_NUM_BW, VOCOS_DIM), 0.1)
+    sd["backbone.norm.shift.weight"] = _normal(g, (VOCOS_NUM_BW, VOCOS_DIM), 0.1)
+    for i in range(VOCOS_LAYERS):
+        p = f"backbone.convnext.{i}"
+        sd[f"{p}.dwconv.weight"] = _uniform(g, (VOCOS_DIM, 1, 7), 1.0 / math.sqrt(7))
+        sd[f"{p}.dwconv.bias"] = _uniform(g, (VOCOS_DIM,), 1.0 / math.sqrt(7))
+        sd[f"{p}.norm.scale.weight"] = 1.0 + _normal(g, (VOCOS_NUM_BW, VOCOS_DIM), 0.1)
+        sd[f"{p}.norm.shift.weight"] = _normal(g, (VOCOS_NUM_BW, VOCOS_DIM), 0.1)
+        sd[f"{p}.pwconv1.weight"] = _uniform(g, (VOCOS_FF, VOCOS_DIM), 1.0 / math.sqrt(VOCOS_DIM))
+        sd[f"{p}.pwconv1.bias"] = _uniform(g, (VOCOS_FF,), 1.0 / math.sqrt(VOCOS_DIM))
+        sd[f"{p}.pwconv2.weight"] = _uniform(g, (VOCOS_DIM, VOCOS_FF), 1.0 / math.sqrt(VOCOS_FF))
+        sd[f"{p}.pwconv2.bias"] = _uniform(g, (VOCOS_DIM,), 1.0 / math.sqrt(VOCOS_FF))
+        sd[f"{p}.gamma"] = torch.full((VOCOS_DIM,), 1.0 / VOCOS_LAYERS) + _normal(g, (VOCOS_DIM,), 0.02)
+    sd["backbone.final_layer_norm.weight"] = 1.0 + _normal(g, (VOCOS_DIM,), 0.1)
+    sd["backbone.final_layer_norm.bias"] = _normal(g, (VOCOS_DIM,), 0.1)
+    # small head weights keep exp(mag) well inside the clip range, like a trained head
+    sd["head.out.weight"] = _uniform(g, (VOCOS_NFFT + 2, VOCOS_DIM), 0.5 / math.sqrt(VOCOS_DIM))
+    sd["head.out.bias"] = _uniform(g, (VOCOS_NFFT + 2,), 0.5 / math.sqrt(VOCOS_DIM))
+    sd["head.istft.window"] = torch.hann_window(VOCOS_NFFT)
+    return sd
+
+
+_BF16_PAT = __import__("re").compile(
+    r"(self_attn\.in_proj_weight|self_attn\.out_proj\.weight|linear1\.weight|linear2\.weight"
+    r"|^ar_predict_layer\.weight|^nar_predict_layers\.\d+\.weight|^nar_audio_embeddings\.[2-7]\.word_embeddings\.weight)$")
+
+
+def is_bf16_matrix(key: str) -> bool:
+    """Which checkpoint tensors the engine's bf16 mode stores in bf16: every GEMM operand (QKV / out-proj /
+    FFN / predict layers).  nar_audio_embeddings.{2..7} are included because the reference ties them to
+    nar_predict_layers.{0..5} (models/vallex.py:261-264) -- one tensor, one precision."""
+    return _BF16_PAT.search(key) is not None
+
+
+def round_state_dict_bf16(sd):
+    """The fp32 state dict holding exactly the values the bf16 engine mode computes with."""
+    return type(sd)((k, (v.to(torch.bfloat16).to(torch.float32) if is_bf16_matrix(k) else v)) for k, v in sd.items())
+
+
+def sine_position_table(length: int, dim: int = D) -> torch.Tensor:
+    """fp32 sinusoid table, computed with the same torch CPU ops (exp/sin/cos in fp32) the
+    reference uses in `modules/embedding.py:68-91` so the uploaded table is bit-identical."""
+    position = torch.arange(0, length, dtype=torch.float32).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, dim, 2, dtype=torch.float32) * -(math.log(10000.0) / dim))
+    pe = torch.zeros(length, dim)
+    pe[:, 0::2] = torch.sin(position * div_term)
+    pe[:, 1::2] = torch.cos(position * div_term)
+    return pe
