@@ -114,6 +114,13 @@ VX_API int vx_last_timing(vx_engine* e, float* ms_prefill, float* ms_decode, flo
                    int64_t* decode_steps, int64_t* kernel_launches);
 VX_API int vx_debug_read(vx_engine* e, const char* what, float* dst, int64_t max_elems, int64_t* out_elems);
 
+/* Isolated kernel checks (tests/test_gpu_kernels.py); host fp32 buffers, current CUDA device.
+ * vx_debug_gemm_tc: C[M,N] = A[M,K] W[N,K]^T (+bias) through the tcgen05 GEMM (epi 0: bf16 row-major, 1: fp32 += into
+ * the given C, 2: ReLU -> bf16 tile image, 3: fp32).  vx_debug_attn_tc: one utterance, qkv [len,3072] -> out [len,1024]
+ * through the bf16 tensor-core attention (mode 0 bidirectional, 1 AR prefill mask with S text rows). */
+VX_API int vx_debug_gemm_tc(const float* A, const float* W, const float* bias, float* C, int64_t M, int N, int K, int epi);
+VX_API int vx_debug_attn_tc(const float* qkv, float* out, int S, int len, int mode);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,6 +13,7 @@
 #include "../../include/vallex_b200.h"
 #include "common.cuh"
 #include "kernels.h"
+#include "tc_common.cuh"
 
 using namespace vx;
 
@@ -45,7 +46,8 @@ __global__ void write_cb0_kernel(Batch bt, const int32_t* __restrict__ cb0, cons
 struct Weight {
   std::vector<int64_t> shape;
   float* f32 = nullptr;  // device fp32 (always present until finalize may drop it for bf16 matrices)
-  bf16* b16 = nullptr;   // device bf16 copy (bf16 mode, GEMM matrices only)
+  bf16* b16 = nullptr;   // device bf16 row-major copy (bf16 mode: decode GEMV operands, tied embedding tables)
+  bf16* img = nullptr;   // device bf16 tile image (bf16 mode: tcgen05 GEMM operands, see tc_common.cuh)
   size_t numel = 0;
 };
 
@@ -56,6 +58,7 @@ struct Buf {
 
 struct LayerW {
   const void *qkv_w, *out_w, *ff1_w, *ff2_w;
+  const void *qkv_i, *out_i, *ff1_i, *ff2_i;  // tile images (bf16 mode)
   const float *qkv_b, *out_b, *ff1_b, *ff2_b, *n1_g, *n1_b, *n2_g, *n2_b;
   const float *ada1, *ada2;  // [7][2048] (NAR only)
 };
@@ -66,13 +69,14 @@ struct vx_engine {
   int device = 0, max_batch = 0, max_ctx = 0, mode = 0;
   cudaStream_t own_stream = nullptr;
   std::map<std::string, Weight> w;
-  bool finalized = false, has_vocos = false, has_valle = false;
+  bool finalized = false, has_vocos = false, has_valle = false, force_simt = false;
   LayerW ar[kL], nar[kL];
   const float *ar_norm_g = nullptr, *ar_norm_b = nullptr, *nar_norm_g = nullptr, *nar_norm_b = nullptr;
   const float* nar_norm_ada = nullptr;  // [7][2048]
   float* ada_all = nullptr;             // [25][7][2048]
   const void* ar_predict = nullptr;
   const void* nar_predict[7] = {};
+  const void* nar_predict_img[7] = {};
   EmbTables nar_emb{};
   const float* pe = nullptr;
   int pe_rows = 0;
@@ -86,6 +90,7 @@ struct vx_engine {
   Batch bt{};
   Buf d_text, d_lang, d_prompt, d_S, d_P, d_ar_row0, d_nar_row0, d_T, d_ctx, d_y, d_budget, d_fin, d_slp, d_nact;
   Buf x, xn, qkv, att, ffh, kc, vc;                 // prefill / NAR activations, KV cache
+  Buf a_img, qkv16, att_img, h_img, t_img;           // bf16 mode: tile-image / bf16 activations
   Buf xs, xsn, qkvs, atts, ffs, logits, part, tick;  // decode-step scratch
   Buf lastmap, out_tok, forced, yemb, yrow0, trow0, tgtmap, nlog, codes, tl_dev, cb0_dev;
   Buf v_codes, v_feat, v_col, v_x, v_h, v_ff, v_head, v_spec, v_frames, v_wave;
@@ -156,6 +161,10 @@ const void* mat(vx_engine* e, const std::string& k) {
   const Weight* w = findw(e, k);
   if (!w) return nullptr;
   return (e->mode == VX_BF16 && w->b16) ? (const void*)w->b16 : (const void*)w->f32;
+}
+const void* matimg(vx_engine* e, const std::string& k) {
+  const Weight* w = findw(e, k);
+  return w ? (const void*)w->img : nullptr;
 }
 const float* vec(vx_engine* e, const std::string& k) {
   const Weight* w = findw(e, k);
@@ -258,6 +267,55 @@ int linear(vx_engine* e, const float* A, int64_t lda, const void* W, int wt, con
   return VX_OK;
 }
 
+// One pre-LN encoder layer over R packed rows (AR prefill: attn_mode 1 + KV scatter; NAR: attn_mode 0 + AdaLN).
+// fp32 mode (or VX_FORCE_SIMT=1): exact SIMT kernels.  bf16 mode: LN -> bf16 tile image -> tcgen05 GEMMs with fused
+// epilogues, mma.sync flash attention.
+int full_layer(vx_engine* e, const LayerW& L, int64_t R, const int32_t* row0, int attn_mode, int maxlen,
+               const float* ada1, const float* ada2, int kv_layer, cudaStream_t st) {
+  const Batch& bt = e->bt;
+  const int wt = e->mode;
+  const size_t kvb = kv_esize(e);
+  float* x = (float*)e->x.p;
+  void* kc = kv_layer >= 0 ? (char*)e->kc.p + (size_t)kv_layer * e->kv_layer_elems * kvb : nullptr;
+  void* vc = kv_layer >= 0 ? (char*)e->vc.p + (size_t)kv_layer * e->kv_layer_elems * kvb : nullptr;
+  if (e->mode == VX_BF16 && !e->force_simt) {
+    launch_layernorm_image(x, nullptr, R, L.n1_g, L.n1_b, ada1, ada1 ? ada1 + kD : nullptr, 1e-5f, e->a_img.p, st);
+    launch_gemm_tc(e->a_img.p, L.qkv_i, L.qkv_b, e->qkv16.p, 3 * kD, R, 3 * kD, kD, TC_EPI_BF16_ROW, st);
+    if (kv_layer >= 0) { launch_kv_scatter_bf16(bt, e->qkv16.p, kc, vc, maxlen, e->ctx_cap, st); e->launches++; }
+    launch_attn_tc(bt, e->qkv16.p, row0, attn_mode, maxlen, e->att_img.p, st);
+    launch_gemm_tc(e->att_img.p, L.out_i, L.out_b, x, kD, R, kD, kD, TC_EPI_F32_RESIDUAL, st);
+    launch_layernorm_image(x, nullptr, R, L.n2_g, L.n2_b, ada2, ada2 ? ada2 + kD : nullptr, 1e-5f, e->a_img.p, st);
+    launch_gemm_tc(e->a_img.p, L.ff1_i, L.ff1_b, e->h_img.p, kFF, R, kFF, kD, TC_EPI_BF16_IMAGE_RELU, st);
+    launch_gemm_tc(e->h_img.p, L.ff2_i, L.ff2_b, x, kD, R, kD, kFF, TC_EPI_F32_RESIDUAL, st);
+    e->launches += 7;
+    return VX_OK;
+  }
+  float* xn = (float*)e->xn.p; float* qkv = (float*)e->qkv.p; float* att = (float*)e->att.p; float* ffh = (float*)e->ffh.p;
+  launch_layernorm(x, nullptr, R, kD, L.n1_g, L.n1_b, ada1, ada1 ? ada1 + kD : nullptr, 1e-5f, xn, st);
+  launch_gemm(xn, kD, L.qkv_w, wt, L.qkv_b, qkv, 3 * kD, R, 3 * kD, kD, EPI_NONE, nullptr, st);
+  if (kv_layer >= 0) { launch_kv_scatter(bt, qkv, kc, vc, wt, maxlen, e->ctx_cap, st); e->launches++; }
+  launch_attn_full(bt, qkv, row0, attn_mode, maxlen, att, st);
+  launch_gemm(att, kD, L.out_w, wt, L.out_b, x, kD, R, kD, kD, EPI_RESIDUAL, nullptr, st);
+  launch_layernorm(x, nullptr, R, kD, L.n2_g, L.n2_b, ada2, ada2 ? ada2 + kD : nullptr, 1e-5f, xn, st);
+  launch_gemm(xn, kD, L.ff1_w, wt, L.ff1_b, ffh, kFF, R, kFF, kD, EPI_RELU, nullptr, st);
+  launch_gemm(ffh, kFF, L.ff2_w, wt, L.ff2_b, x, kD, R, kD, kFF, EPI_RESIDUAL, nullptr, st);
+  e->launches += 7;
+  return VX_OK;
+}
+
+// activation workspaces for R packed rows in the engine's mode
+int ensure_full_buffers(vx_engine* e, int64_t R) {
+  const int64_t Rp = (R + 127) / 128 * 128;
+  ENS(e->x, Rp * kD * 4);
+  if (e->mode == VX_BF16 && !e->force_simt) {
+    ENS(e->a_img, Rp * kD * 2); ENS(e->qkv16, Rp * 3 * kD * 2); ENS(e->att_img, Rp * kD * 2); ENS(e->h_img, Rp * kFF * 2);
+    ENS(e->xn, (size_t)std::max<int64_t>(e->max_batch, 1) * kD * 4);
+  } else {
+    ENS(e->xn, Rp * kD * 4); ENS(e->qkv, Rp * 3 * kD * 4); ENS(e->att, Rp * kD * 4); ENS(e->ffh, Rp * kFF * 4);
+  }
+  return VX_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -284,6 +342,8 @@ int vx_create(int device, int max_batch, int max_ctx, int dtype_mode, vx_engine*
   CK(cudaEventCreate(&e->ev0));
   CK(cudaEventCreate(&e->ev1));
   CK(cudaMallocHost(&e->h_pinned, 4096));
+  const char* fs = getenv("VX_FORCE_SIMT");
+  e->force_simt = fs && fs[0] == '1';
   *out = e;
   return VX_OK;
 }
@@ -295,10 +355,11 @@ void vx_destroy(vx_engine* e) {
   for (auto& kv : e->w) {
     if (kv.second.f32) cudaFree(kv.second.f32);
     if (kv.second.b16) cudaFree(kv.second.b16);
+    if (kv.second.img) cudaFree(kv.second.img);
   }
   Buf* bufs[] = {&e->d_text, &e->d_lang, &e->d_prompt, &e->d_S, &e->d_P, &e->d_ar_row0, &e->d_nar_row0, &e->d_T,
                  &e->d_ctx, &e->d_y, &e->d_budget, &e->d_fin, &e->d_slp, &e->d_nact, &e->x, &e->xn, &e->qkv, &e->att,
-                 &e->ffh, &e->kc, &e->vc, &e->xs, &e->xsn, &e->qkvs, &e->atts, &e->ffs, &e->logits, &e->part, &e->tick,
+                 &e->ffh, &e->kc, &e->vc, &e->a_img, &e->qkv16, &e->att_img, &e->h_img, &e->t_img, &e->xs, &e->xsn, &e->qkvs, &e->atts, &e->ffs, &e->logits, &e->part, &e->tick,
                  &e->lastmap, &e->out_tok, &e->forced, &e->yemb, &e->yrow0, &e->trow0, &e->tgtmap, &e->nlog, &e->codes,
                  &e->tl_dev, &e->cb0_dev, &e->v_codes, &e->v_feat, &e->v_col, &e->v_x, &e->v_h, &e->v_ff, &e->v_head,
                  &e->v_spec, &e->v_frames, &e->v_wave};
@@ -326,6 +387,7 @@ int vx_load_weight(vx_engine* e, const char* key, const float* data, const int64
   if (it != e->w.end()) {
     if (it->second.f32) cudaFree(it->second.f32);
     if (it->second.b16) cudaFree(it->second.b16);
+    if (it->second.img) cudaFree(it->second.img);
     e->w.erase(it);
   }
   CK(cudaMalloc(&wt.f32, std::max<size_t>(wt.numel, 4) * sizeof(float)));
@@ -381,19 +443,27 @@ int vx_finalize_weights(vx_engine* e) {
     CK(cudaStreamSynchronize(st));
     CK(cudaFree(stage_rows));
   }
-  // bf16 copies of the GEMM matrices (bf16 mode); the fp32 originals are released.
+  // bf16 mode: every GEMM matrix gets a tile image (tcgen05 operand); the AR matrices and the tied embedding
+  // tables also keep a row-major bf16 copy (decode GEMV / gathers).  The fp32 originals are released.
   if (e->mode == VX_BF16) {
     for (auto& kv : e->w) {
       Weight& w = kv.second;
-      if (!is_gemm_matrix(kv.first) || w.b16) continue;
-      // tied tensors arrive under two keys with identical contents; each gets its own bf16 copy (6 MB total)
-      CK(cudaMalloc(&w.b16, w.numel * sizeof(bf16)));
-      f32_to_bf16_kernel<<<296, 256, 0, st>>>(w.f32, w.b16, w.numel);
+      if (!is_gemm_matrix(kv.first) || w.img || !w.f32) continue;
+      const int64_t rows = w.shape[0];
+      const int K = (int)w.shape[1];
+      const int64_t rows_pad = (rows + 127) / 128 * 128;
+      CK(cudaMalloc(&w.img, (size_t)rows_pad * K * sizeof(bf16)));
+      launch_pack_tile_image(w.f32, rows, K, w.img, st);
+      const bool need_row_major = e->force_simt || (kv.first.rfind("nar_decoder.", 0) != 0 && kv.first.rfind("nar_predict_layers.", 0) != 0);
+      if (need_row_major) {
+        CK(cudaMalloc(&w.b16, w.numel * sizeof(bf16)));
+        f32_to_bf16_kernel<<<296, 256, 0, st>>>(w.f32, w.b16, w.numel);
+      }
     }
     CK(cudaStreamSynchronize(st));
     for (auto& kv : e->w) {
       Weight& w = kv.second;
-      if (w.b16 && w.f32) {
+      if (w.img && w.f32) {
         cudaFree(w.f32);
         w.f32 = nullptr;
       }
@@ -413,6 +483,10 @@ int vx_finalize_weights(vx_engine* e) {
       L.ff1_b = vec(e, p + ".linear1.bias");
       L.ff2_w = mat(e, p + ".linear2.weight");
       L.ff2_b = vec(e, p + ".linear2.bias");
+      L.qkv_i = matimg(e, p + ".self_attn.in_proj_weight");
+      L.out_i = matimg(e, p + ".self_attn.out_proj.weight");
+      L.ff1_i = matimg(e, p + ".linear1.weight");
+      L.ff2_i = matimg(e, p + ".linear2.weight");
       if (which) {
         L.n1_g = vec(e, p + ".norm1.norm.weight");
         L.n1_b = vec(e, p + ".norm1.norm.bias");
@@ -434,7 +508,10 @@ int vx_finalize_weights(vx_engine* e) {
   e->nar_norm_b = vec(e, "nar_decoder.norm.norm.bias");
   e->nar_norm_ada = e->ada_all + (size_t)24 * 7 * 2 * kD;
   e->ar_predict = mat(e, "ar_predict_layer.weight");
-  for (int j = 0; j < 7; ++j) e->nar_predict[j] = mat(e, "nar_predict_layers." + std::to_string(j) + ".weight");
+  for (int j = 0; j < 7; ++j) {
+    e->nar_predict[j] = mat(e, "nar_predict_layers." + std::to_string(j) + ".weight");
+    e->nar_predict_img[j] = matimg(e, "nar_predict_layers." + std::to_string(j) + ".weight");
+  }
   for (int j = 0; j < 8; ++j) {
     const std::string k = "nar_audio_embeddings." + std::to_string(j) + ".word_embeddings.weight";
     const Weight* w = findw(e, k);
@@ -542,33 +619,19 @@ int vx_ar_prefill(vx_engine* e, void* stream) {
   const int64_t R = e->ar_rows;
   const size_t kvb = kv_esize(e);
   e->kv_layer_elems = (size_t)e->max_batch * kH * e->ctx_cap * kDH;
-  ENS(e->x, R * kD * 4); ENS(e->xn, R * kD * 4); ENS(e->qkv, R * 3 * kD * 4); ENS(e->att, R * kD * 4);
-  ENS(e->ffh, R * kFF * 4);
+  { int _r = ensure_full_buffers(e, R); if (_r) return _r; }
   ENS(e->kc, e->kv_layer_elems * kL * kvb); ENS(e->vc, e->kv_layer_elems * kL * kvb);
   ENS(e->xs, (size_t)B * kD * 4); ENS(e->xsn, (size_t)B * kD * 4); ENS(e->logits, (size_t)B * kARLogits * 4);
   ENS(e->lastmap, B * 4);
   CK(cudaEventRecord(e->ev0, st));
   const Batch& bt = e->bt;
-  float* x = (float*)e->x.p; float* xn = (float*)e->xn.p; float* qkv = (float*)e->qkv.p;
-  float* att = (float*)e->att.p; float* ffh = (float*)e->ffh.p;
+  float* x = (float*)e->x.p;
   launch_init_y(bt, st);
   launch_embed_text(bt, vec(e, "ar_text_embedding.word_embeddings.weight"), vec(e, "ar_language_embedding.word_embeddings.weight"),
                     vec(e, "ar_text_position.alpha"), e->pe, bt.ar_row0, x, st);
   launch_embed_audio_prefill(bt, vec(e, "ar_audio_embedding.word_embeddings.weight"), vec(e, "ar_audio_position.alpha"), e->pe, x, st);
   e->launches += 3;
-  for (int l = 0; l < kL; ++l) {
-    const LayerW& L = e->ar[l];
-    launch_layernorm(x, nullptr, R, kD, L.n1_g, L.n1_b, nullptr, nullptr, 1e-5f, xn, st);
-    launch_gemm(xn, kD, L.qkv_w, wt, L.qkv_b, qkv, 3 * kD, R, 3 * kD, kD, EPI_NONE, nullptr, st);
-    launch_kv_scatter(bt, qkv, (char*)e->kc.p + (size_t)l * e->kv_layer_elems * kvb,
-                      (char*)e->vc.p + (size_t)l * e->kv_layer_elems * kvb, wt, e->ar_maxlen, e->ctx_cap, st);
-    launch_attn_full(bt, qkv, bt.ar_row0, 1, e->ar_maxlen, att, st);
-    launch_gemm(att, kD, L.out_w, wt, L.out_b, x, kD, R, kD, kD, EPI_RESIDUAL, nullptr, st);
-    launch_layernorm(x, nullptr, R, kD, L.n2_g, L.n2_b, nullptr, nullptr, 1e-5f, xn, st);
-    launch_gemm(xn, kD, L.ff1_w, wt, L.ff1_b, ffh, kFF, R, kFF, kD, EPI_RELU, nullptr, st);
-    launch_gemm(ffh, kFF, L.ff2_w, wt, L.ff2_b, x, kD, R, kD, kFF, EPI_RESIDUAL, nullptr, st);
-    e->launches += 8;
-  }
+  for (int l = 0; l < kL; ++l) full_layer(e, e->ar[l], R, bt.ar_row0, 1, e->ar_maxlen, nullptr, nullptr, l, st);
   std::vector<int32_t> last(B);
   for (int b = 0; b < B; ++b) last[b] = e->h_ar_row0[b] + e->hS[b] + e->hP[b];
   memcpy(e->h_pinned, last.data(), B * 4);
@@ -784,14 +847,14 @@ int vx_nar(vx_engine* e, const int32_t* cb0, const int32_t* t_lens, int Tmax, in
   CK(cudaMemcpyAsync(e->yrow0.p, yrow0.data(), B * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(e->trow0.p, trow0.data(), B * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(e->tgtmap.p, tgt.data(), tgt.size() * 4, cudaMemcpyHostToDevice, st));
-  ENS(e->x, R * kD * 4); ENS(e->xn, R * kD * 4); ENS(e->qkv, R * 3 * kD * 4); ENS(e->att, R * kD * 4);
-  ENS(e->ffh, R * kFF * 4);
+  { int _r = ensure_full_buffers(e, R); if (_r) return _r; }
+  ENS(e->xn, (std::max<int64_t>(TR, 1) + 127) / 128 * 128 * kD * 4);
+  ENS(e->t_img, (std::max<int64_t>(TR, 1) + 127) / 128 * 128 * kD * 2);
   ENS(e->yemb, std::max<int64_t>(YR, 1) * kD * 4); ENS(e->nlog, std::max<int64_t>(TR, 1) * kVocab * 4);
   ENS(e->codes, (size_t)B * std::max(Tmax, 1) * kNQ * 4);
   CK(cudaStreamSynchronize(st));  // host vectors above go out of scope; x/xn may have been reallocated
   CK(cudaEventRecord(e->ev0, st));
-  float* x = (float*)e->x.p; float* xn = (float*)e->xn.p; float* qkv = (float*)e->qkv.p;
-  float* att = (float*)e->att.p; float* ffh = (float*)e->ffh.p; float* yemb = (float*)e->yemb.p;
+  float* x = (float*)e->x.p; float* xn = (float*)e->xn.p; float* yemb = (float*)e->yemb.p;
   const int32_t* d_yrow0 = (const int32_t*)e->yrow0.p; const int32_t* d_trow0 = (const int32_t*)e->trow0.p;
   CK(cudaMemsetAsync(e->codes.p, 0, (size_t)B * std::max(Tmax, 1) * kNQ * 4, st));
   launch_nar_copy_cb0(bt, (int32_t*)e->codes.p, Tmax, st);
@@ -805,21 +868,18 @@ int vx_nar(vx_engine* e, const int32_t* cb0, const int32_t* t_lens, int Tmax, in
       e->launches += 2;
       for (int l = 0; l < kL; ++l) {
         const LayerW& L = e->nar[l];
-        const float* a1 = L.ada1 + (size_t)stage * 2 * kD;
-        const float* a2 = L.ada2 + (size_t)stage * 2 * kD;
-        launch_layernorm(x, nullptr, R, kD, L.n1_g, L.n1_b, a1, a1 + kD, 1e-5f, xn, st);
-        launch_gemm(xn, kD, L.qkv_w, wt, L.qkv_b, qkv, 3 * kD, R, 3 * kD, kD, EPI_NONE, nullptr, st);
-        launch_attn_full(bt, qkv, bt.nar_row0, 0, maxlen, att, st);
-        launch_gemm(att, kD, L.out_w, wt, L.out_b, x, kD, R, kD, kD, EPI_RESIDUAL, nullptr, st);
-        launch_layernorm(x, nullptr, R, kD, L.n2_g, L.n2_b, a2, a2 + kD, 1e-5f, xn, st);
-        launch_gemm(xn, kD, L.ff1_w, wt, L.ff1_b, ffh, kFF, R, kFF, kD, EPI_RELU, nullptr, st);
-        launch_gemm(ffh, kFF, L.ff2_w, wt, L.ff2_b, x, kD, R, kD, kFF, EPI_RESIDUAL, nullptr, st);
-        e->launches += 7;
+        full_layer(e, L, R, bt.nar_row0, 0, maxlen, L.ada1 + (size_t)stage * 2 * kD, L.ada2 + (size_t)stage * 2 * kD, -1, st);
       }
       const float* af = e->nar_norm_ada + (size_t)stage * 2 * kD;
-      launch_layernorm(x, (const int32_t*)e->tgtmap.p, TR, kD, e->nar_norm_g, e->nar_norm_b, af, af + kD, 1e-5f, xn, st);
-      e->launches++;
-      linear(e, xn, kD, e->nar_predict[stage], wt, nullptr, (float*)e->nlog.p, kVocab, TR, kVocab, kD, EPI_NONE, st);
+      if (e->mode == VX_BF16 && !e->force_simt) {
+        launch_layernorm_image(x, (const int32_t*)e->tgtmap.p, TR, e->nar_norm_g, e->nar_norm_b, af, af + kD, 1e-5f, e->t_img.p, st);
+        launch_gemm_tc(e->t_img.p, e->nar_predict_img[stage], nullptr, e->nlog.p, kVocab, TR, kVocab, kD, TC_EPI_F32, st);
+        e->launches += 2;
+      } else {
+        launch_layernorm(x, (const int32_t*)e->tgtmap.p, TR, kD, e->nar_norm_g, e->nar_norm_b, af, af + kD, 1e-5f, xn, st);
+        e->launches++;
+        linear(e, xn, kD, e->nar_predict[stage], wt, nullptr, (float*)e->nlog.p, kVocab, TR, kVocab, kD, EPI_NONE, st);
+      }
       launch_nar_argmax_update(bt, (const float*)e->nlog.p, d_trow0, stage, e->nar_emb, yemb, d_yrow0,
                                (int32_t*)e->codes.p, Tmax, st);
       e->launches++;
@@ -910,6 +970,74 @@ int vx_debug_read(vx_engine* e, const char* what, float* dst, int64_t max_elems,
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(dst, src, n * sizeof(float), cudaMemcpyDeviceToHost));
   if (out_elems) *out_elems = n;
+  return VX_OK;
+}
+
+// ---- isolated kernel tests (tests/test_gpu_kernels.py): host fp32 in/out, run on the current device ----
+__global__ void unpack_image_kernel(const uint8_t* __restrict__ img, int64_t rows, int K, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * K) return;
+  const int64_t r = i / K;
+  const int k = (int)(i % K);
+  out[i] = __bfloat162float(*reinterpret_cast<const bf16*>(img + tc::tile_image_offset(r, k, K)));
+}
+__global__ void bf16_to_f32_kernel(const bf16* __restrict__ in, float* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __bfloat162float(in[i]);
+}
+
+int vx_debug_gemm_tc(const float* A, const float* W, const float* bias, float* C, int64_t M, int N, int K, int epi) {
+  if (!A || !W || !C || M < 1 || N % 128 || K % 64) return fail(VX_ERR_ARG, "vx_debug_gemm_tc: bad arguments");
+  const int64_t Mp = (M + 127) / 128 * 128;
+  float *dA = nullptr, *dW = nullptr, *dB = nullptr, *dC = nullptr;
+  void *iA = nullptr, *iW = nullptr, *o16 = nullptr;
+  CK(cudaMalloc(&dA, M * K * 4)); CK(cudaMalloc(&dW, (size_t)N * K * 4)); CK(cudaMalloc(&dC, Mp * N * 4));
+  CK(cudaMalloc(&iA, Mp * K * 2)); CK(cudaMalloc(&iW, (size_t)N * K * 2)); CK(cudaMalloc(&o16, Mp * N * 2));
+  CK(cudaMemcpy(dA, A, M * K * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dW, W, (size_t)N * K * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dC, C, M * N * 4, cudaMemcpyHostToDevice));  // residual input for TC_EPI_F32_RESIDUAL
+  if (bias) { CK(cudaMalloc(&dB, N * 4)); CK(cudaMemcpy(dB, bias, N * 4, cudaMemcpyHostToDevice)); }
+  launch_pack_tile_image(dA, M, K, iA, 0);
+  launch_pack_tile_image(dW, N, K, iW, 0);
+  if (epi == TC_EPI_BF16_ROW) {
+    launch_gemm_tc(iA, iW, dB, o16, N, M, N, K, epi, 0);
+    bf16_to_f32_kernel<<<(unsigned)((M * N + 255) / 256), 256>>>((const bf16*)o16, dC, (size_t)M * N);
+  } else if (epi == TC_EPI_BF16_IMAGE_RELU) {
+    launch_gemm_tc(iA, iW, dB, o16, N, M, N, K, epi, 0);
+    unpack_image_kernel<<<(unsigned)((M * N + 255) / 256), 256>>>((const uint8_t*)o16, M, N, dC);
+  } else {
+    launch_gemm_tc(iA, iW, dB, dC, N, M, N, K, epi, 0);
+  }
+  CK(cudaDeviceSynchronize());
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(C, dC, M * N * 4, cudaMemcpyDeviceToHost));
+  cudaFree(dA); cudaFree(dW); cudaFree(dC); cudaFree(iA); cudaFree(iW); cudaFree(o16);
+  if (dB) cudaFree(dB);
+  return VX_OK;
+}
+
+int vx_debug_attn_tc(const float* qkv, float* out, int S, int len, int mode) {
+  if (!qkv || !out || S < 1 || len <= S - (mode == 0 ? 1 : 0) || (mode != 0 && mode != 1)) return fail(VX_ERR_ARG, "vx_debug_attn_tc: bad arguments");
+  const int64_t Lp = (len + 127) / 128 * 128;
+  float *dq = nullptr, *dout = nullptr;
+  bf16* q16 = nullptr;
+  void* img = nullptr;
+  int32_t* meta = nullptr;  // S, P, T, row0
+  CK(cudaMalloc(&dq, (size_t)len * 3 * kD * 4)); CK(cudaMalloc(&q16, (size_t)len * 3 * kD * 2));
+  CK(cudaMalloc(&img, Lp * kD * 2)); CK(cudaMalloc(&dout, (size_t)len * kD * 4)); CK(cudaMalloc(&meta, 16));
+  CK(cudaMemset(img, 0, Lp * kD * 2));
+  const int32_t h[4] = {S, mode == 1 ? len - S - 1 : 0, mode == 1 ? 0 : len - S, 0};
+  CK(cudaMemcpy(meta, h, 16, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dq, qkv, (size_t)len * 3 * kD * 4, cudaMemcpyHostToDevice));
+  f32_to_bf16_kernel<<<296, 256>>>(dq, q16, (size_t)len * 3 * kD);
+  Batch bt{};
+  bt.B = 1; bt.S = meta; bt.P = meta + 1; bt.T = meta + 2;
+  launch_attn_tc(bt, q16, meta + 3, mode, len, img, 0);
+  unpack_image_kernel<<<(unsigned)(((int64_t)len * kD + 255) / 256), 256>>>((const uint8_t*)img, len, kD, dout);
+  CK(cudaDeviceSynchronize());
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(out, dout, (size_t)len * kD * 4, cudaMemcpyDeviceToHost));
+  cudaFree(dq); cudaFree(q16); cudaFree(img); cudaFree(dout); cudaFree(meta);
   return VX_OK;
 }
 

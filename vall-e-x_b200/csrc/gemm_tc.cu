@@ -1,0 +1,291 @@
+// tcgen05 GEMM for the full-sequence passes (AR prefill, the 7 NAR passes) in bf16 mode.
+//
+//   C[M,N] = A[M,K] (bf16 tile image) x W[N,K]^T (bf16 tile image), fp32 accumulate in TMEM, fused epilogue.
+//
+// Persistent, warp-specialised (see tc_common.cuh for the operand layout):
+//   warp 0   : producer -- one elected lane streams 16 KB operand blocks HBM -> shared with cp.async.bulk
+//              (TMA engine) through a kStages-deep mbarrier ring;
+//   warp 1   : allocates TMEM; one elected lane issues tcgen05.mma (M=128, N=BN, K=16; 4 per 64-wide k block),
+//              tcgen05.commit frees each ring slot and publishes a finished accumulator;
+//   warps 2-5: epilogue -- tcgen05.ld the 128 x BN fp32 accumulator (double-buffered in TMEM, so the next tile's
+//              MMAs overlap), add bias / ReLU / residual, store bf16 row-major, bf16 tile image or fp32.
+// Bound: tensor pipe (dense bf16).  Tiles are walked m-fastest so CTAs running concurrently share the same
+// weight blocks through L2.  modules/activation.py:144,166; modules/transformer.py:371-373; models/vallex.py:677.
+#include "common.cuh"
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace vx {
+using namespace tc;
+
+enum TcEpi { TC_BF16_ROW = 0, TC_F32_RESIDUAL = 1, TC_BF16_IMAGE_RELU = 2, TC_F32 = 3 };
+
+template <int BN>
+struct TcCfg {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kABytes = kBlockBytes;
+  static constexpr int kBBytes = kBlockBytes * (BN / 128);
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const bf16* __restrict__ A, const bf16* __restrict__ W,
+                                                         const float* __restrict__ bias, void* __restrict__ out,
+                                                         int64_t ldc, int64_t M, int N, int K) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty = full + Cfg::kStages;
+  uint64_t* tfull = empty + Cfg::kStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (int)((M + 127) >> 7);
+  const int n_tiles = N / BN;
+  const int k_tiles = K >> 6;
+  const int tiles = m_tiles * n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int mt = t % m_tiles, nt = t / m_tiles;
+        const uint8_t* a_src = reinterpret_cast<const uint8_t*>(A) + (size_t)mt * k_tiles * kBlockBytes;
+        for (int kt = 0; kt < k_tiles; ++kt) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+          bulk_g2s(sa, a_src + (size_t)kt * kBlockBytes, kBlockBytes, &full[stage]);
+#pragma unroll
+          for (int j = 0; j < BN / 128; ++j) {
+            const uint8_t* w_src = reinterpret_cast<const uint8_t*>(W) +
+                                   ((size_t)(nt * (BN / 128) + j) * k_tiles + kt) * kBlockBytes;
+            bulk_g2s(sa + Cfg::kABytes + j * kBlockBytes, w_src, kBlockBytes, &full[stage]);
+          }
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+      int stage = 0;
+      uint32_t phase = 0, acc_phase[2] = {0, 0};
+      int it = 0;
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&tempty[acc], acc_phase[acc] ^ 1);
+        acc_phase[acc] ^= 1;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kt = 0; kt < k_tiles; ++kt) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t adesc = umma_desc_sw128(sa);
+          const uint64_t bdesc = umma_desc_sw128(sa + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
+            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kt | k) ? 1u : 0u);
+          umma_commit(&empty[stage]);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);
+      }
+    }
+  } else {
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    uint32_t acc_phase[2] = {0, 0};
+    int it = 0;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const int mt = t % m_tiles, nt = t / m_tiles;
+      mbar_wait(&tfull[acc], acc_phase[acc]);
+      acc_phase[acc] ^= 1;
+      tc_fence_after();
+      const int64_t row = (int64_t)mt * 128 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(taddr + c0, v);
+        const int n0 = nt * BN + c0;
+        if (bias) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += __ldg(bias + n0 + i);
+        }
+        if (row < M) {
+          if constexpr (EPI == TC_BF16_ROW) {
+            bf16* o = reinterpret_cast<bf16*>(out) + row * ldc + n0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              uint4 p;
+              p.x = __bfloat16_as_ushort(__float2bfloat16_rn(v[i])) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[i + 1])) << 16);
+              p.y = __bfloat16_as_ushort(__float2bfloat16_rn(v[i + 2])) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[i + 3])) << 16);
+              p.z = __bfloat16_as_ushort(__float2bfloat16_rn(v[i + 4])) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[i + 5])) << 16);
+              p.w = __bfloat16_as_ushort(__float2bfloat16_rn(v[i + 6])) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[i + 7])) << 16);
+              *reinterpret_cast<uint4*>(o + i) = p;
+            }
+          } else if constexpr (EPI == TC_BF16_IMAGE_RELU) {
+            uint8_t* img = reinterpret_cast<uint8_t*>(out);
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              uint4 p;
+              auto pk = [](float a, float b) {
+                return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(fmaxf(a, 0.f))) |
+                       ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(fmaxf(b, 0.f))) << 16);
+              };
+              p.x = pk(v[i], v[i + 1]); p.y = pk(v[i + 2], v[i + 3]); p.z = pk(v[i + 4], v[i + 5]); p.w = pk(v[i + 6], v[i + 7]);
+              *reinterpret_cast<uint4*>(img + tile_image_offset(row, n0 + i, N)) = p;
+            }
+          } else if constexpr (EPI == TC_F32_RESIDUAL) {
+            float* o = reinterpret_cast<float*>(out) + row * ldc + n0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              float4 r = *reinterpret_cast<const float4*>(o + i);
+              r.x += v[i]; r.y += v[i + 1]; r.z += v[i + 2]; r.w += v[i + 3];
+              *reinterpret_cast<float4*>(o + i) = r;
+            }
+          } else {
+            float* o = reinterpret_cast<float*>(out) + row * ldc + n0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+template <int BN, int EPI>
+static void tc_launch(const bf16* A, const bf16* W, const float* bias, void* out, int64_t ldc, int64_t M, int N, int K,
+                      cudaStream_t st) {
+  using Cfg = TcCfg<BN>;
+  static bool attr_done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev & 63]) {
+    cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    attr_done[dev & 63] = true;
+  }
+  const int tiles = (int)((M + 127) / 128) * (N / BN);
+  const int grid = tiles < kSMs ? tiles : kSMs;
+  gemm_tc_kernel<BN, EPI><<<grid, 192, Cfg::kSmemBytes, st>>>(A, W, bias, out, ldc, M, N, K);
+}
+
+// epi: TcEpi.  N % 256 == 0 uses 128x256 tiles (shared-memory read rate of the A/B operands stays under
+// 128 B/clk/SM), otherwise 128x128.  K % 64 == 0.  A and W are tile images; M is padded to 128 by the caller's
+// allocation (rows >= M are never stored).
+void launch_gemm_tc(const void* A_img, const void* W_img, const float* bias, void* out, int64_t ldc, int64_t M, int N,
+                    int K, int epi, cudaStream_t st) {
+  if (M <= 0) return;
+  const bf16* A = (const bf16*)A_img;
+  const bf16* W = (const bf16*)W_img;
+#define VX_TC(BN_)                                                                                      \
+  switch (epi) {                                                                                        \
+    case TC_BF16_ROW: tc_launch<BN_, TC_BF16_ROW>(A, W, bias, out, ldc, M, N, K, st); break;            \
+    case TC_F32_RESIDUAL: tc_launch<BN_, TC_F32_RESIDUAL>(A, W, bias, out, ldc, M, N, K, st); break;    \
+    case TC_BF16_IMAGE_RELU: tc_launch<BN_, TC_BF16_IMAGE_RELU>(A, W, bias, out, ldc, M, N, K, st); break; \
+    default: tc_launch<BN_, TC_F32>(A, W, bias, out, ldc, M, N, K, st); break;                         \
+  }
+  if (N % 256 == 0) { VX_TC(256) } else { VX_TC(128) }
+#undef VX_TC
+}
+
+// ---- operand packing -------------------------------------------------------------------------------
+// fp32 row-major [rows, K] -> bf16 tile image (rows padded to 128 with zeros).  Used once per weight at load.
+__global__ void pack_tile_image_kernel(const float* __restrict__ src, int64_t rows, int K, uint8_t* __restrict__ img,
+                                       int64_t rows_pad) {
+  const int64_t chunk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte chunk (8 elements)
+  const int64_t total = rows_pad * (K >> 3);
+  if (chunk >= total) return;
+  const int64_t r = chunk / (K >> 3);
+  const int k = (int)(chunk % (K >> 3)) * 8;
+  uint4 p = make_uint4(0, 0, 0, 0);
+  if (r < rows) {
+    float v[8];
+    load8(src + r * K + k, v);
+    auto pk = [](float a, float b) {
+      return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(b)) << 16);
+    };
+    p.x = pk(v[0], v[1]); p.y = pk(v[2], v[3]); p.z = pk(v[4], v[5]); p.w = pk(v[6], v[7]);
+  }
+  *reinterpret_cast<uint4*>(img + tile_image_offset(r, k, K)) = p;
+}
+void launch_pack_tile_image(const float* src, int64_t rows, int K, void* img, cudaStream_t st) {
+  const int64_t rows_pad = (rows + 127) / 128 * 128;
+  const int64_t total = rows_pad * (K >> 3);
+  pack_tile_image_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, rows, K, (uint8_t*)img, rows_pad);
+}
+
+// LayerNorm / AdaLN rows -> bf16 tile image (the A operand of the next GEMM); same math as layernorm_kernel.
+__global__ void __launch_bounds__(128) layernorm_image_kernel(const float* __restrict__ x,
+                                                              const int32_t* __restrict__ row_map,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta,
+                                                              const float* __restrict__ ada_w,
+                                                              const float* __restrict__ ada_b, float eps,
+                                                              uint8_t* __restrict__ img) {
+  __shared__ float red[32];
+  const int64_t r = blockIdx.x;
+  const int64_t src = row_map ? row_map[r] : r;
+  const int c0 = threadIdx.x * 8;  // 128 threads x 8 = 1024
+  float v[8];
+  {
+    const float4 a = *reinterpret_cast<const float4*>(x + src * kD + c0);
+    const float4 b = *reinterpret_cast<const float4*>(x + src * kD + c0 + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += v[i];
+  const float mean = block_sum(s, red) / (float)kD;
+  float qv = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; qv += d * d; }
+  const float rstd = 1.0f / sqrtf(block_sum(qv, red) / (float)kD + eps);
+  float y[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float t = (v[i] - mean) * rstd;
+    t = t * gamma[c0 + i] + beta[c0 + i];
+    if (ada_w) t = ada_w[c0 + i] * t + ada_b[c0 + i];
+    y[i] = t;
+  }
+  auto pk = [](float a, float b) {
+    return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(b)) << 16);
+  };
+  uint4 p;
+  p.x = pk(y[0], y[1]); p.y = pk(y[2], y[3]); p.z = pk(y[4], y[5]); p.w = pk(y[6], y[7]);
+  *reinterpret_cast<uint4*>(img + tile_image_offset(r, c0, kD)) = p;
+}
+void launch_layernorm_image(const float* x, const int32_t* row_map, int64_t rows, const float* gamma,
+                            const float* beta, const float* ada_w, const float* ada_b, float eps, void* img,
+                            cudaStream_t st) {
+  if (rows <= 0) return;
+  layernorm_image_kernel<<<(unsigned)rows, 128, 0, st>>>(x, row_map, gamma, beta, ada_w, ada_b, eps, (uint8_t*)img);
+}
+
+}  // namespace vx

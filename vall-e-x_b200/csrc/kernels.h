@@ -79,6 +79,19 @@ void launch_kv_scatter(const Batch& bt, const float* qkv, void* kcache, void* vc
 void launch_attn_decode(const Batch& bt, const float* qkv_step, void* kcache, void* vcache, int kvt, int ctx_cap,
                         float* out, float* partial, int32_t* tickets, int nsplit, cudaStream_t st);
 
+// ---- bf16 tensor-core path (tcgen05 GEMM, mma.sync attention); operands are "tile images" (tc_common.cuh) ----
+enum TcEpilogue { TC_EPI_BF16_ROW = 0, TC_EPI_F32_RESIDUAL = 1, TC_EPI_BF16_IMAGE_RELU = 2, TC_EPI_F32 = 3 };
+void launch_gemm_tc(const void* A_img, const void* W_img, const float* bias, void* out, int64_t ldc, int64_t M, int N,
+                    int K, int epi, cudaStream_t st);
+void launch_pack_tile_image(const float* src, int64_t rows, int K, void* img, cudaStream_t st);
+void launch_layernorm_image(const float* x, const int32_t* row_map, int64_t rows, const float* gamma,
+                            const float* beta, const float* ada_w, const float* ada_b, float eps, void* img,
+                            cudaStream_t st);
+void launch_attn_tc(const Batch& bt, const void* qkv_bf16, const int32_t* row0, int mode, int max_len, void* out_img,
+                    cudaStream_t st);
+void launch_kv_scatter_bf16(const Batch& bt, const void* qkv_bf16, void* kcache, void* vcache, int max_len, int ctx_cap,
+                            cudaStream_t st);
+
 // ---- sampling (models/vallex.py:791-853, 569-578) ----
 void launch_sample(const Batch& bt, const float* logits, int top_k, float top_p, float temperature, uint64_t seed,
                    int step, int ignore_eos, const int32_t* forced, int forced_stride, int32_t* out_tokens,
