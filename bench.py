@@ -100,6 +100,17 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def _cpu_sample_once(o, ov, xt, yt, Lp, new_tokens):
+    import torch
+    t0 = time.perf_counter()
+    codes = o.inference(xt, torch.tensor([xt.shape[1]]), yt, Lp, top_k=1, temperature=1.0, prompt_language="en",
+                        text_language="en", max_new_tokens=new_tokens)
+    t1 = time.perf_counter()
+    ov.decode(ov.codes_to_features(codes.permute(2, 0, 1)), torch.tensor([2]))
+    t2 = time.perf_counter()
+    return int(codes.shape[1]), t1 - t0, t2 - t1
+
+
 def cpu_reference_sample(new_tokens: int = 48, threads: int = 0) -> dict:
     """The reference's CPU PyTorch path, restated by the oracle port (oracle/vallex_oracle.py, pinned to the
     reference's goldens), on a bounded sample of the same workload: same prompt and 256-phoneme text, AR prefill +
@@ -108,23 +119,28 @@ def cpu_reference_sample(new_tokens: int = 48, threads: int = 0) -> dict:
     from oracle.vallex_oracle import OracleVALLE
     from oracle.vocos_oracle import OracleVocos
     from vallex_b200.weights import synthetic_state_dict, synthetic_vocos_state_dict
-    cores = threads or os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    ncpu = os.cpu_count() or 1
     x, Lp, prompt = workload_inputs()
     o = OracleVALLE(synthetic_state_dict(0))
     ov = OracleVocos(synthetic_vocos_state_dict(0))
     xt = torch.from_numpy(x.astype(np.int64))[None]
     yt = torch.from_numpy(prompt.astype(np.int64))[None]
-    t0 = time.perf_counter()
-    codes = o.inference(xt, torch.tensor([xt.shape[1]]), yt, Lp, top_k=1, temperature=1.0, prompt_language="en",
-                        text_language="en", max_new_tokens=new_tokens)
-    t1 = time.perf_counter()
-    ov.decode(ov.codes_to_features(codes.permute(2, 0, 1)), torch.tensor([2]))
-    t2 = time.perf_counter()
-    T = int(codes.shape[1])
-    return {"value": T / (t2 - t0), "unit": UNIT, "cores": cores, "kind": "port",
+    # The reference would run with torch's default (all cores); tiny per-token ops make that oversubscribed on a
+    # many-core host, so a short probe picks the fastest thread count and the baseline is reported at ITS best.
+    cands = [threads] if threads else sorted({min(ncpu, c) for c in (8, 16, 32, ncpu)})
+    best, best_rate = cands[0], -1.0
+    if len(cands) > 1:
+        for c in cands:
+            torch.set_num_threads(c)
+            T, ta, tv = _cpu_sample_once(o, ov, xt, yt, Lp, 4)
+            if T / (ta + tv) > best_rate:
+                best, best_rate = c, T / (ta + tv)
+    torch.set_num_threads(best)
+    T, ta, tv = _cpu_sample_once(o, ov, xt, yt, Lp, new_tokens)
+    return {"value": T / (ta + tv), "unit": UNIT, "cores": best, "kind": "port",
             "sample": f"S=314 (Lp=58+256), P=225, AR prefill + {T} greedy steps + 7 NAR passes + Vocos on {T} frames "
-                      f"(AR+NAR {t1 - t0:.2f}s, Vocos {t2 - t1:.2f}s); fp32 torch CPU; reference cannot batch (models/vallex.py:491)"}
+                      f"(AR+NAR {ta:.2f}s, Vocos {tv:.2f}s); fp32 torch CPU, {best} of {ncpu} threads (fastest of {cands}); "
+                      f"reference cannot batch (models/vallex.py:491)"}
 
 
 def main():
@@ -136,7 +152,12 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-sample-tokens", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
+    ap.add_argument("--t-new", type=int, default=T_NEW, help="profiling runs only: shorter forced length")
+    ap.add_argument("--min-warmup", type=int, default=3, help="profiling runs only (ncu replays every launch)")
     a = ap.parse_args()
+    global T_NEW
+    T_NEW = a.t_new
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -228,7 +249,7 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(max(a.warmup, 3)):
+    for _ in range(max(a.warmup, a.min_warmup)):
         device_step(False)
     assert int(d_len[0]) == T_NEW
     launches0 = eng.timing()["kernel_launches"]
@@ -265,14 +286,14 @@ def main():
         wave = voc.decode(voc.codes_to_features(frames), bandwidth_id=torch.tensor([2]))
         return codes, wave
 
-    for _ in range(3):
+    for _ in range(0 if a.no_e2e else 3):
         codes, wave = e2e_step()
     sync_all()
     t0 = time.perf_counter()
-    for _ in range(a.steps):
+    for _ in range(0 if a.no_e2e else a.steps):
         codes, wave = e2e_step()
     sync_all()
-    e2e_wall = time.perf_counter() - t0
+    e2e_wall = max(time.perf_counter() - t0, 1e-9)
     e2e_elapsed = max_over_ranks(e2e_wall, dev) if world > 1 else e2e_wall
     e2e_value = world * a.steps * T_NEW / e2e_elapsed
     h2d = int(S * 4 * 2 + P * 8 * 4 + 8 + 8 * T_NEW * 4)   # ids, lang ids, prompt, lens; codes re-uploaded for Vocos
@@ -293,7 +314,7 @@ def main():
     peak, how = peaks()
     ach = bytes_step / t_step / 1e9
     out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, a.min_warmup),
         "ms_per_step": 1e3 * elapsed / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": a.dtype, "data": "synthetic (seeded random-init weights, seeded phonemes; librispeech_1 prompt tokens from the reference's preset)",
         "config": config,
@@ -305,7 +326,7 @@ def main():
                 "ms_per_step": 1e3 * e2e_elapsed / a.steps, "rtf": (e2e_elapsed / a.steps) / (T_NEW / 75.0)},
         "gpu_launches": int(launches),
         "clocks": clk,
-        "roofline": {"kernel": "AR decode step (all kernels of one step; persistent kernel pending)", "bound": "hbm",
+        "roofline": {"kernel": "ar_decode_persistent_kernel (one launch = all decode steps; per-step figures)", "bound": "hbm",
                      "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                      "peak_source": how, "bytes_per_step": bytes_step, "avg_step_us": t_step * 1e6, "mean_ctx": L_mean},
     }

@@ -104,6 +104,18 @@ def test_bf16_teacher_forced_tokens(name):
     assert nar_match[binding & upstream_ok.all(axis=1, keepdims=True)].mean() > 0.995
 
 
+def test_graph_decode_path_matches_persistent(monkeypatch):
+    """VX_DECODE_GRAPH=1 selects the per-step CUDA-graph decode (separate kernels); same tokens as the
+    persistent kernel (and the reference)."""
+    g = load_golden("tiny_en")
+    monkeypatch.setenv("VX_DECODE_GRAPH", "1")
+    m = _valle(state_dict_for(g["seed"]), "fp32", max_ctx=256)
+    got = _infer(m, g)[0].numpy()
+    assert np.array_equal(got, g["codes"].astype(np.int64))
+    assert m.last_timing["kernel_launches"] > 1000   # one graph replay of ~62 kernels per token
+    m.engine.close()
+
+
 def test_max_new_tokens_is_a_prefix():
     g = load_golden("mid_ja")
     got = _infer(model_for(g["seed"], "fp32"), g, max_new_tokens=20)[0].numpy()

@@ -1,0 +1,46 @@
+// Parameter block of the persistent AR decode kernel (decode_persist.cu), filled by engine.cu.
+#pragma once
+#include <stdint.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vx {
+
+struct PLayer {
+  const void *qkv_w, *out_w, *ff1_w, *ff2_w;
+  const float *qkv_b, *out_b, *ff1_b, *ff2_b, *n1_g, *n1_b, *n2_g, *n2_b;
+};
+
+struct PParams {
+  Batch bt;
+  PLayer layer[kL];
+  const float *norm_g, *norm_b;
+  const void* predict_w;
+  const float *audio_emb, *alpha, *pe;
+  void *kc, *vc;              // [layer][b][h][ctx_cap][64]
+  size_t kv_layer_elems;
+  int ctx_cap;
+  // scratch (global, L2 resident)
+  float* xa;                  // [B][1024] residual stream after the attention block
+  float* pf;                  // [4][B][1024] FFN2 split-K partials of the previous layer
+  float* qkv;                 // [B][3072]
+  float* att;                 // [B][1024]
+  float* hid;                 // [B][4096]
+  float* logits;              // [B][1025]
+  float* part;                // [B][16][nsplit][66]
+  int32_t* tickets;           // [B*16]
+  unsigned int* bar;          // grid barrier counter (zeroed by the host)
+  int nsplit;
+  // sampling
+  int top_k; float top_p; float temperature; uint64_t seed; int ignore_eos;
+  const int32_t* forced; int forced_stride; int32_t* out_tokens; int out_stride;
+  int max_steps;
+  int32_t* steps_done;        // [1]
+};
+
+
+// wt: 0 fp32 / 1 bf16 (weights and KV cache).  B <= 32.  Returns a cudaError_t as int.
+int launch_decode_persistent(const void* params, int wt, int B, int grid, cudaStream_t st);
+
+}  // namespace vx

@@ -12,6 +12,7 @@
 
 #include "../../include/vallex_b200.h"
 #include "common.cuh"
+#include "decode_persist.h"
 #include "kernels.h"
 #include "tc_common.cuh"
 
@@ -92,6 +93,9 @@ struct vx_engine {
   Buf x, xn, qkv, att, ffh, kc, vc;                 // prefill / NAR activations, KV cache
   Buf a_img, qkv16, att_img, h_img, t_img;           // bf16 mode: tile-image / bf16 activations
   Buf xs, xsn, qkvs, atts, ffs, logits, part, tick;  // decode-step scratch
+  Buf p_pf, p_bar;                                   // persistent decode: FFN2 partials, barrier counter + steps
+  int num_sms = 148;
+  bool decode_graph = false;                         // VX_DECODE_GRAPH=1: per-step CUDA-graph path instead of the persistent kernel
   Buf lastmap, out_tok, forced, yemb, yrow0, trow0, tgtmap, nlog, codes, tl_dev, cb0_dev;
   Buf v_codes, v_feat, v_col, v_x, v_h, v_ff, v_head, v_spec, v_frames, v_wave;
   int32_t* h_pinned = nullptr;  // small pinned scratch for polling
@@ -344,6 +348,9 @@ int vx_create(int device, int max_batch, int max_ctx, int dtype_mode, vx_engine*
   CK(cudaMallocHost(&e->h_pinned, 4096));
   const char* fs = getenv("VX_FORCE_SIMT");
   e->force_simt = fs && fs[0] == '1';
+  const char* dg = getenv("VX_DECODE_GRAPH");
+  e->decode_graph = dg && dg[0] == '1';
+  e->num_sms = prop.multiProcessorCount;
   *out = e;
   return VX_OK;
 }
@@ -359,7 +366,7 @@ void vx_destroy(vx_engine* e) {
   }
   Buf* bufs[] = {&e->d_text, &e->d_lang, &e->d_prompt, &e->d_S, &e->d_P, &e->d_ar_row0, &e->d_nar_row0, &e->d_T,
                  &e->d_ctx, &e->d_y, &e->d_budget, &e->d_fin, &e->d_slp, &e->d_nact, &e->x, &e->xn, &e->qkv, &e->att,
-                 &e->ffh, &e->kc, &e->vc, &e->a_img, &e->qkv16, &e->att_img, &e->h_img, &e->t_img, &e->xs, &e->xsn, &e->qkvs, &e->atts, &e->ffs, &e->logits, &e->part, &e->tick,
+                 &e->ffh, &e->kc, &e->vc, &e->a_img, &e->qkv16, &e->att_img, &e->h_img, &e->t_img, &e->xs, &e->xsn, &e->qkvs, &e->atts, &e->ffs, &e->logits, &e->part, &e->tick, &e->p_pf, &e->p_bar,
                  &e->lastmap, &e->out_tok, &e->forced, &e->yemb, &e->yrow0, &e->trow0, &e->tgtmap, &e->nlog, &e->codes,
                  &e->tl_dev, &e->cb0_dev, &e->v_codes, &e->v_feat, &e->v_col, &e->v_x, &e->v_h, &e->v_ff, &e->v_head,
                  &e->v_spec, &e->v_frames, &e->v_wave};
@@ -749,6 +756,51 @@ int vx_ar_decode(vx_engine* e, int max_new, int top_k, float top_p, float temper
   CK(cudaMemsetAsync(e->out_tok.p, 0, (size_t)B * max_steps * 4, st));
   CK(cudaStreamSynchronize(st));  // h_pinned reused below
   const int32_t* forced_dev = forced_tokens ? (const int32_t*)e->forced.p : nullptr;
+
+  if (!e->decode_graph && B <= 32) {
+    // ---- persistent kernel: the whole token loop in one cooperative launch -------------------------------
+    int ns = std::max(1, e->num_sms / (B * kH));
+    ns = std::max(ns, (final_ctx + 2047) / 2048);
+    ns = std::min(ns, 64);
+    ENS(e->part, (size_t)B * kH * ns * (kDH + 2) * 4);
+    ENS(e->p_pf, (size_t)4 * B * kD * 4);
+    ENS(e->p_bar, 64);
+    CK(cudaMemsetAsync(e->p_bar.p, 0, 64, st));
+    PParams pp{};
+    pp.bt = e->bt;
+    for (int l = 0; l < kL; ++l) {
+      const LayerW& L = e->ar[l];
+      pp.layer[l] = PLayer{L.qkv_w, L.out_w, L.ff1_w, L.ff2_w, L.qkv_b, L.out_b, L.ff1_b, L.ff2_b, L.n1_g, L.n1_b, L.n2_g, L.n2_b};
+    }
+    pp.norm_g = e->ar_norm_g; pp.norm_b = e->ar_norm_b; pp.predict_w = e->ar_predict;
+    pp.audio_emb = vec(e, "ar_audio_embedding.word_embeddings.weight"); pp.alpha = vec(e, "ar_audio_position.alpha"); pp.pe = e->pe;
+    pp.kc = e->kc.p; pp.vc = e->vc.p; pp.kv_layer_elems = e->kv_layer_elems; pp.ctx_cap = e->ctx_cap;
+    pp.xa = (float*)e->xs.p; pp.pf = (float*)e->p_pf.p; pp.qkv = (float*)e->qkvs.p; pp.att = (float*)e->atts.p;
+    pp.hid = (float*)e->ffs.p; pp.logits = (float*)e->logits.p; pp.part = (float*)e->part.p; pp.tickets = (int32_t*)e->tick.p;
+    pp.bar = (unsigned int*)e->p_bar.p; pp.nsplit = ns;
+    pp.top_k = top_k; pp.top_p = top_p; pp.temperature = temperature; pp.seed = seed; pp.ignore_eos = ignore_eos;
+    pp.forced = forced_dev; pp.forced_stride = max_steps; pp.out_tokens = (int32_t*)e->out_tok.p; pp.out_stride = max_steps;
+    pp.max_steps = max_steps; pp.steps_done = (int32_t*)((char*)e->p_bar.p + 32);
+    CK(cudaEventRecord(e->ev0, st));
+    const int rc = launch_decode_persistent(&pp, e->mode, B, e->num_sms, st);
+    if (rc != 0) return fail(VX_ERR_CUDA, std::string("persistent decode launch: ") + cudaGetErrorString((cudaError_t)rc));
+    e->launches++;
+    CK(cudaEventRecord(e->ev1, st));
+    CK(cudaMemcpyAsync(e->h_pinned, pp.steps_done, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&e->ms_decode, e->ev0, e->ev1));
+    e->decode_steps = e->h_pinned[0];
+    CK(cudaGetLastError());
+    int r2;
+    if (out_tokens && (r2 = copy_out(out_tokens, e->out_tok.p, (size_t)B * max_steps * 4, mem, st))) return r2;
+    if (out_lens && (r2 = copy_out(out_lens, e->d_T.p, B * 4, mem, st))) return r2;
+    if (out_sum_logprobs && (r2 = copy_out(out_sum_logprobs, e->d_slp.p, B * 4, mem, st))) return r2;
+    e->hT.assign(B, 0);
+    CK(cudaMemcpyAsync(e->hT.data(), e->d_T.p, B * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    e->decoded = true;
+    return VX_OK;
+  }
 
   // capture one iteration [sample -> forward] into a CUDA graph; kernels read all step state from the device
   cudaGraph_t graph = nullptr;
