@@ -156,8 +156,7 @@ def main():
     ap.add_argument("--t-new", type=int, default=T_NEW, help="profiling runs only: shorter forced length")
     ap.add_argument("--min-warmup", type=int, default=3, help="profiling runs only (ncu replays every launch)")
     a = ap.parse_args()
-    global T_NEW
-    T_NEW = a.t_new
+    globals()["T_NEW"] = a.t_new
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
