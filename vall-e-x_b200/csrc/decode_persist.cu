@@ -39,10 +39,11 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& ep
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
     unsigned int v;
     unsigned int spins = 0;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+    do {  // relaxed polling (no per-iteration L1 invalidate), one acquire fence at the end
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
       if (++spins > (1u << 26)) __trap();  // a lost CTA must not hang the box
     } while ((int)(v - epoch) < 0);
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
   }
   __syncthreads();
 }
@@ -94,74 +95,171 @@ __device__ __forceinline__ void ldw8(const float* p, float (&o)[8]) {
   o[4] = __uint_as_float(b.x); o[5] = __uint_as_float(b.y); o[6] = __uint_as_float(b.z); o[7] = __uint_as_float(b.w);
 }
 
-// rows [r0,r1) of W[*,1024] (row stride ldw elements) against sx[MR][1024] (shared); emit(n, acc[MR]) on lane 0.
-template <typename WT, int MR, typename Emit>
-__device__ __forceinline__ void gemv_rows(const WT* __restrict__ W, size_t ldw, int r0, int r1,
-                                          const float* __restrict__ sx, Emit emit) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr bool kTwo = MR <= 8;  // two rows in flight per warp while the accumulators fit in registers
-  for (int n = r0 + warp; n < r1; n += (kTwo ? 2 : 1) * PNW) {
-    const int n2 = n + PNW;
-    const bool two = kTwo && n2 < r1;
-    float w0[4][8], w1[4][8];
-    const WT* p0 = W + (size_t)n * ldw + lane * 8;
-    const WT* p1 = W + (size_t)(two ? n2 : n) * ldw + lane * 8;
+// ---- weight-streaming GEMV with cross-barrier register prefetch ---------------------------------------------
+// A CTA's row slice of one matrix is at most 2 rows per warp (148 CTAs x 16 warps), so a phase's weights fit in
+// registers: they are requested BEFORE the preceding grid barrier (the weights do not depend on it) and consumed
+// after it, which takes the HBM latency of every GEMV phase off the critical path.
+template <typename WT, int MR>
+struct WPre {
+  static constexpr int kRows = (sizeof(WT) == 2 && MR <= 8) ? 2 : 1;
+  static constexpr int kVec = (sizeof(WT) == 2) ? 4 : 8;  // uint4 per row per lane (K = 1024)
+  uint4 r[kRows][kVec];
+};
+
+__device__ __forceinline__ uint4 ldw_raw(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+template <typename WT>
+__device__ __forceinline__ void raw_to_f32(const uint4* v, int it, float (&o)[8]);
+template <>
+__device__ __forceinline__ void raw_to_f32<bf16>(const uint4* v, int it, float (&o)[8]) {
+  const uint32_t w[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
 #pragma unroll
-    for (int it = 0; it < 4; ++it) ldw8(p0 + it * 256, w0[it]);
-    if (kTwo) {
+  for (int i = 0; i < 4; ++i) { o[2 * i] = __uint_as_float(w[i] << 16); o[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+template <>
+__device__ __forceinline__ void raw_to_f32<float>(const uint4* v, int it, float (&o)[8]) {
+  o[0] = __uint_as_float(v[2 * it].x); o[1] = __uint_as_float(v[2 * it].y); o[2] = __uint_as_float(v[2 * it].z); o[3] = __uint_as_float(v[2 * it].w);
+  o[4] = __uint_as_float(v[2 * it + 1].x); o[5] = __uint_as_float(v[2 * it + 1].y); o[6] = __uint_as_float(v[2 * it + 1].z); o[7] = __uint_as_float(v[2 * it + 1].w);
+}
+
+template <typename WT, int MR>
+__device__ __forceinline__ void load_row_raw(const WT* __restrict__ W, size_t ldw, int n, uint4 (&dst)[WPre<WT, MR>::kVec]) {
+  const int lane = threadIdx.x & 31;
+  const WT* p = W + (size_t)n * ldw + lane * 8;
 #pragma unroll
-      for (int it = 0; it < 4; ++it) ldw8(p1 + it * 256, w1[it]);
-    }
-    float a0[MR], a1[MR];
-#pragma unroll
-    for (int m = 0; m < MR; ++m) { a0[m] = 0.f; a1[m] = 0.f; }
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-#pragma unroll
-      for (int m = 0; m < MR; ++m) {
-        const float4 x0 = *reinterpret_cast<const float4*>(&sx[m * kD + it * 256 + lane * 8]);
-        const float4 x1 = *reinterpret_cast<const float4*>(&sx[m * kD + it * 256 + lane * 8 + 4]);
-        const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          a0[m] = fmaf(w0[it][i], xv[i], a0[m]);
-          if (kTwo) a1[m] = fmaf(w1[it][i], xv[i], a1[m]);
-        }
-      }
-    }
-#pragma unroll
-    for (int m = 0; m < MR; ++m) {
-      a0[m] = warp_sum(a0[m]);
-      if (kTwo) a1[m] = warp_sum(a1[m]);
-    }
-    if (lane == 0) {
-      emit(n, a0);
-      if (two) emit(n2, a1);
-    }
+  for (int it = 0; it < 4; ++it) {
+    if constexpr (sizeof(WT) == 2) dst[it] = ldw_raw(p + it * 256);
+    else { dst[2 * it] = ldw_raw(p + it * 256); dst[2 * it + 1] = ldw_raw(p + it * 256 + 4); }
   }
 }
 
-// LayerNorm of B rows held in shared memory (in place), eps 1e-5.  All threads call.
-template <int MR>
-__device__ __forceinline__ void ln_rows_smem(float* sx, int B, const float* __restrict__ g, const float* __restrict__ bta,
-                                             float* red) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  (void)red;
-  for (int m = warp; m < B; m += PNW) {  // one warp per row: 32 values per lane
-    float v[32], s = 0.f;
+// request this warp's first rows of slice [r0,r1)
+template <typename WT, int MR>
+__device__ __forceinline__ void gemv_issue(WPre<WT, MR>& pre, const WT* __restrict__ W, size_t ldw, int r0, int r1) {
+  const int warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) { v[i] = sx[m * kD + lane + i * 32]; s += v[i]; }
-    const float mean = warp_sum(s) / (float)kD;
-    float q = 0.f;
+  for (int j = 0; j < WPre<WT, MR>::kRows; ++j) {
+    const int n = r0 + warp + j * PNW;
+    if (n < r1) load_row_raw<WT, MR>(W, ldw, n, pre.r[j]);
+  }
+}
+
+template <typename WT, int MR>
+__device__ __forceinline__ void row_dot(const uint4 (&raw)[WPre<WT, MR>::kVec], const float* __restrict__ sx, float (&acc)[MR]) {
+  const int lane = threadIdx.x & 31;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) { const float d = v[i] - mean; q += d * d; }
-    const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)kD + 1e-5f);
+  for (int m = 0; m < MR; ++m) acc[m] = 0.f;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int c = lane + i * 32;
-      sx[m * kD + c] = __fadd_rn(__fmul_rn((v[i] - mean) * rstd, g[c]), bta[c]);
+  for (int it = 0; it < 4; ++it) {
+    float w[8];
+    raw_to_f32<WT>(raw, it, w);
+#pragma unroll
+    for (int m = 0; m < MR; ++m) {
+      const float4 x0 = *reinterpret_cast<const float4*>(&sx[m * kD + it * 256 + lane * 8]);
+      const float4 x1 = *reinterpret_cast<const float4*>(&sx[m * kD + it * 256 + lane * 8 + 4]);
+      acc[m] = fmaf(w[0], x0.x, acc[m]); acc[m] = fmaf(w[1], x0.y, acc[m]); acc[m] = fmaf(w[2], x0.z, acc[m]); acc[m] = fmaf(w[3], x0.w, acc[m]);
+      acc[m] = fmaf(w[4], x1.x, acc[m]); acc[m] = fmaf(w[5], x1.y, acc[m]); acc[m] = fmaf(w[6], x1.z, acc[m]); acc[m] = fmaf(w[7], x1.w, acc[m]);
     }
   }
+#pragma unroll
+  for (int m = 0; m < MR; ++m) acc[m] = warp_sum(acc[m]);
+}
+
+// consume the prefetched rows (and any further rows of the slice).  addend(n, m) is evaluated by lane m BEFORE the
+// dot products (its loads overlap them); emit(n, m, value) is called by lane m for batch row m < B.
+template <typename WT, int MR, typename Add, typename Emit>
+__device__ __forceinline__ void gemv_finish(WPre<WT, MR>& pre, const WT* __restrict__ W, size_t ldw, int r0, int r1,
+                                            const float* __restrict__ sx, int B, Add addend, Emit emit) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kRows = WPre<WT, MR>::kRows;
+  float add[kRows];
+#pragma unroll
+  for (int j = 0; j < kRows; ++j) {
+    const int n = r0 + warp + j * PNW;
+    add[j] = (n < r1 && lane < B) ? addend(n, lane) : 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < kRows; ++j) {
+    const int n = r0 + warp + j * PNW;
+    if (n < r1) {
+      float acc[MR];
+      row_dot<WT, MR>(pre.r[j], sx, acc);
+      float mine = 0.f;
+#pragma unroll
+      for (int m = 0; m < MR; ++m)
+        if (lane == m) mine = acc[m];
+      if (lane < B) emit(n, lane, mine + add[j]);
+    }
+  }
+  for (int n = r0 + warp + kRows * PNW; n < r1; n += PNW) {  // only when the grid is smaller than 148 CTAs
+    uint4 raw[WPre<WT, MR>::kVec];
+    load_row_raw<WT, MR>(W, ldw, n, raw);
+    const float ad = (lane < B) ? addend(n, lane) : 0.f;
+    float acc[MR];
+    row_dot<WT, MR>(raw, sx, acc);
+    float mine = 0.f;
+#pragma unroll
+    for (int m = 0; m < MR; ++m)
+      if (lane == m) mine = acc[m];
+    if (lane < B) emit(n, lane, mine + ad);
+  }
+}
+
+// Stage B rows (value(m, c)) into shared memory with LayerNorm (eps 1e-5), all 512 threads, two-pass variance.
+template <int MR, typename Val>
+__device__ __forceinline__ void stage_ln(float* sx, int B, Val value, const float* __restrict__ g,
+                                         const float* __restrict__ bta, float* red /*[2][PNW][8]*/) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float g0 = g[tid], g1 = g[tid + PNT], b0 = bta[tid], b1 = bta[tid + PNT];
+  for (int mb = 0; mb < B; mb += 8) {
+    const int nb = min(8, B - mb);
+    float v0[8], v1[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      v0[m] = (m < nb) ? value(mb + m, tid) : 0.f;
+      v1[m] = (m < nb) ? value(mb + m, tid + PNT) : 0.f;
+    }
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const float s = warp_sum(v0[m] + v1[m]);
+      if (lane == 0) red[warp * 8 + m] = s;
+    }
+    __syncthreads();
+    float mean[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < PNW; ++w) s += red[w * 8 + m];
+      mean[m] = s / (float)kD;
+    }
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const float d0 = v0[m] - mean[m], d1 = v1[m] - mean[m];
+      const float s = warp_sum(d0 * d0 + d1 * d1);
+      if (lane == 0) red[PNW * 8 + warp * 8 + m] = s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      if (m < nb) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < PNW; ++w) s += red[PNW * 8 + w * 8 + m];
+        const float rstd = 1.0f / sqrtf(s / (float)kD + 1e-5f);
+        sx[(mb + m) * kD + tid] = __fadd_rn(__fmul_rn((v0[m] - mean[m]) * rstd, g0), b0);
+        sx[(mb + m) * kD + tid + PNT] = __fadd_rn(__fmul_rn((v1[m] - mean[m]) * rstd, g1), b1);
+      }
+    }
+    __syncthreads();  // red[] is reused by the next chunk; sx complete for the consumers
+  }
+}
+template <typename Val>
+__device__ __forceinline__ void stage_plain(float* sx, int B, Val value) {
+  for (int i = threadIdx.x; i < B * kD; i += PNT) sx[i] = value(i / kD, i % kD);
   __syncthreads();
 }
 
@@ -462,7 +560,7 @@ template <typename WT, int MR>
 __global__ void __launch_bounds__(PNT, 1) ar_decode_persistent_kernel(const PParams p) {
   extern __shared__ __align__(16) float dsm[];
   float* sx = dsm;                       // [MR][1024]
-  float* scratch = dsm + MR * kD;        // attention / sampling scratch
+  float* scratch = dsm + MR * kD;        // attention / sampling / LN-reduction scratch
   const Batch& bt = p.bt;
   const int B = bt.B;
   const int tid = threadIdx.x;
@@ -482,12 +580,15 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_persistent_kernel(const PPar
   const int g0 = (int)(((long long)(blockIdx.x - kc_first) * kD) / kc_n);
   const int g1 = (int)(((long long)(blockIdx.x - kc_first + 1) * kD) / kc_n);
 
+  WPre<WT, MR> pre;
+  const WT* Wqkv0 = reinterpret_cast<const WT*>(p.layer[0].qkv_w);
+  gemv_issue<WT, MR>(pre, Wqkv0, kD, q0, q1);  // layer-0 QKV rows travel while the first token is sampled
+
   int steps = 0;
   for (int step = 0; step < p.max_steps; ++step) {
     // ---- S0: sample, append, embed -------------------------------------------------------------------
     for (int b = blockIdx.x; b < B; b += gridDim.x)
       if (!ld_cg(bt.finished + b)) sample_utterance(p, b, scratch);
-    if (tid == 0) l2_prefetch(reinterpret_cast<const char*>(p.layer[0].qkv_w) + (size_t)q0 * kD * wsz, (size_t)(q1 - q0) * kD * wsz);
     grid_barrier(p.bar, epoch);
     ++steps;
     if (!p.ignore_eos && ld_cg(bt.n_active) <= 0) break;
@@ -495,21 +596,31 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_persistent_kernel(const PPar
 
     for (int l = 0; l < kL; ++l) {
       const PLayer& L = p.layer[l];
-      // ---- P1: LN1 + QKV rows ---------------------------------------------------------------------------
-      if (tid == 0) l2_prefetch(reinterpret_cast<const char*>(L.out_w) + (size_t)o0 * kD * wsz, (size_t)(o1 - o0) * kD * wsz);
-      for (int i = tid; i < B * kD; i += PNT) sx[i] = stream_in(p, l, i / kD, i % kD, B);
-      for (int i = B * kD + tid; i < MR * kD; i += PNT) sx[i] = 0.f;
-      __syncthreads();
-      ln_rows_smem<MR>(sx, B, L.n1_g, L.n1_b, nullptr);
-      gemv_rows<WT, MR>(reinterpret_cast<const WT*>(L.qkv_w), kD, q0, q1, sx, [&](int n, const float (&a)[MR]) {
-        const float bv = L.qkv_b[n];
-#pragma unroll
-        for (int m = 0; m < MR; ++m)
-          if (m < B) p.qkv[(size_t)m * 3 * kD + n] = a[m] + bv;
-      });
+      const WT* Wq = reinterpret_cast<const WT*>(L.qkv_w);
+      const WT* Wo = reinterpret_cast<const WT*>(L.out_w);
+      const WT* W1 = reinterpret_cast<const WT*>(L.ff1_w);
+      const WT* W2 = reinterpret_cast<const WT*>(L.ff2_w) + (size_t)kc * kD;
+      // ---- P1: LN1 + QKV rows; pull this CTA's K/V ranges of the coming attention phase into L2 ----------------
+      for (int u = blockIdx.x; u < B * kH * p.nsplit; u += gridDim.x) {
+        if (tid == 0) {
+          const int split = u % p.nsplit, bh = u / p.nsplit, b = bh / kH, h = bh % kH;
+          const int n = bt.S[b] + bt.P[b] + ld_cg(bt.T + b) + 1;
+          int chunk = (n + p.nsplit - 1) / p.nsplit;
+          chunk = (chunk + 31) & ~31;
+          const int j0 = split * chunk, j1 = min(n - 1, j0 + chunk);
+          if (j1 > j0) {
+            const size_t off = ((size_t)l * p.kv_layer_elems + ((size_t)b * kH + h) * p.ctx_cap * kDH + (size_t)j0 * kDH) * wsz;
+            l2_prefetch(reinterpret_cast<const char*>(p.kc) + off, (size_t)(j1 - j0) * kDH * wsz);
+            l2_prefetch(reinterpret_cast<const char*>(p.vc) + off, (size_t)(j1 - j0) * kDH * wsz);
+          }
+        }
+      }
+      stage_ln<MR>(sx, B, [&](int m, int c) { return stream_in(p, l, m, c, B); }, L.n1_g, L.n1_b, scratch);
+      gemv_finish<WT, MR>(pre, Wq, kD, q0, q1, sx, B, [&](int n, int) { return L.qkv_b[n]; },
+                          [&](int n, int m, float v) { p.qkv[(size_t)m * 3 * kD + n] = v; });
+      gemv_issue<WT, MR>(pre, Wo, kD, o0, o1);   // out-proj rows ride through the attention phase
       grid_barrier(p.bar, epoch);
       // ---- P2: attention ---------------------------------------------------------------------------------
-      if (tid == 0) l2_prefetch(reinterpret_cast<const char*>(L.ff1_w) + (size_t)f0 * kD * wsz, (size_t)(f1 - f0) * kD * wsz);
       for (int u = blockIdx.x; u < B * kH * p.nsplit; u += gridDim.x) {
         const int split = u % p.nsplit, bh = u / p.nsplit;
         const int b = bh / kH, h = bh % kH;
@@ -519,60 +630,36 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_persistent_kernel(const PPar
       }
       grid_barrier(p.bar, epoch);
       // ---- P3: out-proj + residual -> xa -------------------------------------------------------------------
-      for (int i = tid; i < B * kD; i += PNT) sx[i] = __ldcg(p.att + i);
-      for (int i = B * kD + tid; i < MR * kD; i += PNT) sx[i] = 0.f;
       __syncthreads();
-      gemv_rows<WT, MR>(reinterpret_cast<const WT*>(L.out_w), kD, o0, o1, sx, [&](int n, const float (&a)[MR]) {
-        const float bv = L.out_b[n];
-#pragma unroll
-        for (int m = 0; m < MR; ++m)
-          if (m < B) p.xa[(size_t)m * kD + n] = stream_in(p, l, m, n, B) + (a[m] + bv);
-      });
+      stage_plain(sx, B, [&](int m, int c) { return __ldcg(p.att + (size_t)m * kD + c); });
+      gemv_finish<WT, MR>(pre, Wo, kD, o0, o1, sx, B, [&](int n, int m) { return L.out_b[n] + stream_in(p, l, m, n, B); },
+                          [&](int n, int m, float v) { p.xa[(size_t)m * kD + n] = v; });
+      gemv_issue<WT, MR>(pre, W1, kD, f0, f1);
       grid_barrier(p.bar, epoch);
       // ---- P4: LN2 + FFN1 + ReLU -------------------------------------------------------------------------------
-      if (tid < g1 - g0)  // FFN2 slice: one 1024-wide k chunk of rows [g0,g1): a 2-4 KB segment per row
-        l2_prefetch(reinterpret_cast<const char*>(L.ff2_w) + ((size_t)(g0 + tid) * kFF + (size_t)kc * kD) * wsz, (size_t)kD * wsz);
-      for (int i = tid; i < B * kD; i += PNT) sx[i] = __ldcg(p.xa + i);
-      for (int i = B * kD + tid; i < MR * kD; i += PNT) sx[i] = 0.f;
-      __syncthreads();
-      ln_rows_smem<MR>(sx, B, L.n2_g, L.n2_b, nullptr);
-      gemv_rows<WT, MR>(reinterpret_cast<const WT*>(L.ff1_w), kD, f0, f1, sx, [&](int n, const float (&a)[MR]) {
-        const float bv = L.ff1_b[n];
-#pragma unroll
-        for (int m = 0; m < MR; ++m)
-          if (m < B) p.hid[(size_t)m * kFF + n] = fmaxf(a[m] + bv, 0.f);
-      });
+      stage_ln<MR>(sx, B, [&](int m, int c) { return __ldcg(p.xa + (size_t)m * kD + c); }, L.n2_g, L.n2_b, scratch);
+      gemv_finish<WT, MR>(pre, W1, kD, f0, f1, sx, B, [&](int n, int) { return L.ff1_b[n]; },
+                          [&](int n, int m, float v) { p.hid[(size_t)m * kFF + n] = fmaxf(v, 0.f); });
+      gemv_issue<WT, MR>(pre, W2, kFF, g0, g1);
       grid_barrier(p.bar, epoch);
       // ---- P5: FFN2, split-K: rows [g0,g1) x k chunk kc -> partial pf[kc] --------------------------------------
-      if (tid == 0) {
-        const void* nxt = (l + 1 < kL) ? p.layer[l + 1].qkv_w : p.predict_w;
-        const int a0 = (l + 1 < kL) ? q0 : pr0, a1 = (l + 1 < kL) ? q1 : pr1;
-        l2_prefetch(reinterpret_cast<const char*>(nxt) + (size_t)a0 * kD * wsz, (size_t)(a1 - a0) * kD * wsz);
-      }
-      for (int i = tid; i < B * kD; i += PNT) sx[i] = __ldcg(p.hid + (size_t)(i / kD) * kFF + kc * kD + (i % kD));
-      for (int i = B * kD + tid; i < MR * kD; i += PNT) sx[i] = 0.f;
       __syncthreads();
-      gemv_rows<WT, MR>(reinterpret_cast<const WT*>(L.ff2_w) + (size_t)kc * kD, kFF, g0, g1, sx,
-                        [&](int n, const float (&a)[MR]) {
-#pragma unroll
-                          for (int m = 0; m < MR; ++m)
-                            if (m < B) p.pf[((size_t)kc * B + m) * kD + n] = a[m];
-                        });
+      stage_plain(sx, B, [&](int m, int c) { return __ldcg(p.hid + (size_t)m * kFF + kc * kD + c); });
+      gemv_finish<WT, MR>(pre, W2, kFF, g0, g1, sx, B, [&](int, int) { return 0.f; },
+                          [&](int n, int m, float v) { p.pf[((size_t)kc * B + m) * kD + n] = v; });
+      if (l + 1 < kL) gemv_issue<WT, MR>(pre, reinterpret_cast<const WT*>(p.layer[l + 1].qkv_w), kD, q0, q1);
+      else gemv_issue<WT, MR>(pre, reinterpret_cast<const WT*>(p.predict_w), kD, pr0, pr1);
       grid_barrier(p.bar, epoch);
     }
     // ---- PF: final LayerNorm + predict rows -> logits ---------------------------------------------------------
-    for (int i = tid; i < B * kD; i += PNT) sx[i] = stream_in(p, kL, i / kD, i % kD, B);
-    for (int i = B * kD + tid; i < MR * kD; i += PNT) sx[i] = 0.f;
-    __syncthreads();
-    ln_rows_smem<MR>(sx, B, p.norm_g, p.norm_b, nullptr);
-    gemv_rows<WT, MR>(reinterpret_cast<const WT*>(p.predict_w), kD, pr0, pr1, sx, [&](int n, const float (&a)[MR]) {
-#pragma unroll
-      for (int m = 0; m < MR; ++m)
-        if (m < B) p.logits[(size_t)m * kARLogits + n] = a[m];
-    });
+    stage_ln<MR>(sx, B, [&](int m, int c) { return stream_in(p, kL, m, c, B); }, p.norm_g, p.norm_b, scratch);
+    gemv_finish<WT, MR>(pre, reinterpret_cast<const WT*>(p.predict_w), kD, pr0, pr1, sx, B, [&](int, int) { return 0.f; },
+                        [&](int n, int m, float v) { p.logits[(size_t)m * kARLogits + n] = v; });
+    gemv_issue<WT, MR>(pre, Wqkv0, kD, q0, q1);
     grid_barrier(p.bar, epoch);
   }
   if (blockIdx.x == 0 && tid == 0) *p.steps_done = steps;
+  (void)wsz;
 }
 
 template <typename WT, int MR>
