@@ -100,6 +100,9 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+_CPU_CACHE = {}
+
+
 def _cpu_sample_once(o, ov, xt, yt, Lp, new_tokens):
     import torch
     t0 = time.perf_counter()
@@ -121,13 +124,17 @@ def cpu_reference_sample(new_tokens: int = 48, threads: int = 0) -> dict:
     from vallex_b200.weights import synthetic_state_dict, synthetic_vocos_state_dict
     ncpu = os.cpu_count() or 1
     x, Lp, prompt = workload_inputs()
-    o = OracleVALLE(synthetic_state_dict(0))
-    ov = OracleVocos(synthetic_vocos_state_dict(0))
+    if "o" not in _CPU_CACHE:
+        _CPU_CACHE["o"] = OracleVALLE(synthetic_state_dict(0))
+        _CPU_CACHE["ov"] = OracleVocos(synthetic_vocos_state_dict(0))
+    o, ov = _CPU_CACHE["o"], _CPU_CACHE["ov"]
     xt = torch.from_numpy(x.astype(np.int64))[None]
     yt = torch.from_numpy(prompt.astype(np.int64))[None]
     # The reference would run with torch's default (all cores); tiny per-token ops make that oversubscribed on a
     # many-core host, so a short probe picks the fastest thread count and the baseline is reported at ITS best.
     cands = [threads] if threads else sorted({min(ncpu, c) for c in (8, 16, 32, ncpu)})
+    if "threads" in _CPU_CACHE and not threads:
+        cands = [_CPU_CACHE["threads"]]
     best, best_rate = cands[0], -1.0
     if len(cands) > 1:
         for c in cands:
@@ -136,6 +143,7 @@ def cpu_reference_sample(new_tokens: int = 48, threads: int = 0) -> dict:
             if T / (ta + tv) > best_rate:
                 best, best_rate = c, T / (ta + tv)
     torch.set_num_threads(best)
+    _CPU_CACHE["threads"] = best
     T, ta, tv = _cpu_sample_once(o, ov, xt, yt, Lp, new_tokens)
     return {"value": T / (ta + tv), "unit": UNIT, "cores": best, "kind": "port",
             "sample": f"S=314 (Lp=58+256), P=225, AR prefill + {T} greedy steps + 7 NAR passes + Vocos on {T} frames "

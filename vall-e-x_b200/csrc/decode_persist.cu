@@ -32,9 +32,11 @@ constexpr int PCHUNK = 2048;        // max keys per attention unit
 constexpr int PSORT = 2048;
 
 // ---- grid barrier -------------------------------------------------------------------------------------
-__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& epoch) {
+// `prof` (nullable): two clock64 stamps per barrier -- arrival of this CTA, release of the grid
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& epoch, long long*& prof) {
   __syncthreads();
   if (threadIdx.x == 0) {
+    if (prof) *prof++ = clock64();
     epoch += gridDim.x;
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
     unsigned int v;
@@ -44,6 +46,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& ep
       if (++spins > (1u << 26)) __trap();  // a lost CTA must not hang the box
     } while ((int)(v - epoch) < 0);
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    if (prof) *prof++ = clock64();
   }
   __syncthreads();
 }
@@ -584,12 +587,20 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_persistent_kernel(const PPar
   const WT* Wqkv0 = reinterpret_cast<const WT*>(p.layer[0].qkv_w);
   gemv_issue<WT, MR>(pre, Wqkv0, kD, q0, q1);  // layer-0 QKV rows travel while the first token is sampled
 
+  // optional timeline: CTAs 0, grid/2 and grid-1 stamp every barrier of steps [prof_step0, prof_step0 + 4)
+  long long* prof = nullptr;
+  const int prof_slot = (blockIdx.x == 0) ? 0 : (blockIdx.x == gridDim.x / 2) ? 1 : (blockIdx.x == gridDim.x - 1) ? 2 : -1;
+
   int steps = 0;
   for (int step = 0; step < p.max_steps; ++step) {
+    if (p.prof && prof_slot >= 0 && tid == 0) {
+      if (step == p.prof_step0) prof = p.prof + (size_t)prof_slot * 4 * 128;
+      if (step == p.prof_step0 + 4) prof = nullptr;
+    }
     // ---- S0: sample, append, embed -------------------------------------------------------------------
     for (int b = blockIdx.x; b < B; b += gridDim.x)
       if (!ld_cg(bt.finished + b)) sample_utterance(p, b, scratch);
-    grid_barrier(p.bar, epoch);
+    grid_barrier(p.bar, epoch, prof);
     ++steps;
     if (!p.ignore_eos && ld_cg(bt.n_active) <= 0) break;
     if (step == p.max_steps - 1) break;
@@ -619,7 +630,7 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_persistent_kernel(const PPar
       gemv_finish<WT, MR>(pre, Wq, kD, q0, q1, sx, B, [&](int n, int) { return L.qkv_b[n]; },
                           [&](int n, int m, float v) { p.qkv[(size_t)m * 3 * kD + n] = v; });
       gemv_issue<WT, MR>(pre, Wo, kD, o0, o1);   // out-proj rows ride through the attention phase
-      grid_barrier(p.bar, epoch);
+      grid_barrier(p.bar, epoch, prof);
       // ---- P2: attention ---------------------------------------------------------------------------------
       for (int u = blockIdx.x; u < B * kH * p.nsplit; u += gridDim.x) {
         const int split = u % p.nsplit, bh = u / p.nsplit;
@@ -628,20 +639,20 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_persistent_kernel(const PPar
         if (sizeof(WT) == 2) attn_unit<bf16>(p, l, b, h, split, scratch);
         else attn_unit<float>(p, l, b, h, split, scratch);
       }
-      grid_barrier(p.bar, epoch);
+      grid_barrier(p.bar, epoch, prof);
       // ---- P3: out-proj + residual -> xa -------------------------------------------------------------------
       __syncthreads();
       stage_plain(sx, B, [&](int m, int c) { return __ldcg(p.att + (size_t)m * kD + c); });
       gemv_finish<WT, MR>(pre, Wo, kD, o0, o1, sx, B, [&](int n, int m) { return L.out_b[n] + stream_in(p, l, m, n, B); },
                           [&](int n, int m, float v) { p.xa[(size_t)m * kD + n] = v; });
       gemv_issue<WT, MR>(pre, W1, kD, f0, f1);
-      grid_barrier(p.bar, epoch);
+      grid_barrier(p.bar, epoch, prof);
       // ---- P4: LN2 + FFN1 + ReLU -------------------------------------------------------------------------------
       stage_ln<MR>(sx, B, [&](int m, int c) { return __ldcg(p.xa + (size_t)m * kD + c); }, L.n2_g, L.n2_b, scratch);
       gemv_finish<WT, MR>(pre, W1, kD, f0, f1, sx, B, [&](int n, int) { return L.ff1_b[n]; },
                           [&](int n, int m, float v) { p.hid[(size_t)m * kFF + n] = fmaxf(v, 0.f); });
       gemv_issue<WT, MR>(pre, W2, kFF, g0, g1);
-      grid_barrier(p.bar, epoch);
+      grid_barrier(p.bar, epoch, prof);
       // ---- P5: FFN2, split-K: rows [g0,g1) x k chunk kc -> partial pf[kc] --------------------------------------
       __syncthreads();
       stage_plain(sx, B, [&](int m, int c) { return __ldcg(p.hid + (size_t)m * kFF + kc * kD + c); });
@@ -649,14 +660,14 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_persistent_kernel(const PPar
                           [&](int n, int m, float v) { p.pf[((size_t)kc * B + m) * kD + n] = v; });
       if (l + 1 < kL) gemv_issue<WT, MR>(pre, reinterpret_cast<const WT*>(p.layer[l + 1].qkv_w), kD, q0, q1);
       else gemv_issue<WT, MR>(pre, reinterpret_cast<const WT*>(p.predict_w), kD, pr0, pr1);
-      grid_barrier(p.bar, epoch);
+      grid_barrier(p.bar, epoch, prof);
     }
     // ---- PF: final LayerNorm + predict rows -> logits ---------------------------------------------------------
     stage_ln<MR>(sx, B, [&](int m, int c) { return stream_in(p, kL, m, c, B); }, p.norm_g, p.norm_b, scratch);
     gemv_finish<WT, MR>(pre, reinterpret_cast<const WT*>(p.predict_w), kD, pr0, pr1, sx, B, [&](int, int) { return 0.f; },
                         [&](int n, int m, float v) { p.logits[(size_t)m * kARLogits + n] = v; });
     gemv_issue<WT, MR>(pre, Wqkv0, kD, q0, q1);
-    grid_barrier(p.bar, epoch);
+    grid_barrier(p.bar, epoch, prof);
   }
   if (blockIdx.x == 0 && tid == 0) *p.steps_done = steps;
   (void)wsz;

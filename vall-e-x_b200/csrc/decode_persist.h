@@ -37,6 +37,8 @@ struct PParams {
   const int32_t* forced; int forced_stride; int32_t* out_tokens; int out_stride;
   int max_steps;
   int32_t* steps_done;        // [1]
+  long long* prof;            // nullable: [3 CTAs][4 steps][62 barriers][2] clock64 stamps (VX_DECODE_PROF=1)
+  int prof_step0;
 };
 
 

@@ -93,7 +93,7 @@ struct vx_engine {
   Buf x, xn, qkv, att, ffh, kc, vc;                 // prefill / NAR activations, KV cache
   Buf a_img, qkv16, att_img, h_img, t_img;           // bf16 mode: tile-image / bf16 activations
   Buf xs, xsn, qkvs, atts, ffs, logits, part, tick;  // decode-step scratch
-  Buf p_pf, p_bar;                                   // persistent decode: FFN2 partials, barrier counter + steps
+  Buf p_pf, p_bar, p_prof;                                   // persistent decode: FFN2 partials, barrier counter + steps
   int num_sms = 148;
   bool decode_graph = false;                         // VX_DECODE_GRAPH=1: per-step CUDA-graph path instead of the persistent kernel
   Buf lastmap, out_tok, forced, yemb, yrow0, trow0, tgtmap, nlog, codes, tl_dev, cb0_dev;
@@ -366,7 +366,7 @@ void vx_destroy(vx_engine* e) {
   }
   Buf* bufs[] = {&e->d_text, &e->d_lang, &e->d_prompt, &e->d_S, &e->d_P, &e->d_ar_row0, &e->d_nar_row0, &e->d_T,
                  &e->d_ctx, &e->d_y, &e->d_budget, &e->d_fin, &e->d_slp, &e->d_nact, &e->x, &e->xn, &e->qkv, &e->att,
-                 &e->ffh, &e->kc, &e->vc, &e->a_img, &e->qkv16, &e->att_img, &e->h_img, &e->t_img, &e->xs, &e->xsn, &e->qkvs, &e->atts, &e->ffs, &e->logits, &e->part, &e->tick, &e->p_pf, &e->p_bar,
+                 &e->ffh, &e->kc, &e->vc, &e->a_img, &e->qkv16, &e->att_img, &e->h_img, &e->t_img, &e->xs, &e->xsn, &e->qkvs, &e->atts, &e->ffs, &e->logits, &e->part, &e->tick, &e->p_pf, &e->p_bar, &e->p_prof,
                  &e->lastmap, &e->out_tok, &e->forced, &e->yemb, &e->yrow0, &e->trow0, &e->tgtmap, &e->nlog, &e->codes,
                  &e->tl_dev, &e->cb0_dev, &e->v_codes, &e->v_feat, &e->v_col, &e->v_x, &e->v_h, &e->v_ff, &e->v_head,
                  &e->v_spec, &e->v_frames, &e->v_wave};
@@ -781,6 +781,12 @@ int vx_ar_decode(vx_engine* e, int max_new, int top_k, float top_p, float temper
     pp.top_k = top_k; pp.top_p = top_p; pp.temperature = temperature; pp.seed = seed; pp.ignore_eos = ignore_eos;
     pp.forced = forced_dev; pp.forced_stride = max_steps; pp.out_tokens = (int32_t*)e->out_tok.p; pp.out_stride = max_steps;
     pp.max_steps = max_steps; pp.steps_done = (int32_t*)((char*)e->p_bar.p + 32);
+    if (getenv("VX_DECODE_PROF")) {
+      ENS(e->p_prof, 3 * 4 * 128 * 8);
+      CK(cudaMemsetAsync(e->p_prof.p, 0, 3 * 4 * 128 * 8, st));
+      pp.prof = (long long*)e->p_prof.p;
+      pp.prof_step0 = std::max(0, std::min(max_steps - 6, atoi(getenv("VX_DECODE_PROF"))));
+    }
     CK(cudaEventRecord(e->ev0, st));
     const int rc = launch_decode_persistent(&pp, e->mode, B, e->num_sms, st);
     if (rc != 0) return fail(VX_ERR_CUDA, std::string("persistent decode launch: ") + cudaGetErrorString((cudaError_t)rc));
@@ -1016,6 +1022,7 @@ int vx_debug_read(vx_engine* e, const char* what, float* dst, int64_t max_elems,
   else if (k == "nar_logits") { src = e->nlog.p; int64_t tr = 0; for (int t : e->hT) tr += t; n = tr * kVocab; }
   else if (k == "ar_prefill_x") { src = e->x.p; n = (int64_t)e->ar_rows * kD; }
   else if (k == "ada_all") { src = e->ada_all; n = 25 * 7 * 2 * kD; }
+  else if (k == "decode_prof") { src = e->p_prof.p; n = 3 * 4 * 128 * 2; }  // int64 stamps viewed as float pairs
   else return fail(VX_ERR_ARG, "vx_debug_read: unknown item " + k);
   if (!src) return fail(VX_ERR_STATE, "vx_debug_read: item not available yet");
   n = std::min(n, max_elems);
