@@ -41,11 +41,11 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& ep
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
     unsigned int v;
     unsigned int spins = 0;
-    do {  // relaxed polling (no per-iteration L1 invalidate), one acquire fence at the end
+    do {  // relaxed polling (no per-iteration L1 invalidate)
       asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
       if (++spins > (1u << 26)) __trap();  // a lost CTA must not hang the box
     } while ((int)(v - epoch) < 0);
-    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    // no acquire fence: every cross-CTA mutable value is read with ld.global.cg (L2), never through L1
     if (prof) *prof++ = clock64();
   }
   __syncthreads();
@@ -107,7 +107,17 @@ struct WPre {
   static constexpr int kRows = (sizeof(WT) == 2 && MR <= 8) ? 2 : 1;
   static constexpr int kVec = (sizeof(WT) == 2) ? 4 : 8;  // uint4 per row per lane (K = 1024)
   uint4 r[kRows][kVec];
+  float bias[kRows];  // constant addend of each prefetched row (bias [+ previous layer's FFN2 bias]), fetched with the row
 };
+struct LnPre {        // LayerNorm parameters (+ previous layer's FFN2 bias) of this thread's two columns
+  float g0, g1, b0, b1, f0, f1;
+};
+__device__ __forceinline__ void ln_issue(LnPre& lp, const float* __restrict__ g, const float* __restrict__ b,
+                                         const float* __restrict__ fb) {
+  const int t = threadIdx.x;
+  lp.g0 = g[t]; lp.g1 = g[t + PNT]; lp.b0 = b[t]; lp.b1 = b[t + PNT];
+  lp.f0 = fb ? fb[t] : 0.f; lp.f1 = fb ? fb[t + PNT] : 0.f;
+}
 
 __device__ __forceinline__ uint4 ldw_raw(const void* p) {
   uint4 r;
@@ -141,12 +151,18 @@ __device__ __forceinline__ void load_row_raw(const WT* __restrict__ W, size_t ld
 
 // request this warp's first rows of slice [r0,r1)
 template <typename WT, int MR>
-__device__ __forceinline__ void gemv_issue(WPre<WT, MR>& pre, const WT* __restrict__ W, size_t ldw, int r0, int r1) {
+__device__ __forceinline__ void gemv_issue(WPre<WT, MR>& pre, const WT* __restrict__ W, size_t ldw, int r0, int r1,
+                                           const float* __restrict__ bias, const float* __restrict__ bias2) {
   const int warp = threadIdx.x >> 5;
 #pragma unroll
   for (int j = 0; j < WPre<WT, MR>::kRows; ++j) {
     const int n = r0 + warp + j * PNW;
-    if (n < r1) load_row_raw<WT, MR>(W, ldw, n, pre.r[j]);
+    pre.bias[j] = 0.f;
+    if (n < r1) {
+      load_row_raw<WT, MR>(W, ldw, n, pre.r[j]);
+      if (bias) pre.bias[j] = bias[n];
+      if (bias2) pre.bias[j] += bias2[n];
+    }
   }
 }
 
@@ -175,7 +191,8 @@ __device__ __forceinline__ void row_dot(const uint4 (&raw)[WPre<WT, MR>::kVec], 
 // dot products (its loads overlap them); emit(n, m, value) is called by lane m for batch row m < B.
 template <typename WT, int MR, typename Add, typename Emit>
 __device__ __forceinline__ void gemv_finish(WPre<WT, MR>& pre, const WT* __restrict__ W, size_t ldw, int r0, int r1,
-                                            const float* __restrict__ sx, int B, Add addend, Emit emit) {
+                                            const float* __restrict__ sx, int B, const float* __restrict__ bias,
+                                            const float* __restrict__ bias2, Add addend, Emit emit) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kRows = WPre<WT, MR>::kRows;
   float add[kRows];
@@ -194,13 +211,13 @@ __device__ __forceinline__ void gemv_finish(WPre<WT, MR>& pre, const WT* __restr
 #pragma unroll
       for (int m = 0; m < MR; ++m)
         if (lane == m) mine = acc[m];
-      if (lane < B) emit(n, lane, mine + add[j]);
+      if (lane < B) emit(n, lane, mine + (add[j] + pre.bias[j]));
     }
   }
   for (int n = r0 + warp + kRows * PNW; n < r1; n += PNW) {  // only when the grid is smaller than 148 CTAs
     uint4 raw[WPre<WT, MR>::kVec];
     load_row_raw<WT, MR>(W, ldw, n, raw);
-    const float ad = (lane < B) ? addend(n, lane) : 0.f;
+    const float ad = ((lane < B) ? addend(n, lane) : 0.f) + (bias ? bias[n] : 0.f) + (bias2 ? bias2[n] : 0.f);
     float acc[MR];
     row_dot<WT, MR>(raw, sx, acc);
     float mine = 0.f;
@@ -211,50 +228,50 @@ __device__ __forceinline__ void gemv_finish(WPre<WT, MR>& pre, const WT* __restr
   }
 }
 
-// Stage B rows (value(m, c)) into shared memory with LayerNorm (eps 1e-5), all 512 threads, two-pass variance.
+// Stage B rows into shared memory with LayerNorm (eps 1e-5), all 512 threads, two-pass variance.
+// value(m, c) is the dynamic part of the stream; lp.f* (previous layer's FFN2 bias) is added here.
 template <int MR, typename Val>
-__device__ __forceinline__ void stage_ln(float* sx, int B, Val value, const float* __restrict__ g,
-                                         const float* __restrict__ bta, float* red /*[2][PNW][8]*/) {
+__device__ __forceinline__ void stage_ln(float* sx, int B, Val value, const LnPre& lp, float* red /*[2][PNW][8]*/) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const float g0 = g[tid], g1 = g[tid + PNT], b0 = bta[tid], b1 = bta[tid + PNT];
-  for (int mb = 0; mb < B; mb += 8) {
-    const int nb = min(8, B - mb);
-    float v0[8], v1[8];
+  constexpr int R = MR < 8 ? MR : 8;
+  for (int mb = 0; mb < B; mb += R) {
+    const int nb = min(R, B - mb);
+    float v0[R], v1[R];
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
-      v0[m] = (m < nb) ? value(mb + m, tid) : 0.f;
-      v1[m] = (m < nb) ? value(mb + m, tid + PNT) : 0.f;
+    for (int m = 0; m < R; ++m) {
+      v0[m] = (m < nb) ? value(mb + m, tid) + lp.f0 : 0.f;
+      v1[m] = (m < nb) ? value(mb + m, tid + PNT) + lp.f1 : 0.f;
     }
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
+    for (int m = 0; m < R; ++m) {
       const float s = warp_sum(v0[m] + v1[m]);
       if (lane == 0) red[warp * 8 + m] = s;
     }
     __syncthreads();
-    float mean[8];
+    float mean[R];
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
+    for (int m = 0; m < R; ++m) {
       float s = 0.f;
 #pragma unroll
       for (int w = 0; w < PNW; ++w) s += red[w * 8 + m];
       mean[m] = s / (float)kD;
     }
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
+    for (int m = 0; m < R; ++m) {
       const float d0 = v0[m] - mean[m], d1 = v1[m] - mean[m];
       const float s = warp_sum(d0 * d0 + d1 * d1);
       if (lane == 0) red[PNW * 8 + warp * 8 + m] = s;
     }
     __syncthreads();
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
+    for (int m = 0; m < R; ++m) {
       if (m < nb) {
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < PNW; ++w) s += red[PNW * 8 + w * 8 + m];
         const float rstd = 1.0f / sqrtf(s / (float)kD + 1e-5f);
-        sx[(mb + m) * kD + tid] = __fadd_rn(__fmul_rn((v0[m] - mean[m]) * rstd, g0), b0);
-        sx[(mb + m) * kD + tid + PNT] = __fadd_rn(__fmul_rn((v1[m] - mean[m]) * rstd, g1), b1);
+        sx[(mb + m) * kD + tid] = __fadd_rn(__fmul_rn((v0[m] - mean[m]) * rstd, lp.g0), lp.b0);
+        sx[(mb + m) * kD + tid + PNT] = __fadd_rn(__fmul_rn((v1[m] - mean[m]) * rstd, lp.g1), lp.b1);
       }
     }
     __syncthreads();  // red[] is reused by the next chunk; sx complete for the consumers
@@ -267,12 +284,14 @@ __device__ __forceinline__ void stage_plain(float* sx, int B, Val value) {
 }
 
 // residual stream entering a layer: xa (+ previous layer's FFN2 bias and 4 split-K partials, fixed order)
-__device__ __forceinline__ float stream_in(const PParams& p, int l, int b, int c, int B) {
+// (the previous layer's FFN2 bias, a constant, is added from prefetched registers by the callers)
+__device__ __forceinline__ float stream_dyn(const PParams& p, int l, int b, int c, int B) {
   float v = __ldcg(p.xa + (size_t)b * kD + c);
   if (l > 0) {
-    v += p.layer[l - 1].ff2_b[c];
+    float s4 = 0.f;
 #pragma unroll
-    for (int s = 0; s < 4; ++s) v += __ldcg(p.pf + ((size_t)s * B + b) * kD + c);
+    for (int s = 0; s < 4; ++s) s4 += __ldcg(p.pf + ((size_t)s * B + b) * kD + c);
+    v += s4;
   }
   return v;
 }
@@ -307,13 +326,22 @@ __device__ void sample_utterance(const PParams& p, int b, float* smem) {
   }
   __syncthreads();
   const bool need_sort = (p.top_k > 1) || (p.top_p < 1.0f);
-  if (p.top_k == 1) {
+  const bool greedy = (p.top_k == 1);
+  int g_tok = -1;
+  float g_logprob = 0.f;
+  if (greedy) {
+    // top_k == 1 keeps only the maximum (models/vallex.py:803-809): the draw is its index (first one on an exact tie)
+    // and log_softmax over the kept entries is -log(#ties).
     float m = -INFINITY;
     for (int i = tid; i < kARLogits; i += PNT) m = fmaxf(m, v[i]);
     m = block_max(m, red);
+    int first = 0x7fffffff, cnt = 0;
     for (int i = tid; i < kARLogits; i += PNT)
-      if (v[i] < m) v[i] = -INFINITY;
-    __syncthreads();
+      if (v[i] == m) { first = min(first, i); ++cnt; }
+    first = -(int)block_max((float)(-first), red);   // indices < 2^24: exact in fp32
+    cnt = (int)block_sum((float)cnt, red);
+    g_tok = first;
+    g_logprob = -logf((float)cnt);
   }
   if (need_sort) {
     for (int i = tid; i < PSORT; i += PNT) { sv[i] = (i < kARLogits) ? v[i] : -INFINITY; sidx[i] = (int16_t)i; }
@@ -360,9 +388,14 @@ __device__ void sample_utterance(const PParams& p, int b, float* smem) {
     }
   }
   float m = -INFINITY;
+  if (!greedy) {
   for (int i = tid; i < kARLogits; i += PNT) m = fmaxf(m, v[i]);
   m = block_max(m, red);
+  }
   constexpr int CH = (kARLogits + PNT - 1) / PNT;  // 3
+  float Z = 1.f;
+  const int Tb = ld_cg(bt.T + b);
+  if (!greedy) {
   float loc[CH], s = 0.f;
 #pragma unroll
   for (int q = 0; q < CH; ++q) {
@@ -390,8 +423,7 @@ __device__ void sample_utterance(const PParams& p, int b, float* smem) {
   }
   if (tid == 0) *s_tok = -1;
   __syncthreads();
-  const float Z = red[0];
-  const int Tb = ld_cg(bt.T + b);
+  Z = red[0];
   const float u = p_philox(p.seed, (uint32_t)Tb, (uint32_t)b) * Z;
   {
     float c = scan[tid];
@@ -405,12 +437,16 @@ __device__ void sample_utterance(const PParams& p, int b, float* smem) {
     if (cand >= 0) atomicMax(s_tok, cand);
   }
   __syncthreads();
+  } else {
+    if (tid == 0) *s_tok = g_tok;
+    __syncthreads();
+  }
   if (tid == 0) {
     int tok = *s_tok;
     if (tok < 0)
       for (int i = kARLogits - 1; i >= 0; --i)
         if (v[i] > -INFINITY) { tok = i; break; }
-    const float logprob = (v[tok] - m) - logf(Z);
+    const float logprob = greedy ? g_logprob : (v[tok] - m) - logf(Z);
     const int prev = ld_cg(bt.y + (size_t)b * bt.ymax + bt.P[b] + Tb);
     if (prev != kEOS) bt.sum_logprobs[b] += logprob;
     p.out_tokens[(size_t)b * p.out_stride + Tb] = tok;
@@ -528,34 +564,26 @@ __device__ void attn_unit(const PParams& p, int layer, int b, int h, int split, 
   if (tid < kDH) {
     for (int q = 0; q < NG; ++q) od += sacc[q * kDH + tid];
   }
-  float* dst = p.att + (size_t)b * kD + h * kDH;
-  if (p.nsplit == 1) {
-    if (tid < kDH) dst[tid] = od / l;
-    return;
-  }
+  // partial (m, l, o[64]) of this split; the out-proj phase folds the splits while staging (att_combined)
   float* pp = p.part + (((size_t)b * kH + h) * p.nsplit + split) * (kDH + 2);
   if (tid < kDH) pp[2 + tid] = od;
   if (tid == 0) { pp[0] = m; pp[1] = l; }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) *s_last = (atomicAdd(&p.tickets[b * kH + h], 1) == p.nsplit - 1);
-  __syncthreads();
-  if (!*s_last) return;
-  __threadfence();
+}
+
+// softmax-combine the key splits of head c/64 for column c (fixed order -> deterministic)
+__device__ __forceinline__ float att_combined(const PParams& p, int b, int c) {
+  const int h = c >> 6, d = c & 63;
   const float* p0 = p.part + ((size_t)b * kH + h) * p.nsplit * (kDH + 2);
   float M = -INFINITY;
   for (int s = 0; s < p.nsplit; ++s) M = fmaxf(M, __ldcg(p0 + s * (kDH + 2)));
-  if (tid < kDH) {
-    float L = 0.f, O = 0.f;
-    for (int s = 0; s < p.nsplit; ++s) {
-      const float ms = __ldcg(p0 + s * (kDH + 2));
-      const float w = (ms == -INFINITY) ? 0.f : expf(ms - M);
-      L += w * __ldcg(p0 + s * (kDH + 2) + 1);
-      O += w * __ldcg(p0 + s * (kDH + 2) + 2 + tid);
-    }
-    dst[tid] = O / L;
+  float L = 0.f, O = 0.f;
+  for (int s = 0; s < p.nsplit; ++s) {
+    const float ms = __ldcg(p0 + s * (kDH + 2));
+    const float w = (ms == -INFINITY) ? 0.f : expf(ms - M);
+    L += w * __ldcg(p0 + s * (kDH + 2) + 1);
+    O += w * __ldcg(p0 + s * (kDH + 2) + 2 + d);
   }
-  if (tid == 0) p.tickets[b * kH + h] = 0;
+  return O / L;
 }
 
 // ---- the kernel -------------------------------------------------------------------------------------------
@@ -584,8 +612,11 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_persistent_kernel(const PPar
   const int g1 = (int)(((long long)(blockIdx.x - kc_first + 1) * kD) / kc_n);
 
   WPre<WT, MR> pre;
+  LnPre lp;
   const WT* Wqkv0 = reinterpret_cast<const WT*>(p.layer[0].qkv_w);
-  gemv_issue<WT, MR>(pre, Wqkv0, kD, q0, q1);  // layer-0 QKV rows travel while the first token is sampled
+  // everything that does not depend on a barrier is requested BEFORE it: weight rows, their biases, LN parameters
+  gemv_issue<WT, MR>(pre, Wqkv0, kD, q0, q1, p.layer[0].qkv_b, nullptr);
+  ln_issue(lp, p.layer[0].n1_g, p.layer[0].n1_b, nullptr);
 
   // optional timeline: CTAs 0, grid/2 and grid-1 stamp every barrier of steps [prof_step0, prof_step0 + 4)
   long long* prof = nullptr;
@@ -607,6 +638,7 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_persistent_kernel(const PPar
 
     for (int l = 0; l < kL; ++l) {
       const PLayer& L = p.layer[l];
+      const float* fb_prev = (l > 0) ? p.layer[l - 1].ff2_b : nullptr;
       const WT* Wq = reinterpret_cast<const WT*>(L.qkv_w);
       const WT* Wo = reinterpret_cast<const WT*>(L.out_w);
       const WT* W1 = reinterpret_cast<const WT*>(L.ff1_w);
@@ -626,10 +658,10 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_persistent_kernel(const PPar
           }
         }
       }
-      stage_ln<MR>(sx, B, [&](int m, int c) { return stream_in(p, l, m, c, B); }, L.n1_g, L.n1_b, scratch);
-      gemv_finish<WT, MR>(pre, Wq, kD, q0, q1, sx, B, [&](int n, int) { return L.qkv_b[n]; },
+      stage_ln<MR>(sx, B, [&](int m, int c) { return stream_dyn(p, l, m, c, B); }, lp, scratch);
+      gemv_finish<WT, MR>(pre, Wq, kD, q0, q1, sx, B, L.qkv_b, nullptr, [&](int, int) { return 0.f; },
                           [&](int n, int m, float v) { p.qkv[(size_t)m * 3 * kD + n] = v; });
-      gemv_issue<WT, MR>(pre, Wo, kD, o0, o1);   // out-proj rows ride through the attention phase
+      gemv_issue<WT, MR>(pre, Wo, kD, o0, o1, L.out_b, fb_prev);   // out-proj rows ride through the attention phase
       grid_barrier(p.bar, epoch, prof);
       // ---- P2: attention ---------------------------------------------------------------------------------
       for (int u = blockIdx.x; u < B * kH * p.nsplit; u += gridDim.x) {
@@ -640,33 +672,39 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_persistent_kernel(const PPar
         else attn_unit<float>(p, l, b, h, split, scratch);
       }
       grid_barrier(p.bar, epoch, prof);
-      // ---- P3: out-proj + residual -> xa -------------------------------------------------------------------
-      __syncthreads();
-      stage_plain(sx, B, [&](int m, int c) { return __ldcg(p.att + (size_t)m * kD + c); });
-      gemv_finish<WT, MR>(pre, Wo, kD, o0, o1, sx, B, [&](int n, int m) { return L.out_b[n] + stream_in(p, l, m, n, B); },
+      // ---- P3: (combine key splits) + out-proj + residual -> xa ------------------------------------------------
+      stage_plain(sx, B, [&](int m, int c) { return ld_cg(bt.finished + m) ? 0.f : att_combined(p, m, c); });
+      gemv_finish<WT, MR>(pre, Wo, kD, o0, o1, sx, B, L.out_b, fb_prev, [&](int n, int m) { return stream_dyn(p, l, m, n, B); },
                           [&](int n, int m, float v) { p.xa[(size_t)m * kD + n] = v; });
-      gemv_issue<WT, MR>(pre, W1, kD, f0, f1);
+      gemv_issue<WT, MR>(pre, W1, kD, f0, f1, L.ff1_b, nullptr);
+      ln_issue(lp, L.n2_g, L.n2_b, nullptr);
       grid_barrier(p.bar, epoch, prof);
       // ---- P4: LN2 + FFN1 + ReLU -------------------------------------------------------------------------------
-      stage_ln<MR>(sx, B, [&](int m, int c) { return __ldcg(p.xa + (size_t)m * kD + c); }, L.n2_g, L.n2_b, scratch);
-      gemv_finish<WT, MR>(pre, W1, kD, f0, f1, sx, B, [&](int n, int) { return L.ff1_b[n]; },
+      stage_ln<MR>(sx, B, [&](int m, int c) { return __ldcg(p.xa + (size_t)m * kD + c); }, lp, scratch);
+      gemv_finish<WT, MR>(pre, W1, kD, f0, f1, sx, B, L.ff1_b, nullptr, [&](int, int) { return 0.f; },
                           [&](int n, int m, float v) { p.hid[(size_t)m * kFF + n] = fmaxf(v, 0.f); });
-      gemv_issue<WT, MR>(pre, W2, kFF, g0, g1);
+      gemv_issue<WT, MR>(pre, W2, kFF, g0, g1, nullptr, nullptr);
       grid_barrier(p.bar, epoch, prof);
       // ---- P5: FFN2, split-K: rows [g0,g1) x k chunk kc -> partial pf[kc] --------------------------------------
-      __syncthreads();
       stage_plain(sx, B, [&](int m, int c) { return __ldcg(p.hid + (size_t)m * kFF + kc * kD + c); });
-      gemv_finish<WT, MR>(pre, W2, kFF, g0, g1, sx, B, [&](int, int) { return 0.f; },
+      gemv_finish<WT, MR>(pre, W2, kFF, g0, g1, sx, B, nullptr, nullptr, [&](int, int) { return 0.f; },
                           [&](int n, int m, float v) { p.pf[((size_t)kc * B + m) * kD + n] = v; });
-      if (l + 1 < kL) gemv_issue<WT, MR>(pre, reinterpret_cast<const WT*>(p.layer[l + 1].qkv_w), kD, q0, q1);
-      else gemv_issue<WT, MR>(pre, reinterpret_cast<const WT*>(p.predict_w), kD, pr0, pr1);
+      if (l + 1 < kL) {
+        gemv_issue<WT, MR>(pre, reinterpret_cast<const WT*>(p.layer[l + 1].qkv_w), kD, q0, q1, p.layer[l + 1].qkv_b, nullptr);
+        ln_issue(lp, p.layer[l + 1].n1_g, p.layer[l + 1].n1_b, L.ff2_b);
+      } else {
+        gemv_issue<WT, MR>(pre, reinterpret_cast<const WT*>(p.predict_w), kD, pr0, pr1, nullptr, nullptr);
+        ln_issue(lp, p.norm_g, p.norm_b, L.ff2_b);
+      }
       grid_barrier(p.bar, epoch, prof);
     }
     // ---- PF: final LayerNorm + predict rows -> logits ---------------------------------------------------------
-    stage_ln<MR>(sx, B, [&](int m, int c) { return stream_in(p, kL, m, c, B); }, p.norm_g, p.norm_b, scratch);
-    gemv_finish<WT, MR>(pre, reinterpret_cast<const WT*>(p.predict_w), kD, pr0, pr1, sx, B, [&](int, int) { return 0.f; },
+    stage_ln<MR>(sx, B, [&](int m, int c) { return stream_dyn(p, kL, m, c, B); }, lp, scratch);
+    gemv_finish<WT, MR>(pre, reinterpret_cast<const WT*>(p.predict_w), kD, pr0, pr1, sx, B, nullptr, nullptr,
+                        [&](int, int) { return 0.f; },
                         [&](int n, int m, float v) { p.logits[(size_t)m * kARLogits + n] = v; });
-    gemv_issue<WT, MR>(pre, Wqkv0, kD, q0, q1);
+    gemv_issue<WT, MR>(pre, Wqkv0, kD, q0, q1, p.layer[0].qkv_b, nullptr);
+    ln_issue(lp, p.layer[0].n1_g, p.layer[0].n1_b, nullptr);
     grid_barrier(p.bar, epoch, prof);
   }
   if (blockIdx.x == 0 && tid == 0) *p.steps_done = steps;
