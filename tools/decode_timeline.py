@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""Per-phase timeline of the persistent decode kernel (VX_DECODE_PROF=<first step>): for CTAs 0 / grid/2 / grid-1 and 4
-consecutive steps, clock64 at every grid barrier's arrival and release.  Prints mean work time (release of the previous
-barrier -> arrival) and wait time (arrival -> release) per phase in microseconds."""
+"""Per-phase timeline of the persistent decode kernel (VX_DECODE_PROF=<first step>): CTAs 0 / grid/2 / grid-1 stamp
+(tag, clock64) at every grid barrier arrival (1) / release (2) and inside the GEMV phases: after staging (3), after the
+dot products + emit (4), after issuing the next phase's loads (5).  Prints mean segment durations in microseconds."""
+import collections
 import os
 import sys
 
@@ -25,25 +26,28 @@ eng.set_batch([x] * B, [lang] * B, [prompt] * B)
 eng.ar_prefill()
 toks, lens, _ = eng.ar_decode(max_new=1275, top_k=1, ignore_eos=True)
 t = eng.timing()
-print("us/step", 1e3 * t["ms_decode"] / (t["decode_steps"] - 1))
-raw = eng.debug_read("decode_prof", 3 * 4 * 128 * 2).view(np.int64).reshape(3, 4 * 128)
+print("B", B, "us/step", 1e3 * t["ms_decode"] / (t["decode_steps"] - 1))
+raw = eng.debug_read("decode_prof", 3 * 4096 * 2).view(np.int64).reshape(3, 2048, 2)
 mhz = 1965.0
-names = ["S0"] + [f"L{l}.{n}" for l in range(12) for n in ("qkv", "attn", "out", "ff1", "ff2")] + ["PF"]
+names = ["S0"] + [f"{n}" for l in range(12) for n in ("qkv", "attn", "out", "ff1", "ff2")] + ["PF"]
 for c in range(3):
-    st = raw[c]
-    n = int((st != 0).sum()) // 2
-    arr, rel = st[0:2 * n:2], st[1:2 * n:2]
-    work = (arr[1:] - rel[:-1]) / mhz
-    wait = (rel - arr) / mhz
-    per = 62
-    print(f"CTA slot {c}: stamped barriers {n}; mean wait {wait.mean():.2f} us, mean work {work.mean():.2f} us")
+    ev = [(int(tag), int(clk)) for tag, clk in raw[c] if tag != 0]
+    seg = collections.defaultdict(list)
+    phase = 0
+    prev = None
+    for tag, clk in ev:
+        if prev is not None:
+            key = (names[phase % 62], f"{prev[0]}->{tag}")
+            seg[key].append((clk - prev[1]) / mhz)
+        if tag == 2:
+            phase += 1
+        prev = (tag, clk)
+    tot = sum(np.sum(v) for v in seg.values()) / 4.0
+    print(f"CTA slot {c}: {len(ev)} stamps, {tot:.1f} us/step accounted")
     if c == 0:
-        k = (n // per) * per
-        w = work[:k - 1]
-        for i, nm in enumerate(names):
-            idx = [j for j in range(len(w)) if (j + 1) % per == i]
-            widx = [j for j in range(k) if j % per == i]
-            if i in (0, 1, 2, 3, 4, 5, 61) or i % 5 == 1 and i < 12:
-                print(f"  {nm:8s} work {np.mean([w[j] for j in idx]) if idx else float('nan'):6.2f} us   wait {wait[widx].mean():6.2f} us")
-        tot_work = w.reshape(-1)[:].sum() / (k / per)
-        print(f"  per step: work {work[:k-1].sum() / (k / per):.1f} us, wait {wait[:k].sum() / (k / per):.1f} us")
+        agg = collections.defaultdict(list)
+        for (nm, k), v in seg.items():
+            agg[(nm, k)] += v
+        for nm in ("S0", "qkv", "attn", "out", "ff1", "ff2", "PF"):
+            parts = "  ".join(f"{k}:{np.mean(v):5.2f}" for (n2, k), v in sorted(agg.items()) if n2 == nm)
+            print(f"  {nm:5s} {parts}")

@@ -37,7 +37,7 @@ struct PParams {
   const int32_t* forced; int forced_stride; int32_t* out_tokens; int out_stride;
   int max_steps;
   int32_t* steps_done;        // [1]
-  long long* prof;            // nullable: [3 CTAs][4 steps][62 barriers][2] clock64 stamps (VX_DECODE_PROF=1)
+  long long* prof;            // nullable: [3 CTAs][4096] (tag, clock64) pairs of 4 steps (VX_DECODE_PROF=<first step>)
   int prof_step0;
 };
 

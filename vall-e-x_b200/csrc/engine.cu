@@ -782,8 +782,8 @@ int vx_ar_decode(vx_engine* e, int max_new, int top_k, float top_p, float temper
     pp.forced = forced_dev; pp.forced_stride = max_steps; pp.out_tokens = (int32_t*)e->out_tok.p; pp.out_stride = max_steps;
     pp.max_steps = max_steps; pp.steps_done = (int32_t*)((char*)e->p_bar.p + 32);
     if (getenv("VX_DECODE_PROF")) {
-      ENS(e->p_prof, 3 * 4 * 128 * 8);
-      CK(cudaMemsetAsync(e->p_prof.p, 0, 3 * 4 * 128 * 8, st));
+      ENS(e->p_prof, 3 * 4096 * 8);
+      CK(cudaMemsetAsync(e->p_prof.p, 0, 3 * 4096 * 8, st));
       pp.prof = (long long*)e->p_prof.p;
       pp.prof_step0 = std::max(0, std::min(max_steps - 6, atoi(getenv("VX_DECODE_PROF"))));
     }
@@ -1022,7 +1022,7 @@ int vx_debug_read(vx_engine* e, const char* what, float* dst, int64_t max_elems,
   else if (k == "nar_logits") { src = e->nlog.p; int64_t tr = 0; for (int t : e->hT) tr += t; n = tr * kVocab; }
   else if (k == "ar_prefill_x") { src = e->x.p; n = (int64_t)e->ar_rows * kD; }
   else if (k == "ada_all") { src = e->ada_all; n = 25 * 7 * 2 * kD; }
-  else if (k == "decode_prof") { src = e->p_prof.p; n = 3 * 4 * 128 * 2; }  // int64 stamps viewed as float pairs
+  else if (k == "decode_prof") { src = e->p_prof.p; n = 3 * 4096 * 2; }  // int64 stamps viewed as float pairs
   else return fail(VX_ERR_ARG, "vx_debug_read: unknown item " + k);
   if (!src) return fail(VX_ERR_STATE, "vx_debug_read: item not available yet");
   n = std::min(n, max_elems);
