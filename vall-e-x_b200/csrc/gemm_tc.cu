@@ -210,7 +210,10 @@ void launch_gemm_tc(const void* A_img, const void* W_img, const float* bias, voi
     case TC_BF16_IMAGE_RELU: tc_launch<BN_, TC_BF16_IMAGE_RELU>(A, W, bias, out, ldc, M, N, K, st); break; \
     default: tc_launch<BN_, TC_F32>(A, W, bias, out, ldc, M, N, K, st); break;                         \
   }
-  if (N % 256 == 0) { VX_TC(256) } else { VX_TC(128) }
+  // 128x256 tiles keep the operand read rate under the shared-memory limit, but a small problem needs enough tiles to
+  // cover the 148 SMs: fall back to 128x128 when the 256-wide tiling would leave most of the chip idle.
+  const int64_t tiles256 = ((M + 127) / 128) * (N / 256);
+  if (N % 256 == 0 && tiles256 >= kSMs) { VX_TC(256) } else { VX_TC(128) }
 #undef VX_TC
 }
 
