@@ -48,7 +48,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& ep
     unsigned int spins = 0;
     do {  // relaxed polling (no per-iteration L1 invalidate)
       asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
-      if (++spins > (1u << 26)) __trap();  // a lost CTA must not hang the box
+      if (++spins > (1u << 23)) __trap();  // a lost CTA must not hang the box (~seconds)
     } while ((int)(v - epoch) < 0);
     // no acquire fence: every cross-CTA mutable value is read with ld.global.cg (L2), never through L1
     if (prof) { prof[0] = 2; prof[1] = clock64(); prof += 2; }
@@ -522,9 +522,14 @@ __device__ void attn_unit(const PParams& p, int layer, const AttnRange& r, float
 #pragma unroll
   for (int i = 0; i < 8; ++i) qv[i] = sq[dc + i];
   float mloc = -INFINITY;
-  for (int j = j0 + g; j < j1; j += PNT / 8) {
+  for (int jb = j0; jb < j1; jb += PNT / 8) {  // warp-uniform trip count: the shuffles below need every lane
+    const int j = jb + g;
+    const bool valid = j < j1;
     float w[8];
-    if (j == pos) {
+    if (!valid) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w[i] = 0.f;
+    } else if (j == pos) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) w[i] = kv_round<KVT>(sknew[dc + i]);
     } else if (j - j0 < n_staged) {
@@ -538,8 +543,10 @@ __device__ void attn_unit(const PParams& p, int layer, const AttnRange& r, float
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if ((tid & 7) == 0) sp[j - j0] = s;
-    mloc = fmaxf(mloc, s);
+    if (valid) {
+      if ((tid & 7) == 0) sp[j - j0] = s;
+      mloc = fmaxf(mloc, s);
+    }
   }
   const float m = block_max(mloc, red);
   float lloc = 0.f;
