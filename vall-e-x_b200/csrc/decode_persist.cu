@@ -59,6 +59,14 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& ep
 
 __device__ __forceinline__ int ld_cg(const int32_t* p) { return __ldcg(p); }
 
+// VX_DECODE_DBG & 32: record the first non-finite value seen (code = step * 1000 + layer * 10 + site) in steps_done[2..3]
+__device__ __forceinline__ void nan_probe(const PParams& p, int code, float v) {
+  if ((p.dbg & 32) && !(fabsf(v) <= 3.0e38f)) {
+    atomicMin(p.steps_done + 2, code);
+    p.steps_done[3] = __float_as_int(v);
+  }
+}
+
 __device__ __forceinline__ void slice(int total, int& r0, int& r1) {
   r0 = (int)(((long long)blockIdx.x * total) / gridDim.x);
   r1 = (int)(((long long)(blockIdx.x + 1) * total) / gridDim.x);
@@ -70,7 +78,7 @@ struct WPre {
   static constexpr int kRows = (sizeof(WT) == 2) ? (MR <= 4 ? 4 : (MR <= 8 ? 2 : 1)) : (MR <= 4 ? 2 : 1);
   static constexpr int kVec = (sizeof(WT) == 2) ? 4 : 8;  // uint4 per row per lane (K = 1024)
   uint4 r[kRows][kVec];
-  float bias[kRows];  // constant addend of each prefetched row (bias [+ previous layer's FFN2 bias])
+  float bias[kRows], bias2[kRows];  // constant addends of each prefetched row (bias, previous layer's FFN2 bias)
 };
 struct LnPre {  // LayerNorm parameters (+ previous layer's FFN2 bias) of this thread's four columns
   float g[4], b[4], f[4];
@@ -124,10 +132,11 @@ __device__ __forceinline__ void gemv_issue(WPre<WT, MR>& pre, const WT* __restri
   for (int j = 0; j < WPre<WT, MR>::kRows; ++j) {
     const int n = r0 + warp + j * PNW;
     pre.bias[j] = 0.f;
+    pre.bias2[j] = 0.f;
     if (n < r1) {
       load_row_raw<WT, WPre<WT, MR>::kVec>(W, ldw, n, pre.r[j]);
-      if (bias) pre.bias[j] = bias[n];
-      if (bias2) pre.bias[j] += bias2[n];
+      if (bias) pre.bias[j] = bias[n];      // plain loads: consumed only after the barrier, no wait here
+      if (bias2) pre.bias2[j] = bias2[n];
     }
   }
 }
@@ -144,7 +153,7 @@ __device__ __forceinline__ void gemv_finish(WPre<WT, MR>& pre, const WT* __restr
 #pragma unroll
   for (int j = 0; j < kRows; ++j) {
     const int n = r0 + warp + j * PNW;
-    add[j] = ((n < r1 && lane < B) ? addend(n, lane) : 0.f) + pre.bias[j];
+    add[j] = ((n < r1 && lane < B) ? addend(n, lane) : 0.f) + (pre.bias[j] + pre.bias2[j]);
   }
   float acc[kRows][MR];
 #pragma unroll
@@ -423,6 +432,10 @@ __device__ void sample_utterance(const PParams& p, int b, float* smem) {
     if (tok < 0)  // rounding at the CDF tail: fall back to the last token with mass
       for (int i = kARLogits - 1; i >= 0; --i)
         if (v[i] > -INFINITY) { tok = i; break; }
+    if (!(tok >= 0 && tok < kARLogits)) {  // non-finite logits: never index the embedding table out of range
+      if (p.dbg & 32) { atomicMin(p.steps_done + 2, Tb * 1000 + 999); p.steps_done[3] = __float_as_int(m); }
+      tok = 0;
+    }
     const float logprob = greedy ? g_logprob : (v[tok] - m) - logf(Z);
     const int prev = ld_cg(bt.y + (size_t)b * bt.ymax + bt.P[b] + Tb);
     if (prev != kEOS) bt.sum_logprobs[b] += logprob;  // models/vallex.py:572
@@ -587,19 +600,22 @@ __device__ void attn_unit(const PParams& p, int layer, const AttnRange& r, float
 
 // out-proj input: softmax-combine the key splits.  The normalised split weights of every (b, head) go to shared
 // memory first (one exp per split, not per column), then every column folds its splits with coalesced loads.
-__device__ __forceinline__ void stage_att(float* sx, const PParams& p, int B, float* swn /*[B*16*nsplit]*/) {
+__device__ __forceinline__ void stage_att(float* sx, const PParams& p, int B, float* swn /*[B*16*nsplit] + [2*B*16*nsplit]*/) {
   const int tid = threadIdx.x;
   const int ns = p.nsplit;
+  const int npairs = B * kH * ns;
+  float* sml = swn + npairs;  // (m, l) of every (b, head, split): one L2 round trip for all of them
+  for (int i = tid; i < 2 * npairs; i += PNT) sml[i] = __ldcg(p.part + (size_t)(i >> 1) * (kDH + 2) + (i & 1));
+  __syncthreads();
   for (int bh = tid; bh < B * kH; bh += PNT) {
-    const float* p0 = p.part + (size_t)bh * ns * (kDH + 2);
+    const float* ml = sml + (size_t)bh * ns * 2;
     float M = -INFINITY;
-    for (int s = 0; s < ns; ++s) M = fmaxf(M, __ldcg(p0 + s * (kDH + 2)));
+    for (int s = 0; s < ns; ++s) M = fmaxf(M, ml[2 * s]);
     float L = 0.f;
     for (int s = 0; s < ns; ++s) {
-      const float ms = __ldcg(p0 + s * (kDH + 2));
-      const float w = (ms == -INFINITY) ? 0.f : expf(ms - M);
+      const float w = (ml[2 * s] == -INFINITY) ? 0.f : expf(ml[2 * s] - M);
       swn[bh * ns + s] = w;
-      L += w * __ldcg(p0 + s * (kDH + 2) + 1);
+      L += w * ml[2 * s + 1];
     }
     const float inv = 1.0f / L;
     for (int s = 0; s < ns; ++s) swn[bh * ns + s] *= inv;
@@ -609,8 +625,15 @@ __device__ __forceinline__ void stage_att(float* sx, const PParams& p, int B, fl
     const int b = i / kD, c = i % kD, h = c >> 6, d = c & 63;
     const float* wn = swn + (size_t)(b * kH + h) * ns;
     const float* po = p.part + ((size_t)(b * kH + h) * ns) * (kDH + 2) + 2 + d;
+    float o[16];
+#pragma unroll
+    for (int s = 0; s < 16; ++s) o[s] = (s < ns) ? __ldcg(po + (size_t)s * (kDH + 2)) : 0.f;  // all splits in flight at once
     float O = 0.f;
-    for (int s = 0; s < ns; ++s) O = fmaf(wn[s], __ldcg(po + (size_t)s * (kDH + 2)), O);
+#pragma unroll
+    for (int s = 0; s < 16; ++s)
+      if (s < ns) O = fmaf(wn[s], o[s], O);
+    for (int s = 16; s < ns; ++s) O = fmaf(wn[s], __ldcg(po + (size_t)s * (kDH + 2)), O);
+    nan_probe(p, 900000000 + h, O);
     sx[i] = ld_cg(p.bt.finished + b) ? 0.f : O;
   }
   __syncthreads();
@@ -672,7 +695,7 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_persistent_kernel(const PPar
     }
     // ---- S0: sample, append, embed -------------------------------------------------------------------
     for (int b = blockIdx.x; b < B; b += gridDim.x)
-      if (!ld_cg(bt.finished + b)) sample_utterance(p, b, scratch);
+      if (!ld_cg(bt.finished + b) && !(p.dbg & 16)) sample_utterance(p, b, scratch);
     grid_barrier(p.bar, epoch, prof);
     ++steps;
     if (!p.ignore_eos && ld_cg(bt.n_active) <= 0) break;
@@ -702,10 +725,10 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_persistent_kernel(const PPar
           }
         }
       }
-      stage_ln<MR>(sx, B, [&](int m, int c) { return stream_dyn(p, l, m, c, B); }, lp, scratch);
+      if (!(p.dbg & 8)) stage_ln<MR>(sx, B, [&](int m, int c) { const float v = stream_dyn(p, l, m, c, B); nan_probe(p, step * 1000 + l * 10 + 1, v); return v; }, lp, scratch);
       PSTAMP(3);
-      gemv_finish<WT, MR>(pre, Wq, kD, q0, q1, sx, B, L.qkv_b, nullptr, [&](int, int) { return 0.f; },
-                          [&](int n, int m, float v) { p.qkv[(size_t)m * 3 * kD + n] = v; });
+      if (!(p.dbg & 4)) gemv_finish<WT, MR>(pre, Wq, kD, q0, q1, sx, B, L.qkv_b, nullptr, [&](int, int) { return 0.f; },
+                          [&](int n, int m, float v) { nan_probe(p, step * 1000 + l * 10 + 2, v); p.qkv[(size_t)m * 3 * kD + n] = v; });
       PSTAMP(4);
       gemv_issue<WT, MR>(pre, Wo, kD, o0, o1, L.out_b, fb_prev);   // out-proj rows ride through the attention phase
       grid_barrier(p.bar, epoch, prof);
@@ -717,32 +740,32 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_persistent_kernel(const PPar
       PSTAMP(6);
       for (int u = blockIdx.x; u < B * kH * p.nsplit; u += gridDim.x) {
         const AttnRange r = attn_range(p, u);
-        if (ld_cg(bt.finished + r.b)) continue;
+        if (ld_cg(bt.finished + r.b) || (p.dbg & 1)) continue;
         attn_unit<WT>(p, l, r, scratch, ks, vs, (u == (int)blockIdx.x) ? n_staged : 0);
       }
       grid_barrier(p.bar, epoch, prof);
       // ---- P3: combine key splits + out-proj + residual -> xa ---------------------------------------------------
-      stage_att(sx, p, B, scratch);
+      if (!(p.dbg & 2)) stage_att(sx, p, B, scratch);
       PSTAMP(3);
-      gemv_finish<WT, MR>(pre, Wo, kD, o0, o1, sx, B, L.out_b, fb_prev, [&](int n, int m) { return stream_dyn(p, l, m, n, B); },
-                          [&](int n, int m, float v) { p.xa[(size_t)m * kD + n] = v; });
+      if (!(p.dbg & 4)) gemv_finish<WT, MR>(pre, Wo, kD, o0, o1, sx, B, L.out_b, fb_prev, [&](int n, int m) { return stream_dyn(p, l, m, n, B); },
+                          [&](int n, int m, float v) { nan_probe(p, step * 1000 + l * 10 + 4, v); p.xa[(size_t)m * kD + n] = v; });
       PSTAMP(4);
       gemv_issue<WT, MR>(pre, W1, kD, f0, f1, L.ff1_b, nullptr);
       ln_issue(lp, L.n2_g, L.n2_b, nullptr);
       grid_barrier(p.bar, epoch, prof);
       // ---- P4: LN2 + FFN1 + ReLU -------------------------------------------------------------------------------
-      stage_ln<MR>(sx, B, [&](int m, int c) { return __ldcg(p.xa + (size_t)m * kD + c); }, lp, scratch);
+      if (!(p.dbg & 8)) stage_ln<MR>(sx, B, [&](int m, int c) { return __ldcg(p.xa + (size_t)m * kD + c); }, lp, scratch);
       PSTAMP(3);
-      gemv_finish<WT, MR>(pre, W1, kD, f0, f1, sx, B, L.ff1_b, nullptr, [&](int, int) { return 0.f; },
-                          [&](int n, int m, float v) { p.hid[(size_t)m * kFF + n] = fmaxf(v, 0.f); });
+      if (!(p.dbg & 4)) gemv_finish<WT, MR>(pre, W1, kD, f0, f1, sx, B, L.ff1_b, nullptr, [&](int, int) { return 0.f; },
+                          [&](int n, int m, float v) { nan_probe(p, step * 1000 + l * 10 + 5, v); p.hid[(size_t)m * kFF + n] = fmaxf(v, 0.f); });
       PSTAMP(4);
       gemv_issue<WT, MR>(pre, W2, kFF, g0, g1, nullptr, nullptr);
       grid_barrier(p.bar, epoch, prof);
       // ---- P5: FFN2, split-K: rows [g0,g1) x k chunk kc -> partial pf[kc] --------------------------------------
       stage_plain(sx, B, [&](int m, int c) { return __ldcg(p.hid + (size_t)m * kFF + kc * kD + c); });
       PSTAMP(3);
-      gemv_finish<WT, MR>(pre, W2, kFF, g0, g1, sx, B, nullptr, nullptr, [&](int, int) { return 0.f; },
-                          [&](int n, int m, float v) { p.pf[((size_t)kc * B + m) * kD + n] = v; });
+      if (!(p.dbg & 4)) gemv_finish<WT, MR>(pre, W2, kFF, g0, g1, sx, B, nullptr, nullptr, [&](int, int) { return 0.f; },
+                          [&](int n, int m, float v) { nan_probe(p, step * 1000 + l * 10 + 6, v); p.pf[((size_t)kc * B + m) * kD + n] = v; });
       PSTAMP(4);
       if (l + 1 < kL) {
         gemv_issue<WT, MR>(pre, reinterpret_cast<const WT*>(p.layer[l + 1].qkv_w), kD, q0, q1, p.layer[l + 1].qkv_b, nullptr);
@@ -755,7 +778,7 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_persistent_kernel(const PPar
     }
     // ---- PF: final LayerNorm + predict rows -> logits ---------------------------------------------------------
     stage_ln<MR>(sx, B, [&](int m, int c) { return stream_dyn(p, kL, m, c, B); }, lp, scratch);
-    gemv_finish<WT, MR>(pre, reinterpret_cast<const WT*>(p.predict_w), kD, pr0, pr1, sx, B, nullptr, nullptr,
+    if (!(p.dbg & 4)) gemv_finish<WT, MR>(pre, reinterpret_cast<const WT*>(p.predict_w), kD, pr0, pr1, sx, B, nullptr, nullptr,
                         [&](int, int) { return 0.f; },
                         [&](int n, int m, float v) { p.logits[(size_t)m * kARLogits + n] = v; });
     gemv_issue<WT, MR>(pre, Wqkv0, kD, q0, q1, p.layer[0].qkv_b, nullptr);

@@ -766,6 +766,7 @@ int vx_ar_decode(vx_engine* e, int max_new, int top_k, float top_p, float temper
     ENS(e->p_pf, (size_t)4 * B * kD * 4);
     ENS(e->p_bar, 64);
     CK(cudaMemsetAsync(e->p_bar.p, 0, 64, st));
+    { const int32_t big = 0x7fffffff; CK(cudaMemcpyAsync((char*)e->p_bar.p + 40, &big, 4, cudaMemcpyHostToDevice, st)); }
     PParams pp{};
     pp.bt = e->bt;
     for (int l = 0; l < kL; ++l) {
@@ -781,6 +782,7 @@ int vx_ar_decode(vx_engine* e, int max_new, int top_k, float top_p, float temper
     pp.top_k = top_k; pp.top_p = top_p; pp.temperature = temperature; pp.seed = seed; pp.ignore_eos = ignore_eos;
     pp.forced = forced_dev; pp.forced_stride = max_steps; pp.out_tokens = (int32_t*)e->out_tok.p; pp.out_stride = max_steps;
     pp.max_steps = max_steps; pp.steps_done = (int32_t*)((char*)e->p_bar.p + 32);
+    pp.dbg = getenv("VX_DECODE_DBG") ? atoi(getenv("VX_DECODE_DBG")) : 0;
     if (getenv("VX_DECODE_PROF")) {
       ENS(e->p_prof, 3 * 4096 * 8);
       CK(cudaMemsetAsync(e->p_prof.p, 0, 3 * 4096 * 8, st));
@@ -797,6 +799,11 @@ int vx_ar_decode(vx_engine* e, int max_new, int top_k, float top_p, float temper
     CK(cudaEventElapsedTime(&e->ms_decode, e->ev0, e->ev1));
     e->decode_steps = e->h_pinned[0];
     CK(cudaGetLastError());
+    if (pp.dbg & 32) {
+      int32_t probe[2];
+      CK(cudaMemcpy(probe, (char*)e->p_bar.p + 40, 8, cudaMemcpyDeviceToHost));
+      fprintf(stderr, "[vx decode probe] first non-finite code %d (step*1000 + layer*10 + site; 9e8+h = split combine), bits 0x%08x\n", probe[0], (unsigned)probe[1]);
+    }
     int r2;
     if (out_tokens && (r2 = copy_out(out_tokens, e->out_tok.p, (size_t)B * max_steps * 4, mem, st))) return r2;
     if (out_lens && (r2 = copy_out(out_lens, e->d_T.p, B * 4, mem, st))) return r2;
