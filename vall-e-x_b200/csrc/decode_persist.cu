@@ -1,43 +1,41 @@
 // Persistent AR decode kernel: the whole token loop of models/vallex.py:528-598 in ONE cooperative launch.
 //
-// One CTA per SM (256 threads), all resident; every decode step walks
+// One CTA per SM (512 threads), all resident; every decode step walks
 //     S0  sample + append + embed (CTA b serves utterance b)              models/vallex.py:529-531,569-598
-//     12 x [ P1 LN1 + QKV rows | P2 attention (KV append, keys split over CTAs) | P3 split-combine + out-proj + residual
-//            | P4 LN2 + FFN1 + ReLU | P5 FFN2 (split-K x4, partial sums) ]  modules/transformer.py:337-347
-//     PF  final LN + predict rows -> logits                               modules/transformer.py:470-471
-// separated by grid-wide barriers (release/relaxed counter in L2), 62 per step.  Nothing returns to the host between
-// tokens: sampling, EOS/budget bookkeeping and the all-finished early exit live on the device.
+//     12 x [ P1 LN1 + QKV rows | P2 attention (KV append, split-K over CTAs, ticket combine)
+//            | P3 out-proj + residual | P4 LN2 + FFN1 + ReLU | P5 FFN2 (split-K x4, partial sums) ]
+//     PF  final LN + predict rows -> logits                               modules/transformer.py:337-347,470-471
+// separated by grid-wide barriers (release/acquire counter in L2), 62 per step.  Nothing returns to the host
+// between tokens: sampling, EOS/budget bookkeeping and the all-finished early exit live on the device.
 //
-// Data path (HBM / latency bound):
-//  * Weights.  Each CTA owns a fixed, contiguous row slice of every matrix (row-major bf16/fp32).  A slice is at
-//    most 4 rows per warp, so it is requested into REGISTERS with 128-bit streaming loads BEFORE the grid barrier that
-//    precedes its phase (weights do not depend on the barrier) together with its biases and LayerNorm vectors; the
-//    phase itself then only stages the activations (fp32, B x 1024, shared memory), runs the FMAs and a warp-shuffle
-//    reduction.  FFN2 is split over K so every GEMV phase has the same shape; its four partial sums, the bias and
-//    the residual are folded (fixed order -> deterministic) by the consumers.
-//  * KV cache ([layer][b][head][pos][64], 128-byte rows in bf16).  The CTA's key range of the coming attention phase
-//    is contiguous; it is staged into shared memory by the TMA engine (cp.async.bulk + mbarrier) while the QKV phase
-//    runs.  Scores use 8 lanes per key (conflict-free 128-bit shared loads), softmax statistics are block
-//    reductions, P.V accumulates in registers; this step's key/value are appended in place by split 0.
+// Data path (HBM bound): each CTA owns a fixed, contiguous slice of the rows of every weight matrix
+// (row-major, so a slice is one contiguous 40-60 KB range); a warp streams one row at a time with 128-bit
+// coalesced loads (4-8 in flight per lane), activations (fp32, B x 1024) sit in shared memory, the reduction
+// is a warp shuffle.  While a phase runs, the CTA's slice for the NEXT phase is pulled into L2 with
+// cp.async.bulk.prefetch.L2 so HBM keeps streaming across the barriers.  The KV cache ([b][h][pos][64], 128 B
+// rows in bf16) is read once per step with 128-bit loads; this step's key/value are appended in place.
+// FFN2 is split over K so every GEMV phase has the same shape (~21-28 rows x 1024); the four partial sums are
+// folded (fixed order, deterministic) by the consumer's prologue together with bias and residual.
 //
 // Algorithmic bytes per step: 304,412,672 + 49,152 * sum_b(L_b + 1) at bf16.
+#include <cooperative_groups.h>
+
 #include <cstdlib>
 
 #include "common.cuh"
-#include "decode_persist.h"
 #include "kernels.h"
+#include "decode_persist.h"
 #include "tc_common.cuh"
 
 namespace vx {
 
-constexpr int PNT = 256;            // threads per CTA
+constexpr int PNT = 512;            // threads per CTA
 constexpr int PNW = PNT / 32;       // warps
 constexpr int PCHUNK = 2048;        // max keys per attention unit
 constexpr int PSORT = 2048;
-constexpr int KVS_KEYS = 256;       // keys per unit that can be staged in shared memory (2 x 32 KB)
 
 // ---- grid barrier -------------------------------------------------------------------------------------
-// `prof` (nullable): (tag, clock64) stamps -- 1 = arrival of this CTA, 2 = release of the grid
+// `prof` (nullable): two clock64 stamps per barrier -- arrival of this CTA, release of the grid
 __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& epoch, long long*& prof) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -48,7 +46,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& ep
     unsigned int spins = 0;
     do {  // relaxed polling (no per-iteration L1 invalidate)
       asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
-      if (++spins > (1u << 23)) __trap();  // a lost CTA must not hang the box (~seconds)
+      if (++spins > (1u << 24)) __trap();  // a lost CTA must not hang the box
     } while ((int)(v - epoch) < 0);
     // no acquire fence: every cross-CTA mutable value is read with ld.global.cg (L2), never through L1
     if (prof) { prof[0] = 2; prof[1] = clock64(); prof += 2; }
@@ -57,14 +55,30 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& ep
 }
 #define PSTAMP(id_) do { if (prof) { prof[0] = (id_); prof[1] = clock64(); prof += 2; } } while (0)
 
-__device__ __forceinline__ int ld_cg(const int32_t* p) { return __ldcg(p); }
-
-// VX_DECODE_DBG & 32: record the first non-finite value seen (code = step * 1000 + layer * 10 + site) in steps_done[2..3]
-__device__ __forceinline__ void nan_probe(const PParams& p, int code, float v) {
-  if ((p.dbg & 32) && !(fabsf(v) <= 3.0e38f)) {
-    atomicMin(p.steps_done + 2, code);
-    p.steps_done[3] = __float_as_int(v);
+__device__ __forceinline__ void l2_prefetch(const void* p, size_t bytes) {
+  const char* c = reinterpret_cast<const char*>(p);
+  // 16-byte aligned ranges, chunks of <= 32 KB
+  size_t start = reinterpret_cast<size_t>(c) & ~size_t(15);
+  size_t end = (reinterpret_cast<size_t>(c) + bytes + 15) & ~size_t(15);
+  while (start < end) {
+    const unsigned int n = (unsigned int)((end - start) < 32768 ? (end - start) : 32768);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(start), "r"(n) : "memory");
+    start += n;
   }
+}
+
+__device__ __forceinline__ int ld_cg(const int32_t* p) { return __ldcg(p); }
+// KV rows are written during the kernel (append) -> read them through L2 (ld.global.cg), never the .nc path
+__device__ __forceinline__ void ldkv8(const bf16* p, float (&o)[8]) {
+  const uint4 r = __ldcg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { o[2 * i] = __uint_as_float(w[i] << 16); o[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+__device__ __forceinline__ void ldkv8(const float* p, float (&o)[8]) {
+  const float4 a = __ldcg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldcg(reinterpret_cast<const float4*>(p) + 1);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
 }
 
 __device__ __forceinline__ void slice(int total, int& r0, int& r1) {
@@ -72,29 +86,44 @@ __device__ __forceinline__ void slice(int total, int& r0, int& r1) {
   r1 = (int)(((long long)(blockIdx.x + 1) * total) / gridDim.x);
 }
 
+// 128-bit streaming weight loads (bypass L1: each byte is used once per step)
+__device__ __forceinline__ void ldw8(const bf16* p, float (&o)[8]) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { o[2 * i] = __uint_as_float(w[i] << 16); o[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+__device__ __forceinline__ void ldw8(const float* p, float (&o)[8]) {
+  uint4 a, b;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p + 4));
+  o[0] = __uint_as_float(a.x); o[1] = __uint_as_float(a.y); o[2] = __uint_as_float(a.z); o[3] = __uint_as_float(a.w);
+  o[4] = __uint_as_float(b.x); o[5] = __uint_as_float(b.y); o[6] = __uint_as_float(b.z); o[7] = __uint_as_float(b.w);
+}
+
 // ---- weight-streaming GEMV with cross-barrier register prefetch ---------------------------------------------
+// A CTA's row slice of one matrix is at most 2 rows per warp (148 CTAs x 16 warps), so a phase's weights fit in
+// registers: they are requested BEFORE the preceding grid barrier (the weights do not depend on it) and consumed
+// after it, which takes the HBM latency of every GEMV phase off the critical path.
 template <typename WT, int MR>
 struct WPre {
-  static constexpr int kRows = (sizeof(WT) == 2) ? (MR <= 4 ? 4 : (MR <= 8 ? 2 : 1)) : (MR <= 4 ? 2 : 1);
+  static constexpr int kRows = (sizeof(WT) == 2 && MR <= 8) ? 2 : 1;
   static constexpr int kVec = (sizeof(WT) == 2) ? 4 : 8;  // uint4 per row per lane (K = 1024)
   uint4 r[kRows][kVec];
-  float bias[kRows], bias2[kRows];  // constant addends of each prefetched row (bias, previous layer's FFN2 bias)
+  float bias[kRows];  // constant addend of each prefetched row (bias [+ previous layer's FFN2 bias]), fetched with the row
 };
-struct LnPre {  // LayerNorm parameters (+ previous layer's FFN2 bias) of this thread's four columns
-  float g[4], b[4], f[4];
+struct LnPre {        // LayerNorm parameters (+ previous layer's FFN2 bias) of this thread's two columns
+  float g0, g1, b0, b1, f0, f1;
 };
 __device__ __forceinline__ void ln_issue(LnPre& lp, const float* __restrict__ g, const float* __restrict__ b,
                                          const float* __restrict__ fb) {
   const int t = threadIdx.x;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    lp.g[i] = g[t + i * PNT];
-    lp.b[i] = b[t + i * PNT];
-    lp.f[i] = fb ? fb[t + i * PNT] : 0.f;
-  }
+  lp.g0 = g[t]; lp.g1 = g[t + PNT]; lp.b0 = b[t]; lp.b1 = b[t + PNT];
+  lp.f0 = fb ? fb[t] : 0.f; lp.f1 = fb ? fb[t + PNT] : 0.f;
 }
 
-__device__ __forceinline__ uint4 ldw_raw(const void* p) {  // streaming: each weight byte is used once per step
+__device__ __forceinline__ uint4 ldw_raw(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
@@ -112,8 +141,9 @@ __device__ __forceinline__ void raw_to_f32<float>(const uint4* v, int it, float 
   o[0] = __uint_as_float(v[2 * it].x); o[1] = __uint_as_float(v[2 * it].y); o[2] = __uint_as_float(v[2 * it].z); o[3] = __uint_as_float(v[2 * it].w);
   o[4] = __uint_as_float(v[2 * it + 1].x); o[5] = __uint_as_float(v[2 * it + 1].y); o[6] = __uint_as_float(v[2 * it + 1].z); o[7] = __uint_as_float(v[2 * it + 1].w);
 }
-template <typename WT, int NV>
-__device__ __forceinline__ void load_row_raw(const WT* __restrict__ W, size_t ldw, int n, uint4 (&dst)[NV]) {
+
+template <typename WT, int MR>
+__device__ __forceinline__ void load_row_raw(const WT* __restrict__ W, size_t ldw, int n, uint4 (&dst)[WPre<WT, MR>::kVec]) {
   const int lane = threadIdx.x & 31;
   const WT* p = W + (size_t)n * ldw + lane * 8;
 #pragma unroll
@@ -123,7 +153,7 @@ __device__ __forceinline__ void load_row_raw(const WT* __restrict__ W, size_t ld
   }
 }
 
-// request this warp's rows of slice [r0,r1): row j of the warp is r0 + warp + j*PNW
+// request this warp's first rows of slice [r0,r1)
 template <typename WT, int MR>
 __device__ __forceinline__ void gemv_issue(WPre<WT, MR>& pre, const WT* __restrict__ W, size_t ldw, int r0, int r1,
                                            const float* __restrict__ bias, const float* __restrict__ bias2) {
@@ -132,17 +162,37 @@ __device__ __forceinline__ void gemv_issue(WPre<WT, MR>& pre, const WT* __restri
   for (int j = 0; j < WPre<WT, MR>::kRows; ++j) {
     const int n = r0 + warp + j * PNW;
     pre.bias[j] = 0.f;
-    pre.bias2[j] = 0.f;
     if (n < r1) {
-      load_row_raw<WT, WPre<WT, MR>::kVec>(W, ldw, n, pre.r[j]);
-      if (bias) pre.bias[j] = bias[n];      // plain loads: consumed only after the barrier, no wait here
-      if (bias2) pre.bias2[j] = bias2[n];
+      load_row_raw<WT, MR>(W, ldw, n, pre.r[j]);
+      if (bias) pre.bias[j] = bias[n];
+      if (bias2) pre.bias[j] += bias2[n];
     }
   }
 }
 
-// consume the prefetched rows (x is read from shared memory once per k block and reused by all rows of the warp).
-// addend(n, m) is evaluated by lane m BEFORE the dot products; emit(n, m, value) is called by lane m < B.
+template <typename WT, int MR>
+__device__ __forceinline__ void row_dot(const uint4 (&raw)[WPre<WT, MR>::kVec], const float* __restrict__ sx, float (&acc)[MR]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int m = 0; m < MR; ++m) acc[m] = 0.f;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    float w[8];
+    raw_to_f32<WT>(raw, it, w);
+#pragma unroll
+    for (int m = 0; m < MR; ++m) {
+      const float4 x0 = *reinterpret_cast<const float4*>(&sx[m * kD + it * 256 + lane * 8]);
+      const float4 x1 = *reinterpret_cast<const float4*>(&sx[m * kD + it * 256 + lane * 8 + 4]);
+      acc[m] = fmaf(w[0], x0.x, acc[m]); acc[m] = fmaf(w[1], x0.y, acc[m]); acc[m] = fmaf(w[2], x0.z, acc[m]); acc[m] = fmaf(w[3], x0.w, acc[m]);
+      acc[m] = fmaf(w[4], x1.x, acc[m]); acc[m] = fmaf(w[5], x1.y, acc[m]); acc[m] = fmaf(w[6], x1.z, acc[m]); acc[m] = fmaf(w[7], x1.w, acc[m]);
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < MR; ++m) acc[m] = warp_sum(acc[m]);
+}
+
+// consume the prefetched rows (and any further rows of the slice).  addend(n, m) is evaluated by lane m BEFORE the
+// dot products (its loads overlap them); emit(n, m, value) is called by lane m for batch row m < B.
 template <typename WT, int MR, typename Add, typename Emit>
 __device__ __forceinline__ void gemv_finish(WPre<WT, MR>& pre, const WT* __restrict__ W, size_t ldw, int r0, int r1,
                                             const float* __restrict__ sx, int B, const float* __restrict__ bias,
@@ -153,88 +203,52 @@ __device__ __forceinline__ void gemv_finish(WPre<WT, MR>& pre, const WT* __restr
 #pragma unroll
   for (int j = 0; j < kRows; ++j) {
     const int n = r0 + warp + j * PNW;
-    add[j] = ((n < r1 && lane < B) ? addend(n, lane) : 0.f) + (pre.bias[j] + pre.bias2[j]);
-  }
-  float acc[kRows][MR];
-#pragma unroll
-  for (int j = 0; j < kRows; ++j)
-#pragma unroll
-    for (int m = 0; m < MR; ++m) acc[j][m] = 0.f;
-#pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    float w[kRows][8];
-#pragma unroll
-    for (int j = 0; j < kRows; ++j) raw_to_f32<WT>(pre.r[j], it, w[j]);
-#pragma unroll
-    for (int m = 0; m < MR; ++m) {
-      const float4 x0 = *reinterpret_cast<const float4*>(&sx[m * kD + it * 256 + lane * 8]);
-      const float4 x1 = *reinterpret_cast<const float4*>(&sx[m * kD + it * 256 + lane * 8 + 4]);
-      const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-#pragma unroll
-      for (int j = 0; j < kRows; ++j)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[j][m] = fmaf(w[j][i], xv[i], acc[j][m]);
-    }
+    add[j] = (n < r1 && lane < B) ? addend(n, lane) : 0.f;
   }
 #pragma unroll
   for (int j = 0; j < kRows; ++j) {
     const int n = r0 + warp + j * PNW;
-    if (n < r1) {  // warp-uniform
+    if (n < r1) {
+      float acc[MR];
+      row_dot<WT, MR>(pre.r[j], sx, acc);
       float mine = 0.f;
 #pragma unroll
-      for (int m = 0; m < MR; ++m) {
-        const float s = warp_sum(acc[j][m]);
-        if (lane == m) mine = s;
-      }
-      if (lane < B) emit(n, lane, mine + add[j]);
+      for (int m = 0; m < MR; ++m)
+        if (lane == m) mine = acc[m];
+      if (lane < B) emit(n, lane, mine + (add[j] + pre.bias[j]));
     }
   }
-  for (int n = r0 + warp + kRows * PNW; n < r1; n += PNW) {  // rows beyond the prefetch window (small grids / large B)
+  for (int n = r0 + warp + kRows * PNW; n < r1; n += PNW) {  // only when the grid is smaller than 148 CTAs
     uint4 raw[WPre<WT, MR>::kVec];
-    load_row_raw<WT, WPre<WT, MR>::kVec>(W, ldw, n, raw);
+    load_row_raw<WT, MR>(W, ldw, n, raw);
     const float ad = ((lane < B) ? addend(n, lane) : 0.f) + (bias ? bias[n] : 0.f) + (bias2 ? bias2[n] : 0.f);
-    float a1[MR];
-#pragma unroll
-    for (int m = 0; m < MR; ++m) a1[m] = 0.f;
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      float w[8];
-      raw_to_f32<WT>(raw, it, w);
-#pragma unroll
-      for (int m = 0; m < MR; ++m) {
-        const float4 x0 = *reinterpret_cast<const float4*>(&sx[m * kD + it * 256 + lane * 8]);
-        const float4 x1 = *reinterpret_cast<const float4*>(&sx[m * kD + it * 256 + lane * 8 + 4]);
-        const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) a1[m] = fmaf(w[i], xv[i], a1[m]);
-      }
-    }
+    float acc[MR];
+    row_dot<WT, MR>(raw, sx, acc);
     float mine = 0.f;
 #pragma unroll
-    for (int m = 0; m < MR; ++m) {
-      const float s = warp_sum(a1[m]);
-      if (lane == m) mine = s;
-    }
+    for (int m = 0; m < MR; ++m)
+      if (lane == m) mine = acc[m];
     if (lane < B) emit(n, lane, mine + ad);
   }
 }
 
-// Stage B rows into shared memory with LayerNorm (eps 1e-5), two-pass variance, all threads (4 columns each).
-// value(m, c) is the dynamic part of the stream; lp.f (previous layer's FFN2 bias) is added here.
+// Stage B rows into shared memory with LayerNorm (eps 1e-5), all 512 threads, two-pass variance.
+// value(m, c) is the dynamic part of the stream; lp.f* (previous layer's FFN2 bias) is added here.
 template <int MR, typename Val>
 __device__ __forceinline__ void stage_ln(float* sx, int B, Val value, const LnPre& lp, float* red /*[2][PNW][8]*/) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int R = MR < 8 ? MR : 8;
   for (int mb = 0; mb < B; mb += R) {
     const int nb = min(R, B - mb);
-    float v[R][4];
-#pragma unroll
-    for (int m = 0; m < R; ++m)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) v[m][i] = (m < nb) ? value(mb + m, tid + i * PNT) + lp.f[i] : 0.f;
+    float v0[R], v1[R];
 #pragma unroll
     for (int m = 0; m < R; ++m) {
-      const float s = warp_sum((v[m][0] + v[m][1]) + (v[m][2] + v[m][3]));
+      v0[m] = (m < nb) ? value(mb + m, tid) + lp.f0 : 0.f;
+      v1[m] = (m < nb) ? value(mb + m, tid + PNT) + lp.f1 : 0.f;
+    }
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+      const float s = warp_sum(v0[m] + v1[m]);
       if (lane == 0) red[warp * 8 + m] = s;
     }
     __syncthreads();
@@ -248,11 +262,9 @@ __device__ __forceinline__ void stage_ln(float* sx, int B, Val value, const LnPr
     }
 #pragma unroll
     for (int m = 0; m < R; ++m) {
-      float q = 0.f;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { const float d = v[m][i] - mean[m]; q += d * d; }
-      q = warp_sum(q);
-      if (lane == 0) red[PNW * 8 + warp * 8 + m] = q;
+      const float d0 = v0[m] - mean[m], d1 = v1[m] - mean[m];
+      const float s = warp_sum(d0 * d0 + d1 * d1);
+      if (lane == 0) red[PNW * 8 + warp * 8 + m] = s;
     }
     __syncthreads();
 #pragma unroll
@@ -262,9 +274,8 @@ __device__ __forceinline__ void stage_ln(float* sx, int B, Val value, const LnPr
 #pragma unroll
         for (int w = 0; w < PNW; ++w) s += red[PNW * 8 + w * 8 + m];
         const float rstd = 1.0f / sqrtf(s / (float)kD + 1e-5f);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          sx[(mb + m) * kD + tid + i * PNT] = __fadd_rn(__fmul_rn((v[m][i] - mean[m]) * rstd, lp.g[i]), lp.b[i]);
+        sx[(mb + m) * kD + tid] = __fadd_rn(__fmul_rn((v0[m] - mean[m]) * rstd, lp.g0), lp.b0);
+        sx[(mb + m) * kD + tid + PNT] = __fadd_rn(__fmul_rn((v1[m] - mean[m]) * rstd, lp.g1), lp.b1);
       }
     }
     __syncthreads();  // red[] is reused by the next chunk; sx complete for the consumers
@@ -276,8 +287,8 @@ __device__ __forceinline__ void stage_plain(float* sx, int B, Val value) {
   __syncthreads();
 }
 
-// residual stream entering layer l: xa + the previous layer's four FFN2 split-K partials (its bias, a constant, is
-// added from prefetched registers by the callers)
+// residual stream entering a layer: xa (+ previous layer's FFN2 bias and 4 split-K partials, fixed order)
+// (the previous layer's FFN2 bias, a constant, is added from prefetched registers by the callers)
 __device__ __forceinline__ float stream_dyn(const PParams& p, int l, int b, int c, int B) {
   float v = __ldcg(p.xa + (size_t)b * kD + c);
   if (l > 0) {
@@ -307,9 +318,9 @@ __device__ void sample_utterance(const PParams& p, int b, float* smem) {
   float* v = smem;                          // [1032]
   float* sv = smem + 1032;                  // [2048]
   int16_t* sidx = reinterpret_cast<int16_t*>(sv + PSORT);  // [2048]
-  float* scan = reinterpret_cast<float*>(sidx + PSORT);    // [PNT]
+  float* scan = reinterpret_cast<float*>(sidx + PSORT);    // [512]
   float* red = scan + PNT;                  // [32]
-  int* s_tok = reinterpret_cast<int*>(red + 32);           // [2]
+  int* s_tok = reinterpret_cast<int*>(red + 32);
   const Batch& bt = p.bt;
   const int tid = threadIdx.x;
   const float* lg = p.logits + (size_t)b * kARLogits;
@@ -320,147 +331,151 @@ __device__ void sample_utterance(const PParams& p, int b, float* smem) {
   __syncthreads();
   const bool need_sort = (p.top_k > 1) || (p.top_p < 1.0f);
   const bool greedy = (p.top_k == 1);
-  const int Tb = ld_cg(bt.T + b);
   int g_tok = -1;
-  float g_logprob = 0.f, m = -INFINITY, Z = 1.f;
+  float g_logprob = 0.f;
   if (greedy) {
     // top_k == 1 keeps only the maximum (models/vallex.py:803-809): the draw is its index (first one on an exact tie)
     // and log_softmax over the kept entries is -log(#ties).
+    float m = -INFINITY;
     for (int i = tid; i < kARLogits; i += PNT) m = fmaxf(m, v[i]);
     m = block_max(m, red);
-    int first = 0x00ffffff, cnt = 0;
+    int first = 0x7fffffff, cnt = 0;
     for (int i = tid; i < kARLogits; i += PNT)
       if (v[i] == m) { first = min(first, i); ++cnt; }
     first = -(int)block_max((float)(-first), red);   // indices < 2^24: exact in fp32
     cnt = (int)block_sum((float)cnt, red);
     g_tok = first;
     g_logprob = -logf((float)cnt);
-    if (tid == 0) *s_tok = g_tok;
+  }
+  if (need_sort) {
+    for (int i = tid; i < PSORT; i += PNT) { sv[i] = (i < kARLogits) ? v[i] : -INFINITY; sidx[i] = (int16_t)i; }
     __syncthreads();
-  } else {
-    if (need_sort) {
-      for (int i = tid; i < PSORT; i += PNT) { sv[i] = (i < kARLogits) ? v[i] : -INFINITY; sidx[i] = (int16_t)i; }
-      __syncthreads();
-      for (int k = 2; k <= PSORT; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-          for (int i = tid; i < PSORT; i += PNT) {
-            const int ixj = i ^ j;
-            if (ixj > i) {
-              const bool desc = ((i & k) == 0);
-              const float a = sv[i], c = sv[ixj];
-              if (desc ? (a < c) : (a > c)) {
-                sv[i] = c; sv[ixj] = a;
-                const int16_t t = sidx[i]; sidx[i] = sidx[ixj]; sidx[ixj] = t;
-              }
+    for (int k = 2; k <= PSORT; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < PSORT; i += PNT) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const bool desc = ((i & k) == 0);
+            const float a = sv[i], c = sv[ixj];
+            if (desc ? (a < c) : (a > c)) {
+              sv[i] = c; sv[ixj] = a;
+              const int16_t t = sidx[i]; sidx[i] = sidx[ixj]; sidx[ixj] = t;
             }
           }
-          __syncthreads();
-        }
-      if (p.top_k > 1) {
-        const float thr = sv[min(p.top_k, kARLogits) - 1];
-        for (int i = tid; i < kARLogits; i += PNT)
-          if (v[i] < thr) v[i] = -INFINITY;
-        for (int i = tid; i < PSORT; i += PNT)
-          if (sv[i] < thr) sv[i] = -INFINITY;
-        __syncthreads();
-      }
-      if (p.top_p < 1.0f) {
-        const float m0 = sv[0];
-        float part = 0.f;
-        for (int i = tid; i < kARLogits; i += PNT) part += __expf(sv[i] - m0);
-        const float Z0 = block_sum(part, red);
-        if (tid == 0) {
-          float c = 0.f;
-          bool drop_next = false;
-          for (int i = 0; i < kARLogits; ++i) {
-            const bool drop = drop_next;
-            c += __expf(sv[i] - m0) / Z0;
-            drop_next = (c > p.top_p);
-            if (drop) v[sidx[i]] = -INFINITY;
-          }
         }
         __syncthreads();
       }
+    if (p.top_k > 1) {
+      const float thr = sv[min(p.top_k, kARLogits) - 1];
+      for (int i = tid; i < kARLogits; i += PNT)
+        if (v[i] < thr) v[i] = -INFINITY;
+      for (int i = tid; i < PSORT; i += PNT)
+        if (sv[i] < thr) sv[i] = -INFINITY;
+      __syncthreads();
     }
-    for (int i = tid; i < kARLogits; i += PNT) m = fmaxf(m, v[i]);
-    m = block_max(m, red);
-    constexpr int CH = (kARLogits + PNT - 1) / PNT;  // 5
-    float loc[CH], s = 0.f;
+    if (p.top_p < 1.0f) {
+      const float m = sv[0];
+      float part = 0.f;
+      for (int i = tid; i < kARLogits; i += PNT) part += __expf(sv[i] - m);
+      const float Z = block_sum(part, red);
+      if (tid == 0) {
+        float c = 0.f;
+        bool drop_next = false;
+        for (int i = 0; i < kARLogits; ++i) {
+          const bool drop = drop_next;
+          c += __expf(sv[i] - m) / Z;
+          drop_next = (c > p.top_p);
+          if (drop) v[sidx[i]] = -INFINITY;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  float m = -INFINITY;
+  if (!greedy) {
+  for (int i = tid; i < kARLogits; i += PNT) m = fmaxf(m, v[i]);
+  m = block_max(m, red);
+  }
+  constexpr int CH = (kARLogits + PNT - 1) / PNT;  // 3
+  float Z = 1.f;
+  const int Tb = ld_cg(bt.T + b);
+  if (!greedy) {
+  float loc[CH], s = 0.f;
+#pragma unroll
+  for (int q = 0; q < CH; ++q) {
+    const int i = tid * CH + q;
+    loc[q] = (i < kARLogits) ? expf(v[i] - m) : 0.f;
+    s += loc[q];
+  }
+  scan[tid] = s;
+  __syncthreads();
+  if (tid < 32) {
+    constexpr int PER = PNT / 32;
+    float run = 0.f, mine[PER];
+#pragma unroll
+    for (int q = 0; q < PER; ++q) { mine[q] = scan[tid * PER + q]; run += mine[q]; }
+    float incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float n = __shfl_up_sync(0xffffffffu, incl, o);
+      if (tid >= o) incl += n;
+    }
+    float ex = incl - run;
+#pragma unroll
+    for (int q = 0; q < PER; ++q) { scan[tid * PER + q] = ex; ex += mine[q]; }
+    if (tid == 31) red[0] = incl;
+  }
+  if (tid == 0) *s_tok = -1;
+  __syncthreads();
+  Z = red[0];
+  const float u = p_philox(p.seed, (uint32_t)Tb, (uint32_t)b) * Z;
+  {
+    float c = scan[tid];
+    int cand = -1;
 #pragma unroll
     for (int q = 0; q < CH; ++q) {
-      const int i = tid * CH + q;
-      loc[q] = (i < kARLogits) ? expf(v[i] - m) : 0.f;
-      s += loc[q];
+      const float n = c + loc[q];
+      if (cand < 0 && loc[q] > 0.f && u <= n && u > c) cand = tid * CH + q;
+      c = n;
     }
-    scan[tid] = s;
-    __syncthreads();
-    if (tid < 32) {
-      constexpr int PER = PNT / 32;
-      float run = 0.f, mine[PER];
-#pragma unroll
-      for (int q = 0; q < PER; ++q) { mine[q] = scan[tid * PER + q]; run += mine[q]; }
-      float incl = run;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const float n = __shfl_up_sync(0xffffffffu, incl, o);
-        if (tid >= o) incl += n;
-      }
-      float ex = incl - run;
-#pragma unroll
-      for (int q = 0; q < PER; ++q) { scan[tid * PER + q] = ex; ex += mine[q]; }
-      if (tid == 31) red[0] = incl;
-    }
-    if (tid == 0) *s_tok = -1;
-    __syncthreads();
-    Z = red[0];
-    const float u = p_philox(p.seed, (uint32_t)Tb, (uint32_t)b) * Z;
-    {
-      float c = scan[tid];
-      int cand = -1;
-#pragma unroll
-      for (int q = 0; q < CH; ++q) {
-        const float n = c + loc[q];
-        if (cand < 0 && loc[q] > 0.f && u <= n && u > c) cand = tid * CH + q;
-        c = n;
-      }
-      if (cand >= 0) atomicMax(s_tok, cand);
-    }
+    if (cand >= 0) atomicMax(s_tok, cand);
+  }
+  __syncthreads();
+  } else {
+    if (tid == 0) *s_tok = g_tok;
     __syncthreads();
   }
   if (tid == 0) {
     int tok = *s_tok;
-    if (tok < 0)  // rounding at the CDF tail: fall back to the last token with mass
+    if (tok < 0)
       for (int i = kARLogits - 1; i >= 0; --i)
         if (v[i] > -INFINITY) { tok = i; break; }
-    if (!(tok >= 0 && tok < kARLogits)) {  // non-finite logits: never index the embedding table out of range
-      if (p.dbg & 32) { atomicMin(p.steps_done + 2, Tb * 1000 + 999); p.steps_done[3] = __float_as_int(m); }
-      tok = 0;
-    }
     const float logprob = greedy ? g_logprob : (v[tok] - m) - logf(Z);
     const int prev = ld_cg(bt.y + (size_t)b * bt.ymax + bt.P[b] + Tb);
-    if (prev != kEOS) bt.sum_logprobs[b] += logprob;  // models/vallex.py:572
+    if (prev != kEOS) bt.sum_logprobs[b] += logprob;
     p.out_tokens[(size_t)b * p.out_stride + Tb] = tok;
-    int fed = -1;
-    if ((tok == kEOS) && !p.ignore_eos) {
+    const bool eos = (tok == kEOS) && !p.ignore_eos;
+    if (eos) {
       bt.finished[b] = 1;
       atomicSub(bt.n_active, 1);
     } else {
-      const int f = p.forced ? p.forced[(size_t)b * p.forced_stride + Tb] : tok;
-      bt.y[(size_t)b * bt.ymax + bt.P[b] + 1 + Tb] = f;
+      const int fed = p.forced ? p.forced[(size_t)b * p.forced_stride + Tb] : tok;
+      bt.y[(size_t)b * bt.ymax + bt.P[b] + 1 + Tb] = fed;
       bt.T[b] = Tb + 1;
       if (Tb + 1 >= bt.budget[b]) {
         bt.finished[b] = 1;
         atomicSub(bt.n_active, 1);
       } else {
-        fed = f;
+        // next input row: emb[token] + alpha * pe[y position]   (models/vallex.py:529-531)
+        *s_tok = fed;
       }
     }
-    s_tok[0] = fed;
-    s_tok[1] = Tb + 1;
+    if (bt.finished[b]) *s_tok = -1;   // written by this thread just above
+    s_tok[1] = bt.T[b];
   }
   __syncthreads();
-  const int fed = s_tok[0];
-  if (fed >= 0) {  // next input row: emb[token] + alpha * pe[y position]   (models/vallex.py:529-531)
+  const int fed = *s_tok;
+  if (fed >= 0) {
     const int j = bt.P[b] + s_tok[1];
     const float a = p.alpha[0];
     for (int c = tid; c < kD; c += PNT)
@@ -469,97 +484,59 @@ __device__ void sample_utterance(const PParams& p, int b, float* smem) {
   __syncthreads();
 }
 
-// ---- decode attention unit (b, h, split) ------------------------------------------------------------------------
+// ---- decode attention unit (b, h, split): same arithmetic as attn_decode_kernel ------------------------
 template <typename KVT> __device__ __forceinline__ float kv_round(float v);
 template <> __device__ __forceinline__ float kv_round<float>(float v) { return v; }
 template <> __device__ __forceinline__ float kv_round<bf16>(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
-// 8 consecutive cache elements -> fp32.  KV rows are immutable once written and never read before they are
-// written, so ordinary (L1-allocating) loads are safe; the shared-memory path uses the same generic load.
-__device__ __forceinline__ void kv8(const bf16* p, float (&o)[8]) {
-  const uint4 r = *reinterpret_cast<const uint4*>(p);
-  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { o[2 * i] = __uint_as_float(w[i] << 16); o[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
-}
-__device__ __forceinline__ void kv8(const float* p, float (&o)[8]) {
-  const float4 a = *reinterpret_cast<const float4*>(p);
-  const float4 b = *reinterpret_cast<const float4*>(p + 4);
-  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
-}
-
-struct AttnRange { int b, h, split, pos, j0, j1; };
-__device__ __forceinline__ AttnRange attn_range(const PParams& p, int u) {
-  AttnRange r;
-  r.split = u % p.nsplit;
-  const int bh = u / p.nsplit;
-  r.b = bh / kH; r.h = bh % kH;
-  r.pos = p.bt.S[r.b] + p.bt.P[r.b] + ld_cg(p.bt.T + r.b);  // cache slot of this step's key
-  const int n = r.pos + 1;
-  int chunk = (n + p.nsplit - 1) / p.nsplit;
-  chunk = (chunk + 31) & ~31;
-  r.j0 = r.split * chunk;
-  r.j1 = min(n, r.j0 + chunk);
-  return r;
-}
-
-// staged: K rows [j0, j0 + n_staged) at ks, V rows at vs (shared memory, row-major [key][64]); otherwise global.
 template <typename KVT>
-__device__ void attn_unit(const PParams& p, int layer, const AttnRange& r, float* smem, const KVT* ks, const KVT* vs,
-                          int n_staged) {
+__device__ void attn_unit(const PParams& p, int layer, int b, int h, int split, float* smem) {
   float* sq = smem;                  // [64]
   float* sknew = smem + 64;          // [64]
   float* svnew = smem + 128;         // [64]
   float* red = smem + 192;           // [32]
+  int* s_last = reinterpret_cast<int*>(smem + 224);
   float* sp = smem + 256;            // [PCHUNK]
   float* sacc = sp + PCHUNK;         // [PNT/8][64]
+  const Batch& bt = p.bt;
   const int tid = threadIdx.x;
-  const int b = r.b, h = r.h, pos = r.pos, j0 = r.j0, j1 = r.j1;
+  const int pos = bt.S[b] + bt.P[b] + ld_cg(bt.T + b);
+  const int n = pos + 1;
+  int chunk = (n + p.nsplit - 1) / p.nsplit;
+  chunk = (chunk + 31) & ~31;
+  const int j0 = split * chunk, j1 = min(n, j0 + chunk);
   const float* row = p.qkv + (size_t)b * (3 * kD) + h * kDH;
-  __syncthreads();  // scratch reuse across units
+  __syncthreads();  // smem reuse across units
   if (tid < kDH) {
-    sq[tid] = __ldcg(row + tid) * 0.125f;   // 1/sqrt(64), modules/activation.py:161
+    sq[tid] = __ldcg(row + tid) * 0.125f;
     sknew[tid] = __ldcg(row + kD + tid);
     svnew[tid] = __ldcg(row + 2 * kD + tid);
   }
   __syncthreads();
   KVT* kb = reinterpret_cast<KVT*>(p.kc) + (size_t)layer * p.kv_layer_elems + ((size_t)b * kH + h) * p.ctx_cap * kDH;
   KVT* vb = reinterpret_cast<KVT*>(p.vc) + (size_t)layer * p.kv_layer_elems + ((size_t)b * kH + h) * p.ctx_cap * kDH;
-  if (r.split == 0 && tid < kDH) {  // append (rounded to the cache type once; later steps read the same bits)
+  if (split == 0 && tid < kDH) {
     store_as(kb + (size_t)pos * kDH + tid, sknew[tid]);
     store_as(vb + (size_t)pos * kDH + tid, svnew[tid]);
   }
-  // scores: 8 lanes per key, 8 dims per lane
-  const int g = tid >> 3, dc = (tid & 7) * 8;
-  float qv[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) qv[i] = sq[dc + i];
   float mloc = -INFINITY;
-  for (int jb = j0; jb < j1; jb += PNT / 8) {  // warp-uniform trip count: the shuffles below need every lane
-    const int j = jb + g;
-    const bool valid = j < j1;
-    float w[8];
-    if (!valid) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) w[i] = 0.f;
-    } else if (j == pos) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) w[i] = kv_round<KVT>(sknew[dc + i]);
-    } else if (j - j0 < n_staged) {
-      kv8(ks + (size_t)(j - j0) * kDH + dc, w);
-    } else {
-      kv8(kb + (size_t)j * kDH + dc, w);
-    }
+  for (int j = j0 + tid; j < j1; j += PNT) {
     float s = 0.f;
+    if (j == pos) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s = fmaf(qv[i], w[i], s);
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if (valid) {
-      if ((tid & 7) == 0) sp[j - j0] = s;
-      mloc = fmaxf(mloc, s);
+      for (int d = 0; d < kDH; ++d) s = fmaf(sq[d], kv_round<KVT>(sknew[d]), s);
+    } else {
+      const KVT* kr = kb + (size_t)j * kDH;
+#pragma unroll
+      for (int d = 0; d < kDH; d += 8) {
+        float w[8];
+        ldkv8(kr + d, w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s = fmaf(sq[d + i], w[i], s);
+      }
     }
+    sp[j - j0] = s;
+    mloc = fmaxf(mloc, s);
   }
   const float m = block_max(mloc, red);
   float lloc = 0.f;
@@ -568,18 +545,18 @@ __device__ void attn_unit(const PParams& p, int layer, const AttnRange& r, float
     sp[j - j0] = pr;
     lloc += pr;
   }
-  const float l = block_sum(lloc, red);  // also orders the sp[] writes before the PV reads
+  const float l = block_sum(lloc, red);
+  constexpr int NG = PNT / 8;
+  const int g = tid >> 3, dc = (tid & 7) * 8;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int j = j0 + g; j < j1; j += PNT / 8) {
+  for (int j = j0 + g; j < j1; j += NG) {
     const float pr = sp[j - j0];
     float w[8];
     if (j == pos) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) w[i] = kv_round<KVT>(svnew[dc + i]);
-    } else if (j - j0 < n_staged) {
-      kv8(vs + (size_t)(j - j0) * kDH + dc, w);
     } else {
-      kv8(vb + (size_t)j * kDH + dc, w);
+      ldkv8(vb + (size_t)j * kDH + dc, w);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = fmaf(pr, w[i], acc[i]);
@@ -587,74 +564,43 @@ __device__ void attn_unit(const PParams& p, int layer, const AttnRange& r, float
 #pragma unroll
   for (int i = 0; i < 8; ++i) sacc[g * kDH + dc + i] = acc[i];
   __syncthreads();
-  // partial (m, l, o[64]) of this split; the out-proj phase folds the splits while staging (stage_att)
-  float* pp = p.part + (((size_t)b * kH + h) * p.nsplit + r.split) * (kDH + 2);
+  float od = 0.f;
   if (tid < kDH) {
-    float od = 0.f;
-#pragma unroll 8
-    for (int q = 0; q < PNT / 8; ++q) od += sacc[q * kDH + tid];
-    pp[2 + tid] = od;
+    for (int q = 0; q < NG; ++q) od += sacc[q * kDH + tid];
   }
+  // partial (m, l, o[64]) of this split; the out-proj phase folds the splits while staging (att_combined)
+  float* pp = p.part + (((size_t)b * kH + h) * p.nsplit + split) * (kDH + 2);
+  if (tid < kDH) pp[2 + tid] = od;
   if (tid == 0) { pp[0] = m; pp[1] = l; }
 }
 
-// out-proj input: softmax-combine the key splits.  The normalised split weights of every (b, head) go to shared
-// memory first (one exp per split, not per column), then every column folds its splits with coalesced loads.
-__device__ __forceinline__ void stage_att(float* sx, const PParams& p, int B, float* swn /*[B*16*nsplit] + [2*B*16*nsplit]*/) {
-  const int tid = threadIdx.x;
-  const int ns = p.nsplit;
-  const int npairs = B * kH * ns;
-  float* sml = swn + npairs;  // (m, l) of every (b, head, split): one L2 round trip for all of them
-  for (int i = tid; i < 2 * npairs; i += PNT) sml[i] = __ldcg(p.part + (size_t)(i >> 1) * (kDH + 2) + (i & 1));
-  __syncthreads();
-  for (int bh = tid; bh < B * kH; bh += PNT) {
-    const float* ml = sml + (size_t)bh * ns * 2;
-    float M = -INFINITY;
-    for (int s = 0; s < ns; ++s) M = fmaxf(M, ml[2 * s]);
-    float L = 0.f;
-    for (int s = 0; s < ns; ++s) {
-      const float w = (ml[2 * s] == -INFINITY) ? 0.f : expf(ml[2 * s] - M);
-      swn[bh * ns + s] = w;
-      L += w * ml[2 * s + 1];
-    }
-    const float inv = 1.0f / L;
-    for (int s = 0; s < ns; ++s) swn[bh * ns + s] *= inv;
+// softmax-combine the key splits of head c/64 for column c (fixed order -> deterministic)
+__device__ __forceinline__ float att_combined(const PParams& p, int b, int c) {
+  const int h = c >> 6, d = c & 63;
+  const float* p0 = p.part + ((size_t)b * kH + h) * p.nsplit * (kDH + 2);
+  float M = -INFINITY;
+  for (int s = 0; s < p.nsplit; ++s) M = fmaxf(M, __ldcg(p0 + s * (kDH + 2)));
+  float L = 0.f, O = 0.f;
+  for (int s = 0; s < p.nsplit; ++s) {
+    const float ms = __ldcg(p0 + s * (kDH + 2));
+    const float w = (ms == -INFINITY) ? 0.f : expf(ms - M);
+    L += w * __ldcg(p0 + s * (kDH + 2) + 1);
+    O += w * __ldcg(p0 + s * (kDH + 2) + 2 + d);
   }
-  __syncthreads();
-  for (int i = tid; i < B * kD; i += PNT) {
-    const int b = i / kD, c = i % kD, h = c >> 6, d = c & 63;
-    const float* wn = swn + (size_t)(b * kH + h) * ns;
-    const float* po = p.part + ((size_t)(b * kH + h) * ns) * (kDH + 2) + 2 + d;
-    float o[16];
-#pragma unroll
-    for (int s = 0; s < 16; ++s) o[s] = (s < ns) ? __ldcg(po + (size_t)s * (kDH + 2)) : 0.f;  // all splits in flight at once
-    float O = 0.f;
-#pragma unroll
-    for (int s = 0; s < 16; ++s)
-      if (s < ns) O = fmaf(wn[s], o[s], O);
-    for (int s = 16; s < ns; ++s) O = fmaf(wn[s], __ldcg(po + (size_t)s * (kDH + 2)), O);
-    nan_probe(p, 900000000 + h, O);
-    sx[i] = ld_cg(p.bt.finished + b) ? 0.f : O;
-  }
-  __syncthreads();
+  return O / L;
 }
 
 // ---- the kernel -------------------------------------------------------------------------------------------
 template <typename WT, int MR>
 __global__ void __launch_bounds__(PNT, 1) ar_decode_persistent_kernel(const PParams p) {
-  extern __shared__ __align__(128) uint8_t dsm_raw[];
-  // [K stage 32 KB | V stage 32 KB (bf16, B <= 8 only) | sx MR*4 KB | scratch 36 KB | mbarrier]
-  constexpr bool kStageKV = (sizeof(WT) == 2) && MR <= 8;  // 128-byte bf16 rows: 256 keys x (K + V) = 64 KB
-  constexpr int kKvBytes = kStageKV ? 2 * KVS_KEYS * kDH * 2 : 0;
-  WT* ks = reinterpret_cast<WT*>(dsm_raw);
-  WT* vs = reinterpret_cast<WT*>(dsm_raw + kKvBytes / 2);
-  float* sx = reinterpret_cast<float*>(dsm_raw + kKvBytes);
-  float* scratch = sx + MR * kD;
-  uint64_t* kvbar = reinterpret_cast<uint64_t*>(scratch + 9216);
+  extern __shared__ __align__(16) float dsm[];
+  float* sx = dsm;                       // [MR][1024]
+  float* scratch = dsm + MR * kD;        // attention / sampling / LN-reduction scratch
   const Batch& bt = p.bt;
   const int B = bt.B;
   const int tid = threadIdx.x;
   unsigned int epoch = 0;
+  const size_t wsz = sizeof(WT);
 
   int q0, q1, o0, o1, f0, f1, pr0, pr1;
   slice(3 * kD, q0, q1);
@@ -669,13 +615,6 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_persistent_kernel(const PPar
   const int g0 = (int)(((long long)(blockIdx.x - kc_first) * kD) / kc_n);
   const int g1 = (int)(((long long)(blockIdx.x - kc_first + 1) * kD) / kc_n);
 
-  if (tid == 0) {
-    tc::mbar_init(kvbar, 1);
-    tc::fence_barrier_init();
-  }
-  __syncthreads();
-  uint32_t kv_parity = 0;
-
   WPre<WT, MR> pre;
   LnPre lp;
   const WT* Wqkv0 = reinterpret_cast<const WT*>(p.layer[0].qkv_w);
@@ -683,7 +622,7 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_persistent_kernel(const PPar
   gemv_issue<WT, MR>(pre, Wqkv0, kD, q0, q1, p.layer[0].qkv_b, nullptr);
   ln_issue(lp, p.layer[0].n1_g, p.layer[0].n1_b, nullptr);
 
-  // optional timeline: CTAs 0, grid/2 and grid-1 stamp steps [prof_step0, prof_step0 + 4)
+  // optional timeline: CTAs 0, grid/2 and grid-1 stamp every barrier of steps [prof_step0, prof_step0 + 4)
   long long* prof = nullptr;
   const int prof_slot = (blockIdx.x == 0) ? 0 : (blockIdx.x == gridDim.x / 2) ? 1 : (blockIdx.x == gridDim.x - 1) ? 2 : -1;
 
@@ -695,7 +634,7 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_persistent_kernel(const PPar
     }
     // ---- S0: sample, append, embed -------------------------------------------------------------------
     for (int b = blockIdx.x; b < B; b += gridDim.x)
-      if (!ld_cg(bt.finished + b) && !(p.dbg & 16)) sample_utterance(p, b, scratch);
+      if (!ld_cg(bt.finished + b)) sample_utterance(p, b, scratch);
     grid_barrier(p.bar, epoch, prof);
     ++steps;
     if (!p.ignore_eos && ld_cg(bt.n_active) <= 0) break;
@@ -708,64 +647,62 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_persistent_kernel(const PPar
       const WT* Wo = reinterpret_cast<const WT*>(L.out_w);
       const WT* W1 = reinterpret_cast<const WT*>(L.ff1_w);
       const WT* W2 = reinterpret_cast<const WT*>(L.ff2_w) + (size_t)kc * kD;
-      // ---- P1: LN1 + QKV rows.  First: TMA-stage the K/V rows of this CTA's coming attention unit. -------------
-      int n_staged = 0;
-      const bool have_unit = (int)blockIdx.x < B * kH * p.nsplit;
-      if (kStageKV && have_unit) {
-        const AttnRange r = attn_range(p, blockIdx.x);
-        const int cnt = min(r.j1, r.pos) - r.j0;  // the new key (pos) is not in the cache yet
-        if (cnt > 0 && cnt <= KVS_KEYS && !ld_cg(bt.finished + r.b)) {
-          n_staged = cnt;
-          if (tid == 0) {
-            const size_t off = (size_t)l * p.kv_layer_elems + ((size_t)r.b * kH + r.h) * p.ctx_cap * kDH + (size_t)r.j0 * kDH;
-            tc::fence_proxy_async();
-            tc::mbar_expect_tx(kvbar, (uint32_t)cnt * kDH * 2 * 2);
-            tc::bulk_g2s(ks, reinterpret_cast<const WT*>(p.kc) + off, (uint32_t)cnt * kDH * 2, kvbar);
-            tc::bulk_g2s(vs, reinterpret_cast<const WT*>(p.vc) + off, (uint32_t)cnt * kDH * 2, kvbar);
+      // ---- P1: LN1 + QKV rows; pull this CTA's K/V ranges of the coming attention phase into L2 ----------------
+      for (int u = blockIdx.x; u < B * kH * p.nsplit; u += gridDim.x) {
+        if (tid == 0) {
+          const int split = u % p.nsplit, bh = u / p.nsplit, b = bh / kH, h = bh % kH;
+          const int n = bt.S[b] + bt.P[b] + ld_cg(bt.T + b) + 1;
+          int chunk = (n + p.nsplit - 1) / p.nsplit;
+          chunk = (chunk + 31) & ~31;
+          const int j0 = split * chunk, j1 = min(n - 1, j0 + chunk);
+          if (j1 > j0) {
+            const size_t off = ((size_t)l * p.kv_layer_elems + ((size_t)b * kH + h) * p.ctx_cap * kDH + (size_t)j0 * kDH) * wsz;
+            l2_prefetch(reinterpret_cast<const char*>(p.kc) + off, (size_t)(j1 - j0) * kDH * wsz);
+            l2_prefetch(reinterpret_cast<const char*>(p.vc) + off, (size_t)(j1 - j0) * kDH * wsz);
           }
         }
       }
-      if (!(p.dbg & 8)) stage_ln<MR>(sx, B, [&](int m, int c) { const float v = stream_dyn(p, l, m, c, B); nan_probe(p, step * 1000 + l * 10 + 1, v); return v; }, lp, scratch);
+      stage_ln<MR>(sx, B, [&](int m, int c) { return stream_dyn(p, l, m, c, B); }, lp, scratch);
       PSTAMP(3);
-      if (!(p.dbg & 4)) gemv_finish<WT, MR>(pre, Wq, kD, q0, q1, sx, B, L.qkv_b, nullptr, [&](int, int) { return 0.f; },
-                          [&](int n, int m, float v) { nan_probe(p, step * 1000 + l * 10 + 2, v); p.qkv[(size_t)m * 3 * kD + n] = v; });
+      gemv_finish<WT, MR>(pre, Wq, kD, q0, q1, sx, B, L.qkv_b, nullptr, [&](int, int) { return 0.f; },
+                          [&](int n, int m, float v) { p.qkv[(size_t)m * 3 * kD + n] = v; });
       PSTAMP(4);
       gemv_issue<WT, MR>(pre, Wo, kD, o0, o1, L.out_b, fb_prev);   // out-proj rows ride through the attention phase
+      PSTAMP(5);
       grid_barrier(p.bar, epoch, prof);
       // ---- P2: attention ---------------------------------------------------------------------------------
-      if (n_staged > 0) {
-        tc::mbar_wait(kvbar, kv_parity);
-        kv_parity ^= 1;
-      }
-      PSTAMP(6);
       for (int u = blockIdx.x; u < B * kH * p.nsplit; u += gridDim.x) {
-        const AttnRange r = attn_range(p, u);
-        if (ld_cg(bt.finished + r.b) || (p.dbg & 1)) continue;
-        attn_unit<WT>(p, l, r, scratch, ks, vs, (u == (int)blockIdx.x) ? n_staged : 0);
+        const int split = u % p.nsplit, bh = u / p.nsplit;
+        const int b = bh / kH, h = bh % kH;
+        if (ld_cg(bt.finished + b)) continue;
+        if (sizeof(WT) == 2) attn_unit<bf16>(p, l, b, h, split, scratch);
+        else attn_unit<float>(p, l, b, h, split, scratch);
       }
       grid_barrier(p.bar, epoch, prof);
-      // ---- P3: combine key splits + out-proj + residual -> xa ---------------------------------------------------
-      if (!(p.dbg & 2)) stage_att(sx, p, B, scratch);
+      // ---- P3: (combine key splits) + out-proj + residual -> xa ------------------------------------------------
+      stage_plain(sx, B, [&](int m, int c) { return ld_cg(bt.finished + m) ? 0.f : att_combined(p, m, c); });
       PSTAMP(3);
-      if (!(p.dbg & 4)) gemv_finish<WT, MR>(pre, Wo, kD, o0, o1, sx, B, L.out_b, fb_prev, [&](int n, int m) { return stream_dyn(p, l, m, n, B); },
-                          [&](int n, int m, float v) { nan_probe(p, step * 1000 + l * 10 + 4, v); p.xa[(size_t)m * kD + n] = v; });
+      gemv_finish<WT, MR>(pre, Wo, kD, o0, o1, sx, B, L.out_b, fb_prev, [&](int n, int m) { return stream_dyn(p, l, m, n, B); },
+                          [&](int n, int m, float v) { p.xa[(size_t)m * kD + n] = v; });
       PSTAMP(4);
       gemv_issue<WT, MR>(pre, W1, kD, f0, f1, L.ff1_b, nullptr);
       ln_issue(lp, L.n2_g, L.n2_b, nullptr);
+      PSTAMP(5);
       grid_barrier(p.bar, epoch, prof);
       // ---- P4: LN2 + FFN1 + ReLU -------------------------------------------------------------------------------
-      if (!(p.dbg & 8)) stage_ln<MR>(sx, B, [&](int m, int c) { return __ldcg(p.xa + (size_t)m * kD + c); }, lp, scratch);
+      stage_ln<MR>(sx, B, [&](int m, int c) { return __ldcg(p.xa + (size_t)m * kD + c); }, lp, scratch);
       PSTAMP(3);
-      if (!(p.dbg & 4)) gemv_finish<WT, MR>(pre, W1, kD, f0, f1, sx, B, L.ff1_b, nullptr, [&](int, int) { return 0.f; },
-                          [&](int n, int m, float v) { nan_probe(p, step * 1000 + l * 10 + 5, v); p.hid[(size_t)m * kFF + n] = fmaxf(v, 0.f); });
+      gemv_finish<WT, MR>(pre, W1, kD, f0, f1, sx, B, L.ff1_b, nullptr, [&](int, int) { return 0.f; },
+                          [&](int n, int m, float v) { p.hid[(size_t)m * kFF + n] = fmaxf(v, 0.f); });
       PSTAMP(4);
       gemv_issue<WT, MR>(pre, W2, kFF, g0, g1, nullptr, nullptr);
+      PSTAMP(5);
       grid_barrier(p.bar, epoch, prof);
       // ---- P5: FFN2, split-K: rows [g0,g1) x k chunk kc -> partial pf[kc] --------------------------------------
       stage_plain(sx, B, [&](int m, int c) { return __ldcg(p.hid + (size_t)m * kFF + kc * kD + c); });
       PSTAMP(3);
-      if (!(p.dbg & 4)) gemv_finish<WT, MR>(pre, W2, kFF, g0, g1, sx, B, nullptr, nullptr, [&](int, int) { return 0.f; },
-                          [&](int n, int m, float v) { nan_probe(p, step * 1000 + l * 10 + 6, v); p.pf[((size_t)kc * B + m) * kD + n] = v; });
+      gemv_finish<WT, MR>(pre, W2, kFF, g0, g1, sx, B, nullptr, nullptr, [&](int, int) { return 0.f; },
+                          [&](int n, int m, float v) { p.pf[((size_t)kc * B + m) * kD + n] = v; });
       PSTAMP(4);
       if (l + 1 < kL) {
         gemv_issue<WT, MR>(pre, reinterpret_cast<const WT*>(p.layer[l + 1].qkv_w), kD, q0, q1, p.layer[l + 1].qkv_b, nullptr);
@@ -778,7 +715,7 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_persistent_kernel(const PPar
     }
     // ---- PF: final LayerNorm + predict rows -> logits ---------------------------------------------------------
     stage_ln<MR>(sx, B, [&](int m, int c) { return stream_dyn(p, kL, m, c, B); }, lp, scratch);
-    if (!(p.dbg & 4)) gemv_finish<WT, MR>(pre, reinterpret_cast<const WT*>(p.predict_w), kD, pr0, pr1, sx, B, nullptr, nullptr,
+    gemv_finish<WT, MR>(pre, reinterpret_cast<const WT*>(p.predict_w), kD, pr0, pr1, sx, B, nullptr, nullptr,
                         [&](int, int) { return 0.f; },
                         [&](int n, int m, float v) { p.logits[(size_t)m * kARLogits + n] = v; });
     gemv_issue<WT, MR>(pre, Wqkv0, kD, q0, q1, p.layer[0].qkv_b, nullptr);
@@ -786,12 +723,337 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_persistent_kernel(const PPar
     grid_barrier(p.bar, epoch, prof);
   }
   if (blockIdx.x == 0 && tid == 0) *p.steps_done = steps;
+  (void)wsz;
+}
+
+// =================================================================================================================
+// Ring variant (bf16 weights, B <= 8): the CTA's weight-row slice of every GEMV phase -- plus that phase's LayerNorm
+// vectors and biases -- is staged into shared memory by the TMA engine (cp.async.bulk -> mbarrier, 1-D bulk copies of
+// the contiguous slice) TWO phases ahead through a 2-slot ring, so HBM streams continuously across the grid barriers
+// and no phase waits on DRAM latency; the dot products read weights from shared memory with conflict-free 128-bit loads.
+// =================================================================================================================
+
+constexpr int RW_ROWS = 32;
+constexpr int RW_BYTES = RW_ROWS * 2048;             // weight rows (K = 1024 bf16)
+constexpr int RLN_OFF = RW_BYTES;                    // gamma | beta | previous FFN2 bias (3 x 4 KB)
+constexpr int RBIAS_OFF = RLN_OFF + 3 * 4096;        // bias | bias2 (2 x 256 B)
+constexpr int RSTAGE_BYTES = RBIAS_OFF + 512;        // 78,336 B per ring slot
+
+struct RSlice {
+  const bf16* W; size_t ldw; int r0, r1, N;
+  const float *bias, *bias2, *lg, *lb, *lf;
+};
+
+// thread 0: arm the slot's mbarrier and launch the bulk copies of slice `s`
+__device__ __forceinline__ void ring_issue(uint8_t* slot, uint64_t* bar, const RSlice& s) {
+  using namespace tc;
+  const int rows = s.r1 - s.r0;
+  const int a0 = s.r0 & ~3;
+  int nb = ((s.r1 - a0) + 3) & ~3;
+  if (a0 + nb > s.N) nb = s.N - a0;
+  uint32_t bytes = (uint32_t)rows * 2048u;
+  if (s.lg) bytes += 8192u;
+  if (s.lf) bytes += 4096u;
+  if (s.bias) bytes += (uint32_t)nb * 4u;
+  if (s.bias2) bytes += (uint32_t)nb * 4u;
+  fence_proxy_async();  // the slot was last read through the generic proxy
+  mbar_expect_tx(bar, bytes);
+  if (s.ldw == (size_t)kD) {
+    bulk_g2s(slot, s.W + (size_t)s.r0 * kD, (uint32_t)rows * 2048u, bar);
+  } else {
+    for (int r = 0; r < rows; ++r) bulk_g2s(slot + r * 2048, s.W + (size_t)(s.r0 + r) * s.ldw, 2048u, bar);
+  }
+  if (s.lg) { bulk_g2s(slot + RLN_OFF, s.lg, 4096u, bar); bulk_g2s(slot + RLN_OFF + 4096, s.lb, 4096u, bar); }
+  if (s.lf) bulk_g2s(slot + RLN_OFF + 8192, s.lf, 4096u, bar);
+  if (s.bias) bulk_g2s(slot + RBIAS_OFF, s.bias + a0, (uint32_t)nb * 4u, bar);
+  if (s.bias2) bulk_g2s(slot + RBIAS_OFF + 256, s.bias2 + a0, (uint32_t)nb * 4u, bar);
+}
+
+template <int MR>
+__device__ __forceinline__ void ring_row_dot(const uint8_t* wrow, const float* __restrict__ sx, float (&acc)[MR]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int m = 0; m < MR; ++m) acc[m] = 0.f;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const uint4 r = *reinterpret_cast<const uint4*>(wrow + it * 512 + lane * 16);
+    const uint32_t w4[4] = {r.x, r.y, r.z, r.w};
+    float w[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { w[2 * i] = __uint_as_float(w4[i] << 16); w[2 * i + 1] = __uint_as_float(w4[i] & 0xffff0000u); }
+#pragma unroll
+    for (int m = 0; m < MR; ++m) {
+      const float4 x0 = *reinterpret_cast<const float4*>(&sx[m * kD + it * 256 + lane * 8]);
+      const float4 x1 = *reinterpret_cast<const float4*>(&sx[m * kD + it * 256 + lane * 8 + 4]);
+      float a = acc[m], c = 0.f;  // two chains halve the FMA dependency depth
+      a = fmaf(w[0], x0.x, a); c = fmaf(w[1], x0.y, c); a = fmaf(w[2], x0.z, a); c = fmaf(w[3], x0.w, c);
+      a = fmaf(w[4], x1.x, a); c = fmaf(w[5], x1.y, c); a = fmaf(w[6], x1.z, a); c = fmaf(w[7], x1.w, c);
+      acc[m] = a + c;
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < MR; ++m) acc[m] = warp_sum(acc[m]);
+}
+
+// rows of the slice from the ring slot; addend(n, m) evaluated by lane m before the dots; emit(n, m, v) by lane m.
+template <int MR, typename Add, typename Emit>
+__device__ __forceinline__ void ring_finish(const uint8_t* slot, const RSlice& s, const float* __restrict__ sx, int B,
+                                            Add addend, Emit emit) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int a0 = s.r0 & ~3;
+  const float* sb = reinterpret_cast<const float*>(slot + RBIAS_OFF);
+  const float* sb2 = reinterpret_cast<const float*>(slot + RBIAS_OFF + 256);
+  for (int n = s.r0 + warp; n < s.r1; n += PNW) {
+    float ad = (lane < B) ? addend(n, lane) : 0.f;
+    if (s.bias) ad += sb[n - a0];
+    if (s.bias2) ad += sb2[n - a0];
+    float acc[MR];
+    ring_row_dot<MR>(slot + (size_t)(n - s.r0) * 2048, sx, acc);
+    float mine = 0.f;
+#pragma unroll
+    for (int m = 0; m < MR; ++m)
+      if (lane == m) mine = acc[m];
+    if (lane < B) emit(n, lane, mine + ad);
+  }
+}
+
+// LayerNorm staging with the parameters taken from the ring slot
+template <int MR, typename Val>
+__device__ __forceinline__ void ring_stage_ln(float* sx, int B, Val value, const uint8_t* slot, bool has_f, float* red) {
+  const float* lnp = reinterpret_cast<const float*>(slot + RLN_OFF);
+  LnPre lp;
+  const int t = threadIdx.x;
+  lp.g0 = lnp[t]; lp.g1 = lnp[t + PNT]; lp.b0 = lnp[1024 + t]; lp.b1 = lnp[1024 + t + PNT];
+  lp.f0 = has_f ? lnp[2048 + t] : 0.f; lp.f1 = has_f ? lnp[2048 + t + PNT] : 0.f;
+  stage_ln<MR>(sx, B, value, lp, red);
+}
+
+// out-proj input: softmax-combine the key splits.  (m, l) of every (b, head, split) first go to shared memory, then
+// each thread folds its columns with all split loads in flight at once.
+template <int MR>
+__device__ __forceinline__ void stage_att(float* sx, const PParams& p, int B, float* sml /*[B*16*nsplit*2]*/) {
+  const int tid = threadIdx.x;
+  const int npairs = B * kH * p.nsplit;
+  for (int i = tid; i < npairs * 2; i += PNT) {
+    const int pair = i >> 1, which = i & 1;
+    sml[i] = __ldcg(p.part + (size_t)pair * (kDH + 2) + which);
+  }
+  __syncthreads();
+  for (int i = tid; i < B * kD; i += PNT) {
+    const int b = i / kD, c = i % kD, h = c >> 6, d = c & 63;
+    const float* ml = sml + (size_t)(b * kH + h) * p.nsplit * 2;
+    const float* po = p.part + ((size_t)(b * kH + h) * p.nsplit) * (kDH + 2) + 2 + d;
+    float o[16];
+#pragma unroll
+    for (int s2 = 0; s2 < 16; ++s2) o[s2] = (s2 < p.nsplit) ? __ldcg(po + (size_t)s2 * (kDH + 2)) : 0.f;
+    float M = -INFINITY;
+    for (int s2 = 0; s2 < p.nsplit; ++s2) M = fmaxf(M, ml[2 * s2]);
+    float L = 0.f, O = 0.f;
+#pragma unroll
+    for (int s2 = 0; s2 < 16; ++s2) {
+      if (s2 < p.nsplit) {
+        const float ms = ml[2 * s2];
+        const float w = (ms == -INFINITY) ? 0.f : expf(ms - M);
+        L += w * ml[2 * s2 + 1];
+        O += w * o[s2];
+      }
+    }
+    for (int s2 = 16; s2 < p.nsplit; ++s2) {  // nsplit > 16 only for very long contexts
+      const float ms = ml[2 * s2];
+      const float w = (ms == -INFINITY) ? 0.f : expf(ms - M);
+      L += w * ml[2 * s2 + 1];
+      O += w * __ldcg(po + (size_t)s2 * (kDH + 2));
+    }
+    sx[i] = ld_cg(p.bt.finished + b) ? 0.f : O / L;
+  }
+  __syncthreads();
+}
+
+template <int MR>
+__global__ void __launch_bounds__(PNT, 1) ar_decode_ring_kernel(const PParams p) {
+  using namespace tc;
+  extern __shared__ __align__(128) uint8_t rsm[];
+  uint8_t* ring = rsm;                                                   // [2][RSTAGE_BYTES]
+  float* sx = reinterpret_cast<float*>(rsm + 2 * RSTAGE_BYTES);          // [MR][1024]
+  float* scratch = sx + MR * kD;                                         // attention / sampling / LN scratch
+  uint64_t* rbar = reinterpret_cast<uint64_t*>(rsm + 2 * RSTAGE_BYTES + (size_t)MR * kD * 4 + 32768);
+  const Batch& bt = p.bt;
+  const int B = bt.B;
+  const int tid = threadIdx.x;
+  unsigned int epoch = 0;
+
+  int q0, q1, o0, o1, f0, f1, pr0, pr1;
+  slice(3 * kD, q0, q1);
+  slice(kD, o0, o1);
+  slice(kFF, f0, f1);
+  slice(kARLogits, pr0, pr1);
+  const int per = gridDim.x / 4;
+  const int kc = min((int)blockIdx.x / per, 3);
+  const int kc_first = kc * per;
+  const int kc_n = (kc == 3) ? (int)gridDim.x - kc_first : per;
+  const int g0 = (int)(((long long)(blockIdx.x - kc_first) * kD) / kc_n);
+  const int g1 = (int)(((long long)(blockIdx.x - kc_first + 1) * kD) / kc_n);
+
+  // GEMV phase c of the 49-phase cycle of one step: 4 per layer (qkv, out, ff1, ff2) + the predict layer
+  auto slice_of = [&](int c) {
+    RSlice s{};
+    if (c == 4 * kL) {
+      s.W = reinterpret_cast<const bf16*>(p.predict_w); s.ldw = kD; s.r0 = pr0; s.r1 = pr1; s.N = kARLogits;
+      s.lg = p.norm_g; s.lb = p.norm_b; s.lf = p.layer[kL - 1].ff2_b;
+      return s;
+    }
+    const int l = c >> 2, kind = c & 3;
+    const PLayer& L = p.layer[l];
+    const float* fb_prev = (l > 0) ? p.layer[l - 1].ff2_b : nullptr;
+    if (kind == 0) { s.W = (const bf16*)L.qkv_w; s.ldw = kD; s.r0 = q0; s.r1 = q1; s.N = 3 * kD; s.bias = L.qkv_b; s.lg = L.n1_g; s.lb = L.n1_b; s.lf = fb_prev; }
+    else if (kind == 1) { s.W = (const bf16*)L.out_w; s.ldw = kD; s.r0 = o0; s.r1 = o1; s.N = kD; s.bias = L.out_b; s.bias2 = fb_prev; }
+    else if (kind == 2) { s.W = (const bf16*)L.ff1_w; s.ldw = kD; s.r0 = f0; s.r1 = f1; s.N = kFF; s.bias = L.ff1_b; s.lg = L.n2_g; s.lb = L.n2_b; }
+    else { s.W = (const bf16*)L.ff2_w + (size_t)kc * kD; s.ldw = kFF; s.r0 = g0; s.r1 = g1; s.N = kD; }
+    return s;
+  };
+  constexpr int CYC = 4 * kL + 1;
+  if (tid == 0) {
+    mbar_init(&rbar[0], 1); mbar_init(&rbar[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  int g = 0;  // GEMV phases consumed so far (phase g lives in ring slot g & 1, its mbarrier parity is (g >> 1) & 1)
+  if (tid == 0) {
+    ring_issue(ring, &rbar[0], slice_of(0));
+    ring_issue(ring + RSTAGE_BYTES, &rbar[1], slice_of(1));
+  }
+  long long* prof = nullptr;
+  const int prof_slot = (blockIdx.x == 0) ? 0 : (blockIdx.x == gridDim.x / 2) ? 1 : (blockIdx.x == gridDim.x - 1) ? 2 : -1;
+
+  // finish GEMV phase g: after every thread has left the slot, thread 0 refills it with phase g + 2, then the grid barrier
+  auto next_phase = [&]() {
+    __syncthreads();
+    if (tid == 0) ring_issue(ring + (g & 1) * RSTAGE_BYTES, &rbar[g & 1], slice_of((g + 2) % CYC));
+    ++g;
+    grid_barrier(p.bar, epoch, prof);
+  };
+
+  int steps = 0;
+  for (int step = 0; step < p.max_steps; ++step) {
+    if (p.prof && prof_slot >= 0 && tid == 0) {
+      if (step == p.prof_step0) prof = p.prof + (size_t)prof_slot * 4096;
+      if (step == p.prof_step0 + 4) prof = nullptr;
+    }
+    // ---- S0 ----
+    for (int b = blockIdx.x; b < B; b += gridDim.x)
+      if (!ld_cg(bt.finished + b)) sample_utterance(p, b, scratch);
+    grid_barrier(p.bar, epoch, prof);
+    ++steps;
+    if (!p.ignore_eos && ld_cg(bt.n_active) <= 0) break;
+    if (step == p.max_steps - 1) break;
+
+    for (int l = 0; l < kL; ++l) {
+      // ---- P1: LN1 + QKV ----
+      for (int u = blockIdx.x; u < B * kH * p.nsplit; u += gridDim.x) {
+        if (tid == 0) {  // K/V ranges of the coming attention units -> L2
+          const int split = u % p.nsplit, bh = u / p.nsplit, b = bh / kH, h = bh % kH;
+          const int n = bt.S[b] + bt.P[b] + ld_cg(bt.T + b) + 1;
+          int chunk = (n + p.nsplit - 1) / p.nsplit;
+          chunk = (chunk + 31) & ~31;
+          const int j0 = split * chunk, j1 = min(n - 1, j0 + chunk);
+          if (j1 > j0) {
+            const size_t off = ((size_t)l * p.kv_layer_elems + ((size_t)b * kH + h) * p.ctx_cap * kDH + (size_t)j0 * kDH) * 2;
+            l2_prefetch(reinterpret_cast<const char*>(p.kc) + off, (size_t)(j1 - j0) * kDH * 2);
+            l2_prefetch(reinterpret_cast<const char*>(p.vc) + off, (size_t)(j1 - j0) * kDH * 2);
+          }
+        }
+      }
+      {
+        const RSlice s = slice_of(g % CYC);
+        const uint8_t* slot = ring + (g & 1) * RSTAGE_BYTES;
+        mbar_wait(&rbar[g & 1], (g >> 1) & 1);
+        PSTAMP(6);
+        ring_stage_ln<MR>(sx, B, [&](int m, int c) { return stream_dyn(p, l, m, c, B); }, slot, s.lf != nullptr, scratch);
+        PSTAMP(3);
+        ring_finish<MR>(slot, s, sx, B, [&](int, int) { return 0.f; },
+                        [&](int n, int m, float v) { p.qkv[(size_t)m * 3 * kD + n] = v; });
+        PSTAMP(4);
+        next_phase();
+      }
+      // ---- P2: attention ----
+      for (int u = blockIdx.x; u < B * kH * p.nsplit; u += gridDim.x) {
+        const int split = u % p.nsplit, bh = u / p.nsplit;
+        const int b = bh / kH, h = bh % kH;
+        if (ld_cg(bt.finished + b)) continue;
+        attn_unit<bf16>(p, l, b, h, split, scratch);
+      }
+      grid_barrier(p.bar, epoch, prof);
+      // ---- P3: combine splits + out-proj + residual ----
+      {
+        const RSlice s = slice_of(g % CYC);
+        const uint8_t* slot = ring + (g & 1) * RSTAGE_BYTES;
+        stage_att<MR>(sx, p, B, scratch);
+        PSTAMP(3);
+        mbar_wait(&rbar[g & 1], (g >> 1) & 1);
+        PSTAMP(6);
+        ring_finish<MR>(slot, s, sx, B, [&](int n, int m) { return stream_dyn(p, l, m, n, B); },
+                        [&](int n, int m, float v) { p.xa[(size_t)m * kD + n] = v; });
+        PSTAMP(4);
+        next_phase();
+      }
+      // ---- P4: LN2 + FFN1 + ReLU ----
+      {
+        const RSlice s = slice_of(g % CYC);
+        const uint8_t* slot = ring + (g & 1) * RSTAGE_BYTES;
+        mbar_wait(&rbar[g & 1], (g >> 1) & 1);
+        PSTAMP(6);
+        ring_stage_ln<MR>(sx, B, [&](int m, int c) { return __ldcg(p.xa + (size_t)m * kD + c); }, slot, false, scratch);
+        PSTAMP(3);
+        ring_finish<MR>(slot, s, sx, B, [&](int, int) { return 0.f; },
+                        [&](int n, int m, float v) { p.hid[(size_t)m * kFF + n] = fmaxf(v, 0.f); });
+        PSTAMP(4);
+        next_phase();
+      }
+      // ---- P5: FFN2 split-K ----
+      {
+        const RSlice s = slice_of(g % CYC);
+        const uint8_t* slot = ring + (g & 1) * RSTAGE_BYTES;
+        stage_plain(sx, B, [&](int m, int c) { return __ldcg(p.hid + (size_t)m * kFF + kc * kD + c); });
+        PSTAMP(3);
+        mbar_wait(&rbar[g & 1], (g >> 1) & 1);
+        PSTAMP(6);
+        ring_finish<MR>(slot, s, sx, B, [&](int, int) { return 0.f; },
+                        [&](int n, int m, float v) { p.pf[((size_t)kc * B + m) * kD + n] = v; });
+        PSTAMP(4);
+        next_phase();
+      }
+    }
+    // ---- PF: final LN + predict ----
+    {
+      const RSlice s = slice_of(g % CYC);
+      const uint8_t* slot = ring + (g & 1) * RSTAGE_BYTES;
+      mbar_wait(&rbar[g & 1], (g >> 1) & 1);
+      ring_stage_ln<MR>(sx, B, [&](int m, int c) { return stream_dyn(p, kL, m, c, B); }, slot, true, scratch);
+      ring_finish<MR>(slot, s, sx, B, [&](int, int) { return 0.f; },
+                      [&](int n, int m, float v) { p.logits[(size_t)m * kARLogits + n] = v; });
+      next_phase();
+    }
+  }
+  // drain the two bulk-copy groups still in flight before the CTA (and its shared memory) goes away
+  mbar_wait(&rbar[g & 1], (g >> 1) & 1);
+  mbar_wait(&rbar[(g + 1) & 1], ((g + 1) >> 1) & 1);
+  if (blockIdx.x == 0 && tid == 0) *p.steps_done = steps;
+}
+
+template <int MR>
+static cudaError_t ring_launch(const PParams& p, int grid, cudaStream_t st) {
+  const size_t smem = 2 * (size_t)RSTAGE_BYTES + (size_t)MR * kD * 4 + 32768 + 64;
+  cudaError_t e = cudaFuncSetAttribute(ar_decode_ring_kernel<MR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  void* args[] = {(void*)&p};
+  return cudaLaunchCooperativeKernel((void*)ar_decode_ring_kernel<MR>, dim3(grid), dim3(PNT), args, smem, st);
 }
 
 template <typename WT, int MR>
 static cudaError_t persist_launch(const PParams& p, int grid, cudaStream_t st) {
-  const size_t kv_bytes = (sizeof(WT) == 2 && MR <= 8) ? 2 * (size_t)KVS_KEYS * kDH * 2 : 0;
-  const size_t smem = kv_bytes + (size_t)MR * kD * 4 + 9216 * 4 + 64;
+  const size_t scratch_floats = 256 + PCHUNK + (PNT / 8) * kDH;             // attention
+  const size_t sample_floats = 1032 + PSORT + PSORT / 2 + PNT + 32 + 8;     // sampling
+  const size_t smem = ((size_t)MR * kD + std::max(scratch_floats, sample_floats)) * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(ar_decode_persistent_kernel<WT, MR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
@@ -802,10 +1064,18 @@ static cudaError_t persist_launch(const PParams& p, int grid, cudaStream_t st) {
   return cudaLaunchCooperativeKernel((void*)ar_decode_persistent_kernel<WT, MR>, dim3(grid), dim3(PNT), args, smem, st);
 }
 
-// wt: 0 fp32 / 1 bf16 (weights and KV cache).  B <= 32.  Returns a cudaError_t as int.
+// wt: 0 fp32 / 1 bf16.  B <= 32.  Returns a cudaError_t as int.
 int launch_decode_persistent(const void* params, int wt, int B, int grid, cudaStream_t st) {
   const PParams& p = *reinterpret_cast<const PParams*>(params);
   const int mr = B <= 1 ? 1 : B <= 2 ? 2 : B <= 4 ? 4 : B <= 8 ? 8 : B <= 16 ? 16 : 32;
+  if (wt == 1 && mr <= 8 && grid >= 128 && getenv("VX_DECODE_RING")) {  // experimental TMA-ring variant (slower: smem-bound dots)  // 28 rows/CTA max fits the 32-row ring slot
+    switch (mr) {
+      case 1: return (int)ring_launch<1>(p, grid, st);
+      case 2: return (int)ring_launch<2>(p, grid, st);
+      case 4: return (int)ring_launch<4>(p, grid, st);
+      default: return (int)ring_launch<8>(p, grid, st);
+    }
+  }
 #define VX_P(WT_, MR_) return (int)persist_launch<WT_, MR_>(p, grid, st)
   if (wt == 0) {
     switch (mr) { case 1: VX_P(float, 1); case 2: VX_P(float, 2); case 4: VX_P(float, 4); case 8: VX_P(float, 8); case 16: VX_P(float, 16); default: VX_P(float, 32); }

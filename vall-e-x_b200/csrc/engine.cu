@@ -760,6 +760,7 @@ int vx_ar_decode(vx_engine* e, int max_new, int top_k, float top_p, float temper
   if (!e->decode_graph && B <= 32) {
     // ---- persistent kernel: the whole token loop in one cooperative launch -------------------------------
     int ns = std::max(1, e->num_sms / (B * kH));
+    if (getenv("VX_DECODE_NSPLIT")) ns = std::max(1, atoi(getenv("VX_DECODE_NSPLIT")));
     ns = std::max(ns, (final_ctx + 2047) / 2048);
     ns = std::min(ns, 64);
     ENS(e->part, (size_t)B * kH * ns * (kDH + 2) * 4);
