@@ -205,17 +205,52 @@ __device__ __forceinline__ void gemv_finish(WPre<WT, MR>& pre, const WT* __restr
     const int n = r0 + warp + j * PNW;
     add[j] = (n < r1 && lane < B) ? addend(n, lane) : 0.f;
   }
+  if constexpr (kRows == 2) {
+    // both prefetched rows in ONE pass over x: the shared-memory reads of the activations (the bottleneck of a
+    // 16-warp GEMV phase) are shared by the two rows
+    const int n0 = r0 + warp, n1 = r0 + warp + PNW;
+    if (n0 < r1) {  // warp-uniform
+      float a0[MR], a1[MR];
 #pragma unroll
-  for (int j = 0; j < kRows; ++j) {
-    const int n = r0 + warp + j * PNW;
-    if (n < r1) {
-      float acc[MR];
-      row_dot<WT, MR>(pre.r[j], sx, acc);
-      float mine = 0.f;
+      for (int m = 0; m < MR; ++m) { a0[m] = 0.f; a1[m] = 0.f; }
 #pragma unroll
-      for (int m = 0; m < MR; ++m)
-        if (lane == m) mine = acc[m];
-      if (lane < B) emit(n, lane, mine + (add[j] + pre.bias[j]));
+      for (int it = 0; it < 4; ++it) {
+        float w0[8], w1[8];
+        raw_to_f32<WT>(pre.r[0], it, w0);
+        raw_to_f32<WT>(pre.r[1], it, w1);
+#pragma unroll
+        for (int m = 0; m < MR; ++m) {
+          const float4 x0 = *reinterpret_cast<const float4*>(&sx[m * kD + it * 256 + lane * 8]);
+          const float4 x1 = *reinterpret_cast<const float4*>(&sx[m * kD + it * 256 + lane * 8 + 4]);
+          const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { a0[m] = fmaf(w0[i], xv[i], a0[m]); a1[m] = fmaf(w1[i], xv[i], a1[m]); }
+        }
+      }
+      float m0 = 0.f, m1 = 0.f;
+#pragma unroll
+      for (int m = 0; m < MR; ++m) {
+        const float s0 = warp_sum(a0[m]), s1 = warp_sum(a1[m]);
+        if (lane == m) { m0 = s0; m1 = s1; }
+      }
+      if (lane < B) {
+        emit(n0, lane, m0 + (add[0] + pre.bias[0]));
+        if (n1 < r1) emit(n1, lane, m1 + (add[1] + pre.bias[1]));
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < kRows; ++j) {
+      const int n = r0 + warp + j * PNW;
+      if (n < r1) {
+        float acc[MR];
+        row_dot<WT, MR>(pre.r[j], sx, acc);
+        float mine = 0.f;
+#pragma unroll
+        for (int m = 0; m < MR; ++m)
+          if (lane == m) mine = acc[m];
+        if (lane < B) emit(n, lane, mine + (add[j] + pre.bias[j]));
+      }
     }
   }
   for (int n = r0 + warp + kRows * PNW; n < r1; n += PNW) {  // only when the grid is smaller than 148 CTAs
@@ -577,11 +612,29 @@ __device__ void attn_unit(const PParams& p, int layer, int b, int h, int split, 
 // softmax-combine the key splits of head c/64 for column c (fixed order -> deterministic)
 __device__ __forceinline__ float att_combined(const PParams& p, int b, int c) {
   const int h = c >> 6, d = c & 63;
-  const float* p0 = p.part + ((size_t)b * kH + h) * p.nsplit * (kDH + 2);
+  const int ns = p.nsplit;
+  const float* p0 = p.part + ((size_t)b * kH + h) * ns * (kDH + 2);
+  constexpr int U = 12;  // splits folded with every load in flight at once (one L2 round trip instead of 3*ns)
+  float mv[U], lv[U], ov[U];
+#pragma unroll
+  for (int s = 0; s < U; ++s) {
+    const bool ok = s < ns;
+    mv[s] = ok ? __ldcg(p0 + s * (kDH + 2)) : -INFINITY;
+    lv[s] = ok ? __ldcg(p0 + s * (kDH + 2) + 1) : 0.f;
+    ov[s] = ok ? __ldcg(p0 + s * (kDH + 2) + 2 + d) : 0.f;
+  }
   float M = -INFINITY;
-  for (int s = 0; s < p.nsplit; ++s) M = fmaxf(M, __ldcg(p0 + s * (kDH + 2)));
+#pragma unroll
+  for (int s = 0; s < U; ++s) M = fmaxf(M, mv[s]);
+  for (int s = U; s < ns; ++s) M = fmaxf(M, __ldcg(p0 + s * (kDH + 2)));
   float L = 0.f, O = 0.f;
-  for (int s = 0; s < p.nsplit; ++s) {
+#pragma unroll
+  for (int s = 0; s < U; ++s) {
+    const float w = (mv[s] == -INFINITY) ? 0.f : expf(mv[s] - M);
+    L += w * lv[s];
+    O += w * ov[s];
+  }
+  for (int s = U; s < ns; ++s) {
     const float ms = __ldcg(p0 + s * (kDH + 2));
     const float w = (ms == -INFINITY) ? 0.f : expf(ms - M);
     L += w * __ldcg(p0 + s * (kDH + 2) + 1);
