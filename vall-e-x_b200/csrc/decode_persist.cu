@@ -116,8 +116,17 @@ struct WPre {
 struct LnPre {        // LayerNorm parameters (+ previous layer's FFN2 bias) of this thread's two columns
   float g0, g1, b0, b1, f0, f1;
 };
-__device__ __forceinline__ void ln_issue(LnPre& lp, const float* __restrict__ g, const float* __restrict__ b,
+// Before a barrier: pull the NEXT LayerNorm's vectors (gamma, beta, previous FFN2 bias; 12 KB) towards L2 -- no
+// registers are held across the barrier.  ln_load (after the barrier) then hits L2 and overlaps the activation loads.
+__device__ __forceinline__ void ln_issue(LnPre&, const float* __restrict__ g, const float* __restrict__ b,
                                          const float* __restrict__ fb) {
+  const int t = threadIdx.x;
+  if (t < 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(g + t * 32));
+  else if (t < 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + (t - 32) * 32));
+  else if (t < 96 && fb) asm volatile("prefetch.global.L2 [%0];" ::"l"(fb + (t - 64) * 32));
+}
+__device__ __forceinline__ void ln_load(LnPre& lp, const float* __restrict__ g, const float* __restrict__ b,
+                                        const float* __restrict__ fb) {
   const int t = threadIdx.x;
   lp.g0 = g[t]; lp.g1 = g[t + PNT]; lp.b0 = b[t]; lp.b1 = b[t + PNT];
   lp.f0 = fb ? fb[t] : 0.f; lp.f1 = fb ? fb[t + PNT] : 0.f;
@@ -715,6 +724,7 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_persistent_kernel(const PPar
           }
         }
       }
+      ln_load(lp, L.n1_g, L.n1_b, fb_prev);
       stage_ln<MR>(sx, B, [&](int m, int c) { return stream_dyn(p, l, m, c, B); }, lp, scratch);
       PSTAMP(3);
       gemv_finish<WT, MR>(pre, Wq, kD, q0, q1, sx, B, L.qkv_b, nullptr, [&](int, int) { return 0.f; },
@@ -743,6 +753,7 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_persistent_kernel(const PPar
       PSTAMP(5);
       grid_barrier(p.bar, epoch, prof);
       // ---- P4: LN2 + FFN1 + ReLU -------------------------------------------------------------------------------
+      ln_load(lp, L.n2_g, L.n2_b, nullptr);
       stage_ln<MR>(sx, B, [&](int m, int c) { return __ldcg(p.xa + (size_t)m * kD + c); }, lp, scratch);
       PSTAMP(3);
       gemv_finish<WT, MR>(pre, W1, kD, f0, f1, sx, B, L.ff1_b, nullptr, [&](int, int) { return 0.f; },
@@ -767,6 +778,7 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_persistent_kernel(const PPar
       grid_barrier(p.bar, epoch, prof);
     }
     // ---- PF: final LayerNorm + predict rows -> logits ---------------------------------------------------------
+    ln_load(lp, p.norm_g, p.norm_b, p.layer[kL - 1].ff2_b);
     stage_ln<MR>(sx, B, [&](int m, int c) { return stream_dyn(p, kL, m, c, B); }, lp, scratch);
     gemv_finish<WT, MR>(pre, reinterpret_cast<const WT*>(p.predict_w), kD, pr0, pr1, sx, B, nullptr, nullptr,
                         [&](int, int) { return 0.f; },
