@@ -13,7 +13,7 @@
 
 namespace vx {
 
-constexpr int FQ = 128, FK = 64;  // 4 warps x 32 query rows; every K/V fragment feeds two m16 tiles
+constexpr int FQ = 64, FK = 64;
 
 __device__ __forceinline__ uint32_t swz(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
 
@@ -41,13 +41,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(b)) << 16);
 }
 
-__global__ void __launch_bounds__(128, 2) attn_tc_kernel(Batch bt, const bf16* __restrict__ qkv,
-                                                         const int32_t* __restrict__ row0, int mode,
-                                                         uint8_t* __restrict__ out_img) {
-  extern __shared__ __align__(1024) uint8_t attn_sm[];
-  uint8_t* sQ = attn_sm;                         // [128][128 B]
-  uint8_t* sK = attn_sm + FQ * 128;              // [2][64][128 B]
-  uint8_t* sV = sK + 2 * FK * 128;               // [2][64][128 B]
+__global__ void __launch_bounds__(128) attn_tc_kernel(Batch bt, const bf16* __restrict__ qkv,
+                                                      const int32_t* __restrict__ row0, int mode,
+                                                      uint8_t* __restrict__ out_img) {
+  __shared__ __align__(1024) uint8_t sQ[FQ * 128];
+  __shared__ __align__(1024) uint8_t sK[2][FK * 128];
+  __shared__ __align__(1024) uint8_t sV[2][FK * 128];
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * FQ;
   const int S = bt.S[b];
   const int len = (mode == 1) ? S + bt.P[b] + 1 : S + bt.P[b] + bt.T[b];
@@ -66,12 +65,13 @@ __global__ void __launch_bounds__(128, 2) attn_tc_kernel(Batch bt, const bf16* _
       const int r = idx >> 3, c = idx & 7;
       const bool ok = (k0 + r) < len;
       const bf16* src = base + (size_t)(ok ? (k0 + r) : 0) * (3 * kD) + c * 8;
-      cp_async16(sK + buf * FK * 128 + swz(r, c), src + kD, ok);
-      cp_async16(sV + buf * FK * 128 + swz(r, c), src + 2 * kD, ok);
+      cp_async16(sK[buf] + swz(r, c), src + kD, ok);
+      cp_async16(sV[buf] + swz(r, c), src + 2 * kD, ok);
     }
   };
+  // Q tile (64 x 64 bf16)
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {  // Q tile: 128 rows x 8 chunks
+  for (int i = 0; i < 4; ++i) {
     const int idx = tid + i * 128;
     const int r = idx >> 3, c = idx & 7;
     const bool ok = (q0 + r) < len;
@@ -80,16 +80,15 @@ __global__ void __launch_bounds__(128, 2) attn_tc_kernel(Batch bt, const bf16* _
   load_kv(0, 0);
   cp_async_commit();
 
-  float o[2][8][4];
+  float o[8][4];
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int j = 0; j < 8; ++j)
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) o[mt][j][i] = 0.f;
-  float m_r[2][2] = {{-INFINITY, -INFINITY}, {-INFINITY, -INFINITY}}, l_r[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-  uint32_t qf[2][4][4];
+    for (int i = 0; i < 4; ++i) o[j][i] = 0.f;
+  float m_r[2] = {-INFINITY, -INFINITY}, l_r[2] = {0.f, 0.f};
+  uint32_t qf[4][4];
   const float sl2 = 0.125f * 1.44269504088896340736f;  // 1/sqrt(64) * log2(e)
+  const int qrow_lo = q0 + warp * 16 + (lane >> 2);
 
   for (int t = 0; t < ntiles; ++t) {
     const int buf = t & 1;
@@ -99,120 +98,103 @@ __global__ void __launch_bounds__(128, 2) attn_tc_kernel(Batch bt, const bf16* _
     __syncthreads();
     if (t == 0) {
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const int r = warp * 32 + mt * 16 + (lane & 15), c = kk * 2 + (lane >> 4);
-          ldsm_x4(tc::smem_u32(sQ + swz(r, c)), qf[mt][kk][0], qf[mt][kk][1], qf[mt][kk][2], qf[mt][kk][3]);
-        }
+      for (int kk = 0; kk < 4; ++kk) {  // A fragments of this warp's 16 query rows
+        const int r = warp * 16 + (lane & 15), c = kk * 2 + (lane >> 4);
+        ldsm_x4(tc::smem_u32(sQ + swz(r, c)), qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3]);
+      }
     }
-    const uint8_t* kt = sK + buf * FK * 128;
-    const uint8_t* vt = sV + buf * FK * 128;
-    float s[2][8][4];
+    float s[8][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int j = 0; j < 8; ++j)
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) s[mt][j][i] = 0.f;
+      for (int i = 0; i < 4; ++i) s[j][i] = 0.f;
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
-      for (int jp = 0; jp < 4; ++jp) {
+      for (int jp = 0; jp < 4; ++jp) {  // two key n-tiles per ldmatrix.x4
         uint32_t b0, b1, b2, b3;
         const int r = jp * 16 + (lane & 7) + ((lane >> 4) << 3), c = kk * 2 + ((lane >> 3) & 1);
-        ldsm_x4(tc::smem_u32(kt + swz(r, c)), b0, b1, b2, b3);
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          mma_bf16(s[mt][2 * jp], qf[mt][kk][0], qf[mt][kk][1], qf[mt][kk][2], qf[mt][kk][3], b0, b1);
-          mma_bf16(s[mt][2 * jp + 1], qf[mt][kk][0], qf[mt][kk][1], qf[mt][kk][2], qf[mt][kk][3], b2, b3);
-        }
+        ldsm_x4(tc::smem_u32(sK[buf] + swz(r, c)), b0, b1, b2, b3);
+        mma_bf16(s[2 * jp], qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3], b0, b1);
+        mma_bf16(s[2 * jp + 1], qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3], b2, b3);
       }
     }
+    // mask + online softmax (rows qrow_lo and qrow_lo + 8)
     const int k0 = t * FK;
-    uint32_t pf[2][4][4];
+    float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-      const int qrow_lo = q0 + warp * 32 + mt * 16 + (lane >> 2);
-      float mx[2] = {-INFINITY, -INFINITY};
+    for (int j = 0; j < 8; ++j)
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int kj = k0 + j * 8 + (lane & 3) * 2 + (i & 1);
-          const int qi = qrow_lo + ((i >> 1) << 3);
-          bool vis = kj < len;
-          if (mode == 1) vis = vis && (kj < S || kj <= qi);
-          s[mt][j][i] = vis ? s[mt][j][i] * sl2 : -INFINITY;
-          mx[i >> 1] = fmaxf(mx[i >> 1], s[mt][j][i]);
-        }
-      float corr[2];
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
-        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
-        const float m_new = fmaxf(m_r[mt][r], mx[r]);
-        corr[r] = (m_new == -INFINITY) ? 1.f : exp2f(m_r[mt][r] - m_new);
-        m_r[mt][r] = m_new;
+      for (int i = 0; i < 4; ++i) {
+        const int kj = k0 + j * 8 + (lane & 3) * 2 + (i & 1);
+        const int qi = qrow_lo + ((i >> 1) << 3);
+        bool vis = kj < len;
+        if (mode == 1) vis = vis && (kj < S || kj <= qi);
+        s[j][i] = vis ? s[j][i] * sl2 : -INFINITY;
+        mx[i >> 1] = fmaxf(mx[i >> 1], s[j][i]);
       }
-      float rs[2] = {0.f, 0.f};
+    float corr[2];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float pv[4];
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      const float m_new = fmaxf(m_r[r], mx[r]);
+      corr[r] = (m_new == -INFINITY) ? 1.f : exp2f(m_r[r] - m_new);
+      m_r[r] = m_new;
+    }
+    float rs[2] = {0.f, 0.f};
+    uint32_t pf[4][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          pv[i] = (s[mt][j][i] == -INFINITY) ? 0.f : exp2f(s[mt][j][i] - m_r[mt][i >> 1]);
-          rs[i >> 1] += pv[i];
-        }
-        pf[mt][j >> 1][(j & 1) * 2 + 0] = pack_bf16(pv[0], pv[1]);
-        pf[mt][j >> 1][(j & 1) * 2 + 1] = pack_bf16(pv[2], pv[3]);
+    for (int j = 0; j < 8; ++j) {
+      float p[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float mref = m_r[i >> 1];
+        p[i] = (s[j][i] == -INFINITY) ? 0.f : exp2f(s[j][i] - mref);
+        rs[i >> 1] += p[i];
       }
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 1);
-        rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 2);
-        l_r[mt][r] = l_r[mt][r] * corr[r] + rs[r];
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        o[mt][j][0] *= corr[0]; o[mt][j][1] *= corr[0]; o[mt][j][2] *= corr[1]; o[mt][j][3] *= corr[1];
-      }
+      pf[j >> 1][(j & 1) * 2 + 0] = pack_bf16(p[0], p[1]);
+      pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p[2], p[3]);
     }
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
+    for (int r = 0; r < 2; ++r) {
+      rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 1);
+      rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 2);
+      l_r[r] = l_r[r] * corr[r] + rs[r];
+    }
 #pragma unroll
-      for (int dp = 0; dp < 4; ++dp) {
+    for (int j = 0; j < 8; ++j) {
+      o[j][0] *= corr[0]; o[j][1] *= corr[0]; o[j][2] *= corr[1]; o[j][3] *= corr[1];
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {      // keys 16kk .. 16kk+15
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {    // two d n-tiles per ldmatrix.x4.trans
         uint32_t b0, b1, b2, b3;
         const int r = kk * 16 + (lane & 7) + (((lane >> 3) & 1) << 3), c = dp * 2 + (lane >> 4);
-        ldsm_x4_t(tc::smem_u32(vt + swz(r, c)), b0, b1, b2, b3);
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          mma_bf16(o[mt][2 * dp], pf[mt][kk][0], pf[mt][kk][1], pf[mt][kk][2], pf[mt][kk][3], b0, b1);
-          mma_bf16(o[mt][2 * dp + 1], pf[mt][kk][0], pf[mt][kk][1], pf[mt][kk][2], pf[mt][kk][3], b2, b3);
-        }
+        ldsm_x4_t(tc::smem_u32(sV[buf] + swz(r, c)), b0, b1, b2, b3);
+        mma_bf16(o[2 * dp], pf[kk][0], pf[kk][1], pf[kk][2], pf[kk][3], b0, b1);
+        mma_bf16(o[2 * dp + 1], pf[kk][0], pf[kk][1], pf[kk][2], pf[kk][3], b2, b3);
       }
     }
     __syncthreads();  // everyone done with buf before it is refilled two iterations later
   }
   cp_async_wait<0>();
-  // normalise, stage through sQ (this warp's 32 rows only), then 16-byte stores into the tile image
+  // normalise, stage through sQ (this warp's 16 rows only), then 16-byte stores into the tile image
+  const float inv0 = 1.0f / l_r[0], inv1 = 1.0f / l_r[1];
   __syncwarp();
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt) {
-    const float inv0 = 1.0f / l_r[mt][0], inv1 = 1.0f / l_r[mt][1];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int r_lo = warp * 32 + mt * 16 + (lane >> 2);
-      const int within = (lane & 3) * 4;
-      *reinterpret_cast<uint32_t*>(sQ + swz(r_lo, j) + within) = pack_bf16(o[mt][j][0] * inv0, o[mt][j][1] * inv0);
-      *reinterpret_cast<uint32_t*>(sQ + swz(r_lo + 8, j) + within) = pack_bf16(o[mt][j][2] * inv1, o[mt][j][3] * inv1);
-    }
+  for (int j = 0; j < 8; ++j) {
+    const int r_lo = warp * 16 + (lane >> 2), c = j;       // chunk j holds d 8j..8j+7
+    const int within = (lane & 3) * 4;                      // byte offset of this thread's pair inside the chunk
+    *reinterpret_cast<uint32_t*>(sQ + swz(r_lo, c) + within) = pack_bf16(o[j][0] * inv0, o[j][1] * inv0);
+    *reinterpret_cast<uint32_t*>(sQ + swz(r_lo + 8, c) + within) = pack_bf16(o[j][2] * inv1, o[j][3] * inv1);
   }
   __syncwarp();
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int idx = lane + i * 32;  // 32 rows x 8 chunks
-    const int r = warp * 32 + (idx >> 3), c = idx & 7;
+  for (int i = 0; i < 4; ++i) {
+    const int idx = lane + i * 32;  // 16 rows x 8 chunks
+    const int r = warp * 16 + (idx >> 3), c = idx & 7;
     const int qi = q0 + r;
     if (qi < len) {
       const uint4 v = *reinterpret_cast<const uint4*>(sQ + swz(r, c));
@@ -224,16 +206,8 @@ __global__ void __launch_bounds__(128, 2) attn_tc_kernel(Batch bt, const bf16* _
 void launch_attn_tc(const Batch& bt, const void* qkv_bf16, const int32_t* row0, int mode, int max_len, void* out_img,
                     cudaStream_t st) {
   if (max_len <= 0) return;
-  const int smem = FQ * 128 + 4 * FK * 128;  // 48 KB
-  static bool attr_done[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!attr_done[dev & 63]) {
-    cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr_done[dev & 63] = true;
-  }
-  attn_tc_kernel<<<dim3((max_len + FQ - 1) / FQ, kH, bt.B), 128, smem, st>>>(bt, (const bf16*)qkv_bf16, row0, mode,
-                                                                             (uint8_t*)out_img);
+  attn_tc_kernel<<<dim3((max_len + FQ - 1) / FQ, kH, bt.B), 128, 0, st>>>(bt, (const bf16*)qkv_bf16, row0, mode,
+                                                                          (uint8_t*)out_img);
 }
 
 // bf16 qkv rows -> KV cache (bf16) for the AR prefill in bf16 mode
