@@ -104,5 +104,49 @@ def main(names):
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
 
 
+def make_eos_cases():
+    """True EOS termination (models/vallex.py:574): random-init weights never emit EOS, so row 1024 of
+    ar_predict_layer.weight is crafted from the reference's own final hidden state at step t* (w = c * h / |h|^2 makes the
+    EOS logit exactly c there) and the REFERENCE is re-run with the patched checkpoint; a candidate is kept only if the
+    reference really stops at T == t*.  t* = 0 is the "first sample is EOS" edge (T = 0, NAR on an empty target)."""
+    torch.set_num_threads(os.cpu_count())
+    seed, x, Lp, prompt, pl, tl = build_inputs("tiny_en")
+    sd = synthetic_state_dict(seed)
+    model = ref_shim.load_reference_valle(sd)
+    hs, lg = [], []
+    h1 = model.ar_decoder.norm.register_forward_hook(lambda m, i, o: hs.append(o.detach()[0, -1].clone()))
+    h2 = model.ar_predict_layer.register_forward_hook(lambda m, i, o: lg.append(o.detach()[0].clone()))
+    with torch.no_grad():
+        model.inference(torch.from_numpy(x)[None], torch.tensor([len(x)]), torch.from_numpy(prompt)[None], enroll_x_lens=Lp,
+                        top_k=1, temperature=1.0, prompt_language=pl, text_language=tl)
+    h1.remove(); h2.remove()
+    for name, cands in (("eos_mid", [37, 23, 41, 29, 53]), ("eos_first", [0])):
+        for t in cands:
+            h = hs[t]
+            c = float(lg[t].max()) + 1.0
+            row = (c * h / (h * h).sum()).float()
+            sd2 = dict(sd)
+            w = sd["ar_predict_layer.weight"].clone()
+            w[1024] = row
+            sd2["ar_predict_layer.weight"] = w
+            m2 = ref_shim.load_reference_valle(sd2)
+            with torch.no_grad():
+                codes = m2.inference(torch.from_numpy(x)[None], torch.tensor([len(x)]), torch.from_numpy(prompt)[None],
+                                     enroll_x_lens=Lp, top_k=1, temperature=1.0, prompt_language=pl, text_language=tl)
+            T = codes.shape[1]
+            print(f"{name}: t*={t} -> reference T={T}", flush=True)
+            if T == t:
+                np.savez_compressed(os.path.join(OUT, name + ".npz"), x=x, Lp=np.int64(Lp), prompt=prompt,
+                                    prompt_language=np.array(pl), text_language=np.array([tl]),
+                                    text_language_is_list=np.bool_(False), seed=np.int64(seed),
+                                    eos_row=row.numpy().astype(np.float32), codes=codes[0].numpy().astype(np.int16))
+                break
+        else:
+            raise SystemExit(f"no EOS candidate worked for {name}")
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["eos"]:
+        make_eos_cases()
+        sys.exit(0)
     main(sys.argv[1:] or [n for n in CASES if n != "cfg1_librispeech"])

@@ -116,6 +116,33 @@ def test_graph_decode_path_matches_persistent(monkeypatch):
     m.engine.close()
 
 
+@pytest.mark.parametrize("name,T", [("eos_mid", 37), ("eos_first", 0)])
+def test_true_eos_termination(name, T):
+    """The decode loop stops on a sampled EOS exactly where the reference does (fixture: reference run with a crafted
+    EOS row), including the T = 0 edge where the first sample is EOS and the NAR sees an empty target."""
+    g = load_golden(name)
+    sd = dict(state_dict_for(g["seed"]))
+    w = sd["ar_predict_layer.weight"].clone()
+    w[1024] = torch.from_numpy(g["eos_row"])
+    sd["ar_predict_layer.weight"] = w
+    for dtype in ("fp32", "bf16"):
+        m = _valle(sd, dtype, max_ctx=256)
+        got = _infer(m, g)[0].numpy()
+        assert got.shape == (T, 8), (dtype, got.shape)
+        if dtype == "fp32":
+            assert np.array_equal(got, g["codes"].astype(np.int64))
+        m.engine.close()
+
+
+def test_best_of_greedy_beams_agree():
+    """best_of replicas under top_k=1 are identical beams (models/vallex.py:525-527,583-594): same tokens as best_of=1."""
+    g = load_golden("tiny_en")
+    m = _valle(state_dict_for(g["seed"]), "fp32", max_ctx=256, max_batch=3)
+    got = _infer(m, g, best_of=3)[0].numpy()
+    assert np.array_equal(got, g["codes"].astype(np.int64))
+    m.engine.close()
+
+
 def test_max_new_tokens_is_a_prefix():
     g = load_golden("mid_ja")
     got = _infer(model_for(g["seed"], "fp32"), g, max_new_tokens=20)[0].numpy()

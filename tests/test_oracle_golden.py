@@ -48,6 +48,20 @@ def test_oracle_prefix_of_full_size_case():
     assert np.array_equal(yy[0, 1 + y.shape[1]:].numpy(), g["codes"][:24, 0].astype(np.int64))
 
 
+@pytest.mark.parametrize("name,T", [("eos_mid", 37), ("eos_first", 0)])
+def test_oracle_true_eos_termination(name, T):
+    """EOS sampled by the model (models/vallex.py:574): row 1024 of the predict layer is crafted in the fixture so the
+    REFERENCE stops after T tokens (T = 0: the very first sample is EOS, NAR runs on an empty target)."""
+    g = load_golden(name)
+    sd = dict(state_dict_for(g["seed"]))
+    w = sd["ar_predict_layer.weight"].clone()
+    w[1024] = torch.from_numpy(g["eos_row"])
+    sd["ar_predict_layer.weight"] = w
+    codes = _run(OracleVALLE(sd), g)[0].numpy()
+    assert codes.shape == (T, 8) == g["codes"].shape
+    assert np.array_equal(codes, g["codes"].astype(np.int64))
+
+
 def test_golden_edge_cases_present():
     assert load_golden("noprompt_en")["prompt"].shape == (0, 8)       # no prompt: P = 0, Lp = 0
     assert bool(load_golden("mixlang")["text_language_is_list"])      # per-token language list
