@@ -320,6 +320,10 @@ def main():
     bytes_step = wbytes + KV_BYTES_PER_KEY * kvb * (L_mean + 1)
     peak, how = peaks()
     ach = bytes_step / t_step / 1e9
+    traffic = None  # measured DRAM bytes per decode step from the committed ncu --set full capture of this kernel
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.isfile(tp) and a.dtype == "bf16":
+        traffic = json.load(open(tp))
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, a.min_warmup),
         "ms_per_step": 1e3 * elapsed / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -334,7 +338,8 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": {"kernel": "ar_decode_persistent_kernel (one launch = all decode steps; per-step figures)", "bound": "hbm",
-                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": (traffic or {}).get("dram_bytes_per_step"),
+                     "traffic_note": (None if traffic is None else f"per decode step, {traffic['capture']} ({traffic['source']}); algorithmic at that context: {traffic['algorithmic_bytes_per_step']:.0f} B"),
                      "peak_source": how, "bytes_per_step": bytes_step, "avg_step_us": t_step * 1e6, "mean_ctx": L_mean},
     }
     if not a.no_cpu_baseline:
