@@ -120,6 +120,8 @@ VX_API int vx_debug_read(vx_engine* e, const char* what, float* dst, int64_t max
  * through the bf16 tensor-core attention (mode 0 bidirectional, 1 AR prefill mask with S text rows). */
 VX_API int vx_debug_gemm_tc(const float* A, const float* W, const float* bias, float* C, int64_t M, int N, int K, int epi);
 VX_API int vx_debug_attn_tc(const float* qkv, float* out, int S, int len, int mode);
+/* same contract through the tcgen05/TMEM attention kernel (attention_t5.cu) */
+VX_API int vx_debug_attn_t5(const float* qkv, float* out, int S, int len, int mode);
 
 #ifdef __cplusplus
 }

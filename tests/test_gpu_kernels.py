@@ -34,14 +34,17 @@ def test_tcgen05_gemm(M, N, K, epi):
     assert err < tol * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("variant", ["tc", "t5"])
 @pytest.mark.parametrize("S,length,mode", [(6, 12, 1), (30, 200, 1), (122, 348, 1), (20, 64, 0), (40, 300, 0), (314, 1814, 0)])
-def test_tensor_core_attention(S, length, mode):
+def test_tensor_core_attention(S, length, mode, variant):
+    """variant tc: mma.sync flash attention (default); t5: tcgen05/TMEM two-pass attention (VX_ATTN_T5=1)."""
     from vallex_b200 import _capi
     lib = _capi.lib()
     g = torch.Generator().manual_seed(S * 1000 + length)
     qkv = torch.randn(length, 3072, generator=g)
     out = torch.zeros(length, 1024)
-    _capi.check(lib.vx_debug_attn_tc(_capi.ptr(qkv), _capi.ptr(out), S, length, mode), "attn_tc")
+    fn = lib.vx_debug_attn_tc if variant == "tc" else lib.vx_debug_attn_t5
+    _capi.check(fn(_capi.ptr(qkv), _capi.ptr(out), S, length, mode), "attn_" + variant)
     q, k, v = [_bf(t).view(length, 16, 64).transpose(0, 1).double() for t in qkv.split(1024, dim=-1)]
     att = (q @ k.transpose(-2, -1)) / 8.0
     if mode == 1:
@@ -50,5 +53,5 @@ def test_tensor_core_attention(S, length, mode):
         att = att.masked_fill(~((j < S) | (j <= i)), float("-inf"))
     ref = (torch.softmax(att, -1) @ v).transpose(0, 1).reshape(length, 1024)
     err = (out.double() - ref).abs().max().item()
-    print(f"attn_tc S={S} len={length} mode={mode}: max abs err {err:.3e}")
+    print(f"attn_{variant} S={S} len={length} mode={mode}: max abs err {err:.3e}")
     assert err < 3e-2

@@ -92,6 +92,9 @@ struct vx_engine {
   Buf d_text, d_lang, d_prompt, d_S, d_P, d_ar_row0, d_nar_row0, d_T, d_ctx, d_y, d_budget, d_fin, d_slp, d_nact;
   Buf x, xn, qkv, att, ffh, kc, vc;                 // prefill / NAR activations, KV cache
   Buf a_img, qkv16, att_img, h_img, t_img;           // bf16 mode: tile-image / bf16 activations
+  Buf q_img, k_img, vt_img;                          // per-head attention operand images (tcgen05 attention)
+  bool attn_t5 = false;                              // VX_ATTN_T5=1: tcgen05/TMEM attention instead of mma.sync
+  int64_t full_rows = 0;                             // packed rows of the current full-sequence pass (128-aligned starts)
   Buf xs, xsn, qkvs, atts, ffs, logits, part, tick;  // decode-step scratch
   Buf p_pf, p_bar, p_prof;                                   // persistent decode: FFN2 partials, barrier counter + steps
   int num_sms = 148;
@@ -286,7 +289,13 @@ int full_layer(vx_engine* e, const LayerW& L, int64_t R, const int32_t* row0, in
     launch_layernorm_image(x, nullptr, R, L.n1_g, L.n1_b, ada1, ada1 ? ada1 + kD : nullptr, 1e-5f, e->a_img.p, st);
     launch_gemm_tc(e->a_img.p, L.qkv_i, L.qkv_b, e->qkv16.p, 3 * kD, R, 3 * kD, kD, TC_EPI_BF16_ROW, st);
     if (kv_layer >= 0) { launch_kv_scatter_bf16(bt, e->qkv16.p, kc, vc, maxlen, e->ctx_cap, st); e->launches++; }
-    launch_attn_tc(bt, e->qkv16.p, row0, attn_mode, maxlen, e->att_img.p, st);
+    if (e->attn_t5) {
+      launch_pack_qkv_heads(e->qkv16.p, e->full_rows, e->q_img.p, e->k_img.p, e->vt_img.p, st);
+      launch_attn_t5(bt, e->q_img.p, e->k_img.p, e->vt_img.p, e->full_rows, row0, attn_mode, maxlen, e->att_img.p, st);
+      e->launches++;
+    } else {
+      launch_attn_tc(bt, e->qkv16.p, row0, attn_mode, maxlen, e->att_img.p, st);
+    }
     launch_gemm_tc(e->att_img.p, L.out_i, L.out_b, x, kD, R, kD, kD, TC_EPI_F32_RESIDUAL, st);
     launch_layernorm_image(x, nullptr, R, L.n2_g, L.n2_b, ada2, ada2 ? ada2 + kD : nullptr, 1e-5f, e->a_img.p, st);
     launch_gemm_tc(e->a_img.p, L.ff1_i, L.ff1_b, e->h_img.p, kFF, R, kFF, kD, TC_EPI_BF16_IMAGE_RELU, st);
@@ -313,6 +322,8 @@ int ensure_full_buffers(vx_engine* e, int64_t R) {
   ENS(e->x, Rp * kD * 4);
   if (e->mode == VX_BF16 && !e->force_simt) {
     ENS(e->a_img, Rp * kD * 2); ENS(e->qkv16, Rp * 3 * kD * 2); ENS(e->att_img, Rp * kD * 2); ENS(e->h_img, Rp * kFF * 2);
+    if (e->attn_t5) { ENS(e->q_img, Rp * kD * 2); ENS(e->k_img, Rp * kD * 2); ENS(e->vt_img, Rp * kD * 2); }
+    e->full_rows = Rp;
     ENS(e->xn, (size_t)std::max<int64_t>(e->max_batch, 1) * kD * 4);
   } else {
     ENS(e->xn, Rp * kD * 4); ENS(e->qkv, Rp * 3 * kD * 4); ENS(e->att, Rp * kD * 4); ENS(e->ffh, Rp * kFF * 4);
@@ -348,6 +359,8 @@ int vx_create(int device, int max_batch, int max_ctx, int dtype_mode, vx_engine*
   CK(cudaMallocHost(&e->h_pinned, 4096));
   const char* fs = getenv("VX_FORCE_SIMT");
   e->force_simt = fs && fs[0] == '1';
+  const char* t5 = getenv("VX_ATTN_T5");
+  e->attn_t5 = t5 && t5[0] == '1';
   const char* dg = getenv("VX_DECODE_GRAPH");
   e->decode_graph = dg && dg[0] == '1';
   e->num_sms = prop.multiProcessorCount;
@@ -366,7 +379,7 @@ void vx_destroy(vx_engine* e) {
   }
   Buf* bufs[] = {&e->d_text, &e->d_lang, &e->d_prompt, &e->d_S, &e->d_P, &e->d_ar_row0, &e->d_nar_row0, &e->d_T,
                  &e->d_ctx, &e->d_y, &e->d_budget, &e->d_fin, &e->d_slp, &e->d_nact, &e->x, &e->xn, &e->qkv, &e->att,
-                 &e->ffh, &e->kc, &e->vc, &e->a_img, &e->qkv16, &e->att_img, &e->h_img, &e->t_img, &e->xs, &e->xsn, &e->qkvs, &e->atts, &e->ffs, &e->logits, &e->part, &e->tick, &e->p_pf, &e->p_bar, &e->p_prof,
+                 &e->ffh, &e->kc, &e->vc, &e->a_img, &e->qkv16, &e->att_img, &e->h_img, &e->t_img, &e->q_img, &e->k_img, &e->vt_img, &e->xs, &e->xsn, &e->qkvs, &e->atts, &e->ffs, &e->logits, &e->part, &e->tick, &e->p_pf, &e->p_bar, &e->p_prof,
                  &e->lastmap, &e->out_tok, &e->forced, &e->yemb, &e->yrow0, &e->trow0, &e->tgtmap, &e->nlog, &e->codes,
                  &e->tl_dev, &e->cb0_dev, &e->v_codes, &e->v_feat, &e->v_col, &e->v_x, &e->v_h, &e->v_ff, &e->v_head,
                  &e->v_spec, &e->v_frames, &e->v_wave};
@@ -583,7 +596,7 @@ int vx_set_batch(vx_engine* e, int B, const int32_t* text_ids, const int32_t* te
     const int len = e->hS[b] + e->hP[b] + 1;
     if (len >= e->max_ctx) return fail(VX_ERR_CAPACITY, "vx_set_batch: S+P+1 exceeds max_ctx");
     e->h_ar_row0[b] = rows;
-    rows += len;
+    rows += (e->attn_t5 && e->mode == VX_BF16 && !e->force_simt) ? (len + 127) / 128 * 128 : len;  // tcgen05 attention: key tiles = image blocks
     maxlen = std::max(maxlen, len);
   }
   e->B = B; e->Smax = Smax; e->Pmax = Pmax; e->ar_rows = rows; e->ar_maxlen = maxlen;
@@ -633,6 +646,7 @@ int vx_ar_prefill(vx_engine* e, void* stream) {
   CK(cudaEventRecord(e->ev0, st));
   const Batch& bt = e->bt;
   float* x = (float*)e->x.p;
+  if (e->attn_t5 && e->mode == VX_BF16 && !e->force_simt) CK(cudaMemsetAsync(x, 0, (size_t)e->full_rows * kD * 4, st));  // pad rows stay finite
   launch_init_y(bt, st);
   launch_embed_text(bt, vec(e, "ar_text_embedding.word_embeddings.weight"), vec(e, "ar_language_embedding.word_embeddings.weight"),
                     vec(e, "ar_text_position.alpha"), e->pe, bt.ar_row0, x, st);
@@ -902,7 +916,8 @@ int vx_nar(vx_engine* e, const int32_t* cb0, const int32_t* t_lens, int Tmax, in
     if (e->hT[b] > Tmax) return fail(VX_ERR_ARG, "vx_nar: Tmax smaller than a generated length");
     nrow0[b] = (int32_t)R; yrow0[b] = (int32_t)YR; trow0[b] = (int32_t)TR;
     const int pt = e->hP[b] + e->hT[b];
-    R += e->hS[b] + pt; YR += pt; TR += e->hT[b];
+    R += (e->attn_t5 && e->mode == VX_BF16 && !e->force_simt) ? (e->hS[b] + pt + 127) / 128 * 128 : e->hS[b] + pt;
+    YR += pt; TR += e->hT[b];
     maxlen = std::max(maxlen, e->hS[b] + pt); maxpt = std::max(maxpt, pt); maxT = std::max(maxT, e->hT[b]);
   }
   std::vector<int32_t> tgt((size_t)std::max<int64_t>(TR, 1));
@@ -928,6 +943,7 @@ int vx_nar(vx_engine* e, const int32_t* cb0, const int32_t* t_lens, int Tmax, in
   e->launches += 2;
   if (TR > 0) {
     for (int stage = 0; stage < kNQ - 1; ++stage) {
+      if (e->attn_t5 && e->mode == VX_BF16 && !e->force_simt) CK(cudaMemsetAsync(x, 0, (size_t)e->full_rows * kD * 4, st));
       launch_embed_text(bt, vec(e, "nar_text_embedding.word_embeddings.weight"), vec(e, "nar_language_embedding.word_embeddings.weight"),
                         vec(e, "nar_text_position.alpha"), e->pe, bt.nar_row0, x, st);
       launch_nar_build_x(bt, yemb, d_yrow0, vec(e, "nar_audio_position.alpha"), e->pe, x, maxpt, st);
@@ -1105,6 +1121,34 @@ int vx_debug_attn_tc(const float* qkv, float* out, int S, int len, int mode) {
   CK(cudaGetLastError());
   CK(cudaMemcpy(out, dout, (size_t)len * kD * 4, cudaMemcpyDeviceToHost));
   cudaFree(dq); cudaFree(q16); cudaFree(img); cudaFree(dout); cudaFree(meta);
+  return VX_OK;
+}
+
+int vx_debug_attn_t5(const float* qkv, float* out, int S, int len, int mode) {
+  if (!qkv || !out || S < 1 || len <= S - (mode == 0 ? 1 : 0) || (mode != 0 && mode != 1)) return fail(VX_ERR_ARG, "vx_debug_attn_t5: bad arguments");
+  const int64_t Lp = (len + 127) / 128 * 128;
+  float *dq = nullptr, *dout = nullptr;
+  bf16* q16 = nullptr;
+  void *img = nullptr, *qi = nullptr, *ki = nullptr, *vi = nullptr;
+  int32_t* meta = nullptr;  // S, P, T, row0
+  CK(cudaMalloc(&dq, (size_t)Lp * 3 * kD * 4)); CK(cudaMalloc(&q16, (size_t)Lp * 3 * kD * 2));
+  CK(cudaMalloc(&img, Lp * kD * 2)); CK(cudaMalloc(&dout, (size_t)len * kD * 4)); CK(cudaMalloc(&meta, 16));
+  CK(cudaMalloc(&qi, Lp * kD * 2)); CK(cudaMalloc(&ki, Lp * kD * 2)); CK(cudaMalloc(&vi, Lp * kD * 2));
+  CK(cudaMemset(img, 0, Lp * kD * 2));
+  CK(cudaMemset(dq, 0, (size_t)Lp * 3 * kD * 4));
+  const int32_t h[4] = {S, mode == 1 ? len - S - 1 : 0, mode == 1 ? 0 : len - S, 0};
+  CK(cudaMemcpy(meta, h, 16, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dq, qkv, (size_t)len * 3 * kD * 4, cudaMemcpyHostToDevice));
+  f32_to_bf16_kernel<<<296, 256>>>(dq, q16, (size_t)Lp * 3 * kD);
+  Batch bt{};
+  bt.B = 1; bt.S = meta; bt.P = meta + 1; bt.T = meta + 2;
+  launch_pack_qkv_heads(q16, Lp, qi, ki, vi, 0);
+  launch_attn_t5(bt, qi, ki, vi, Lp, meta + 3, mode, len, img, 0);
+  unpack_image_kernel<<<(unsigned)(((int64_t)len * kD + 255) / 256), 256>>>((const uint8_t*)img, len, kD, dout);
+  CK(cudaDeviceSynchronize());
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(out, dout, (size_t)len * kD * 4, cudaMemcpyDeviceToHost));
+  cudaFree(dq); cudaFree(q16); cudaFree(img); cudaFree(dout); cudaFree(meta); cudaFree(qi); cudaFree(ki); cudaFree(vi);
   return VX_OK;
 }
 

@@ -92,6 +92,11 @@ void launch_attn_tc(const Batch& bt, const void* qkv_bf16, const int32_t* row0, 
 void launch_kv_scatter_bf16(const Batch& bt, const void* qkv_bf16, void* kcache, void* vcache, int max_len, int ctx_cap,
                             cudaStream_t st);
 
+// tcgen05/TMEM attention (attention_t5.cu): per-head operand images packed from the row-major bf16 QKV
+void launch_pack_qkv_heads(const void* qkv_bf16, int64_t R, void* q_img, void* k_img, void* vt_img, cudaStream_t st);
+void launch_attn_t5(const Batch& bt, const void* q_img, const void* k_img, const void* vt_img, int64_t R,
+                    const int32_t* row0, int mode, int max_len, void* out_img, cudaStream_t st);
+
 // ---- sampling (models/vallex.py:791-853, 569-578) ----
 void launch_sample(const Batch& bt, const float* logits, int top_k, float top_p, float temperature, uint64_t seed,
                    int step, int ignore_eos, const int32_t* forced, int forced_stride, int32_t* out_tokens,
