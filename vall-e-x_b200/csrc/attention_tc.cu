@@ -119,20 +119,30 @@ __global__ void __launch_bounds__(128) attn_tc_kernel(Batch bt, const bf16* __re
         mma_bf16(s[2 * jp + 1], qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3], b2, b3);
       }
     }
-    // mask + online softmax (rows qrow_lo and qrow_lo + 8)
+    // mask + online softmax (rows qrow_lo and qrow_lo + 8).  Interior key tiles (every key visible to every row of this
+    // warp) skip the per-element visibility logic: raw scores stay unscaled and the exp argument is one FFMA.
     const int k0 = t * FK;
+    const bool full = (k0 + FK <= len) && (mode == 0 || k0 + FK <= S || k0 + FK - 1 <= q0 + warp * 16);
     float mx[2] = {-INFINITY, -INFINITY};
+    if (full) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+      for (int j = 0; j < 8; ++j)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int kj = k0 + j * 8 + (lane & 3) * 2 + (i & 1);
-        const int qi = qrow_lo + ((i >> 1) << 3);
-        bool vis = kj < len;
-        if (mode == 1) vis = vis && (kj < S || kj <= qi);
-        s[j][i] = vis ? s[j][i] * sl2 : -INFINITY;
-        mx[i >> 1] = fmaxf(mx[i >> 1], s[j][i]);
-      }
+        for (int i = 0; i < 4; ++i) mx[i >> 1] = fmaxf(mx[i >> 1], s[j][i]);
+      mx[0] *= sl2; mx[1] *= sl2;   // sl2 > 0: max commutes with the scale
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int kj = k0 + j * 8 + (lane & 3) * 2 + (i & 1);
+          const int qi = qrow_lo + ((i >> 1) << 3);
+          bool vis = kj < len;
+          if (mode == 1) vis = vis && (kj < S || kj <= qi);
+          s[j][i] = vis ? s[j][i] : -INFINITY;
+          mx[i >> 1] = fmaxf(mx[i >> 1], s[j][i] * sl2);
+        }
+    }
     float corr[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -149,8 +159,8 @@ __global__ void __launch_bounds__(128) attn_tc_kernel(Batch bt, const bf16* __re
       float p[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float mref = m_r[i >> 1];
-        p[i] = (s[j][i] == -INFINITY) ? 0.f : exp2f(s[j][i] - mref);
+        // masked scores are -inf: fmaf(-inf, sl2, -m) = -inf -> exp2f = 0 (m is finite once any key of the row was seen)
+        p[i] = exp2f(fmaf(s[j][i], sl2, -m_r[i >> 1]));
         rs[i >> 1] += p[i];
       }
       pf[j >> 1][(j & 1) * 2 + 0] = pack_bf16(p[0], p[1]);
