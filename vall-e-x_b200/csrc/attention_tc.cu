@@ -37,8 +37,15 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(b)) << 16);
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {  // one cvt.rn.bf16x2.f32 (low half = a)
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ float ex2(float x) {  // single MUFU.EX2; ex2(-inf) = 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 __global__ void __launch_bounds__(128) attn_tc_kernel(Batch bt, const bf16* __restrict__ qkv,
@@ -149,7 +156,7 @@ __global__ void __launch_bounds__(128) attn_tc_kernel(Batch bt, const bf16* __re
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
       const float m_new = fmaxf(m_r[r], mx[r]);
-      corr[r] = (m_new == -INFINITY) ? 1.f : exp2f(m_r[r] - m_new);
+      corr[r] = (m_new == -INFINITY) ? 1.f : ex2(m_r[r] - m_new);
       m_r[r] = m_new;
     }
     float rs[2] = {0.f, 0.f};
@@ -160,7 +167,7 @@ __global__ void __launch_bounds__(128) attn_tc_kernel(Batch bt, const bf16* __re
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         // masked scores are -inf: fmaf(-inf, sl2, -m) = -inf -> exp2f = 0 (m is finite once any key of the row was seen)
-        p[i] = exp2f(fmaf(s[j][i], sl2, -m_r[i >> 1]));
+        p[i] = ex2(fmaf(s[j][i], sl2, -m_r[i >> 1]));
         rs[i >> 1] += p[i];
       }
       pf[j >> 1][(j & 1) * 2 + 0] = pack_bf16(p[0], p[1]);
