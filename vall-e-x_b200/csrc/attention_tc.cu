@@ -48,7 +48,7 @@ __device__ __forceinline__ float ex2(float x) {  // single MUFU.EX2; ex2(-inf) =
   return y;
 }
 
-__global__ void __launch_bounds__(128) attn_tc_kernel(Batch bt, const bf16* __restrict__ qkv,
+__global__ void __launch_bounds__(128, 4) attn_tc_kernel(Batch bt, const bf16* __restrict__ qkv,
                                                       const int32_t* __restrict__ row0, int mode,
                                                       uint8_t* __restrict__ out_img) {
   __shared__ __align__(1024) uint8_t sQ[FQ * 128];
