@@ -533,6 +533,8 @@ template <typename KVT> __device__ __forceinline__ float kv_round(float v);
 template <> __device__ __forceinline__ float kv_round<float>(float v) { return v; }
 template <> __device__ __forceinline__ float kv_round<bf16>(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
+__device__ __forceinline__ float att_combined(const PParams& p, int b, int c);
+
 template <typename KVT>
 __device__ void attn_unit(const PParams& p, int layer, int b, int h, int split, float* smem) {
   float* sq = smem;                  // [64]
@@ -612,10 +614,24 @@ __device__ void attn_unit(const PParams& p, int layer, int b, int h, int split, 
   if (tid < kDH) {
     for (int q = 0; q < NG; ++q) od += sacc[q * kDH + tid];
   }
-  // partial (m, l, o[64]) of this split; the out-proj phase folds the splits while staging (att_combined)
+  // partial (m, l, o[64]) of this split.  The LAST split of (b, h) to arrive (ticket) folds all of them in fixed split
+  // order -- deterministic whoever is last -- into att[b][h*64 ..], so the out-proj phase stages 4 KB per utterance
+  // instead of every CTA gathering all partials.
   float* pp = p.part + (((size_t)b * kH + h) * p.nsplit + split) * (kDH + 2);
   if (tid < kDH) pp[2 + tid] = od;
   if (tid == 0) { pp[0] = m; pp[1] = l; }
+  if (p.dbg & 2) return;   // bisecting aid: the out-proj phase folds the splits itself
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();       // the CTA's partial is visible device-wide before the ticket is taken
+    *s_last = (atomicAdd(p.tickets + b * kH + h, 1) == p.nsplit - 1);
+  }
+  __syncthreads();
+  if (*s_last) {
+    __threadfence();
+    if (tid < kDH) p.att[(size_t)b * kD + h * kDH + tid] = att_combined(p, b, h * kDH + tid);
+    if (tid == 0) p.tickets[b * kH + h] = 0;   // next use is behind a grid barrier
+  }
 }
 
 // softmax-combine the key splits of head c/64 for column c (fixed order -> deterministic)
@@ -743,7 +759,10 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_persistent_kernel(const PPar
       }
       grid_barrier(p.bar, epoch, prof);
       // ---- P3: (combine key splits) + out-proj + residual -> xa ------------------------------------------------
-      stage_plain(sx, B, [&](int m, int c) { return ld_cg(bt.finished + m) ? 0.f : att_combined(p, m, c); });
+      stage_plain(sx, B, [&](int m, int c) {
+        if (ld_cg(bt.finished + m)) return 0.f;
+        return (p.dbg & 2) ? att_combined(p, m, c) : __ldcg(p.att + (size_t)m * kD + c);
+      });
       PSTAMP(3);
       gemv_finish<WT, MR>(pre, Wo, kD, o0, o1, sx, B, L.out_b, fb_prev, [&](int n, int m) { return stream_dyn(p, l, m, n, B); },
                           [&](int n, int m, float v) { p.xa[(size_t)m * kD + n] = v; });

@@ -39,7 +39,7 @@ struct PParams {
   int32_t* steps_done;        // [1]
   long long* prof;            // nullable: [3 CTAs][4096] (tag, clock64) pairs of 4 steps (VX_DECODE_PROF=<first step>)
   int prof_step0;
-  int dbg;                    // VX_DECODE_DBG bit mask: bisecting aid (1 no attention, 2 no split-combine, 4 no GEMV, 8 no LN staging, 16 no sampling)
+  int dbg;                    // VX_DECODE_DBG bit mask: bisecting aid (1 no attention, 2 fold the key splits in the out-proj phase instead of by ticket, 4 no GEMV, 8 no LN staging, 16 no sampling)
 };
 
 
