@@ -173,22 +173,20 @@ def test_max_new_tokens_is_a_prefix():
 
 def test_batched_ragged_equals_sequential():
     """B utterances with different S/P in one batch == each alone (the reference is batch-1 only;
-    SURVEY.md 7, hard part 7: batching must be a vmap of independent calls)."""
+    SURVEY.md 7, hard part 7: batching must be a vmap of independent calls).  Goes through VALLE.inference_batch, the
+    call generate_audio_from_long_text(mode='fixed-prompt') makes."""
     names = ["tiny_en", "noprompt_en"]
     gs = [load_golden(n) for n in names]
     assert int(gs[0]["seed"]) == int(gs[1]["seed"])
     m = _valle(state_dict_for(gs[0]["seed"]), "fp32", max_ctx=512, max_batch=2)
-    eng = m.engine
-    langs = [m._lang_ids(len(g["x"]), int(g["Lp"]), g["prompt_language_arg"], g["text_language_arg"]) for g in gs]
-    eng.set_batch([g["x"].astype(np.int32) for g in gs], langs, [g["prompt"].astype(np.int32) for g in gs])
-    eng.ar_prefill()
-    toks, lens, _ = eng.ar_decode(top_k=1)
-    codes = eng.nar(Tmax=int(lens.max()))
-    for b, g in enumerate(gs):
-        T = g["codes"].shape[0]
-        assert int(lens[b]) == T
-        assert np.array_equal(codes[b, :T], g["codes"].astype(np.int32)), names[b]
-    eng.close()
+    items = [(torch.from_numpy(g["x"].astype(np.int64))[None], torch.from_numpy(g["prompt"].astype(np.int64))[None],
+              int(g["Lp"]), g["prompt_language_arg"], g["text_language_arg"]) for g in gs]
+    outs = m.inference_batch(items + items[:1], top_k=1, temperature=1.0, quiet=True)   # 3 items, max_batch 2: two chunks
+    assert len(outs) == 3
+    for out, g, name in zip(outs, gs + gs[:1], names + names[:1]):
+        assert out.shape == (1,) + g["codes"].shape and out.dtype == torch.int64
+        assert np.array_equal(out[0].numpy(), g["codes"].astype(np.int64)), name
+    m.engine.close()
 
 
 def test_sampling_mode_statistics():

@@ -75,3 +75,65 @@ def test_synthetic_checkpoint_layout():
     assert v["head.out.weight"].shape == (1282, 384) and v["backbone.embed.weight"].shape == (384, 128, 7)
     pe = sine_position_table(16)
     assert pe.shape == (16, 1024) and float(pe[0, 1]) == 1.0 and float(pe[0, 0]) == 0.0
+
+
+class _StubModel:
+    """Records the calls generate_audio_from_long_text makes; emits T = number of new phonemes frames of constant codes."""
+    def __init__(self, with_batch=True):
+        self.calls = []
+        if not with_batch:
+            self.inference_batch = None
+            del self.inference_batch
+
+    def _frames(self, x, enroll):
+        T = int(x.shape[1]) - int(enroll)
+        return torch.full((1, T, 8), int(x[0, -1]), dtype=torch.long)
+
+    def inference(self, x, x_lens, y, enroll_x_lens, **kw):
+        self.calls.append(("single", int(x.shape[1]), int(y.shape[1]), kw.get("top_k"), kw.get("prompt_language")))
+        return self._frames(x, enroll_x_lens)
+
+
+class _StubBatchModel(_StubModel):
+    def inference_batch(self, items, **kw):
+        self.calls.append(("batch", len(items), kw.get("top_k")))
+        return [self._frames(x, enroll) for x, y, enroll, lp, tl in items]
+
+
+class _StubVocos:
+    def codes_to_features(self, codes):
+        self.codes = codes
+        return codes
+
+    def decode(self, features, bandwidth_id=None):
+        return features[0].float().repeat_interleave(320, dim=-1)[:1]
+
+
+def test_long_text_fixed_prompt_batches_sentences(tmp_path, monkeypatch):
+    """utils/generation.py:199-227: fixed-prompt sentences are independent -> one ragged batch; the concatenated codes and
+    the single Vocos pass are the same as the sequential path's."""
+    np.savez(tmp_path / "p.npz", audio_tokens=np.zeros((1, 7, 8), np.int64), text_tokens=np.full((1, 3), 9, np.int64),
+             lang_code=np.int32(2))
+    sents = [np.arange(5, 9), np.arange(10, 16), np.arange(20, 23)]
+    results = {}
+    for name, mdl, kw in (("batched", _StubBatchModel(), {}), ("sequential", _StubBatchModel(), {"batch_sentences": False}),
+                          ("no_batch_api", _StubModel(), {})):
+        voc = _StubVocos()
+        monkeypatch.setattr(generation, "model", mdl, raising=False)
+        monkeypatch.setattr(generation, "vocos", voc, raising=False)
+        wav = generation.generate_audio_from_long_text(sents, prompt=str(tmp_path / "p.npz"), language="en",
+                                                       mode="fixed-prompt", **kw)
+        results[name] = (mdl.calls, voc.codes.clone(), wav)
+    assert results["batched"][0] == [("batch", 3, -100)]
+    assert [c[0] for c in results["sequential"][0]] == ["single"] * 3
+    assert results["sequential"][0][0] == ("single", 3 + 4, 7, -100, "en")
+    assert [c[0] for c in results["no_batch_api"][0]] == ["single"] * 3
+    for k in ("sequential", "no_batch_api"):
+        assert torch.equal(results["batched"][1], results[k][1])
+        assert np.array_equal(results["batched"][2], results[k][2])
+    assert results["batched"][1].shape == (8, 1, 4 + 6 + 3)
+    # sliding-window is sequential by construction
+    monkeypatch.setattr(generation, "model", _StubBatchModel(), raising=False)
+    with pytest.raises(ValueError, match="fixed-prompt"):
+        generation.generate_audio_from_long_text(sents, prompt=str(tmp_path / "p.npz"), language="en",
+                                                 mode="sliding-window", batch_sentences=True)

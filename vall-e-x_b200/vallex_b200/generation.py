@@ -99,7 +99,8 @@ def _tokenize(text, lang_token: str):
     return phone_tokens, langs
 
 
-def _one_utterance(text, audio_prompts, text_prompts, lang_pr, language, accent, **infer_kw):
+def _prepare_utterance(text, text_prompts, lang_pr, language, accent):
+    """Token / language bookkeeping of utils/generation.py:112-146 -> (text_tokens [1,S], Lp, prompt_language, text_language)."""
     lang_token = lang2token[language]
     lang = token2lang[lang_token]
     if lang_pr is None:
@@ -111,11 +112,17 @@ def _one_utterance(text, audio_prompts, text_prompts, lang_pr, language, accent,
     if langs is None:
         langs = [lang if lang != "mix" else "en"] * len(phone_tokens)
     text_tokens = torch.cat([text_prompts.long(), torch.tensor([phone_tokens], dtype=torch.long)], dim=-1)
-    text_tokens_lens = torch.tensor([text_tokens.shape[-1]], dtype=torch.int32)
     lang = lang if accent == "no-accent" else token2lang[langdropdown2token[accent]]
+    return text_tokens, enroll_x_lens, lang_pr, (langs if accent == "no-accent" else lang)
+
+
+def _one_utterance(text, audio_prompts, text_prompts, lang_pr, language, accent, **infer_kw):
+    text_tokens, enroll_x_lens, lang_pr, text_language = _prepare_utterance(text, text_prompts, lang_pr, language, accent)
+    text_tokens_lens = torch.tensor([text_tokens.shape[-1]], dtype=torch.int32)
+    kw = dict(top_k=-100, temperature=1)   # utils/generation.py:142-143
+    kw.update(infer_kw)
     encoded_frames = model.inference(text_tokens, text_tokens_lens, audio_prompts, enroll_x_lens=enroll_x_lens,
-                                     top_k=-100, temperature=1, prompt_language=lang_pr,
-                                     text_language=langs if accent == "no-accent" else lang, **infer_kw)
+                                     prompt_language=lang_pr, text_language=text_language, **kw)
     return encoded_frames, text_tokens, enroll_x_lens
 
 
@@ -145,8 +152,11 @@ def generate_audio(text, prompt=None, language="auto", accent="no-accent", **inf
 
 @torch.no_grad()
 def generate_audio_from_long_text(text, prompt=None, language="auto", accent="no-accent", mode="sliding-window",
-                                  **infer_kw):
-    """utils/generation.py:154-276.  `text` may be a list of pre-split sentences (each a str or phoneme ids)."""
+                                  batch_sentences=None, **infer_kw):
+    """utils/generation.py:154-276.  `text` may be a list of pre-split sentences (each a str or phoneme ids).
+    `batch_sentences` (engine extension; default: on in 'fixed-prompt' mode when the model offers `inference_batch`):
+    the sentences of a fixed-prompt request share nothing but the prompt (utils/generation.py:199-224), so they are
+    decoded as one ragged batch instead of one after another.  'sliding-window' is sequential by construction."""
     if mode not in ("fixed-prompt", "sliding-window"):
         raise ValueError(f"No such mode {mode}")
     if prompt is None or prompt == "":
@@ -163,11 +173,29 @@ def generate_audio_from_long_text(text, prompt=None, language="auto", accent="no
         language = _detect_language(text if isinstance(text, str) else str(sentences[0]))
     audio_prompts, text_prompts, lang_pr = _load_prompt(prompt if prompt else None)
     complete_tokens = torch.zeros([1, NUM_QUANTIZERS, 0]).type(torch.LongTensor)
+    cleaned = []
     for sent in sentences:
         if isinstance(sent, str):
             sent = sent.replace("\n", "").strip(" ")
             if sent == "":
                 continue
+        cleaned.append(sent)
+    sentences = cleaned
+    if batch_sentences is None:
+        batch_sentences = mode == "fixed-prompt" and hasattr(model, "inference_batch") and len(sentences) > 1
+    if batch_sentences:
+        if mode != "fixed-prompt":
+            raise ValueError("batch_sentences needs mode='fixed-prompt' (sliding-window feeds each sentence's output to the next)")
+        items = []
+        for sent in sentences:
+            text_tokens, enroll, lp, tl = _prepare_utterance(sent, text_prompts, lang_pr, language, accent)
+            items.append((text_tokens, audio_prompts, enroll, lp, tl))
+        kw = dict(top_k=-100, temperature=1)
+        kw.update(infer_kw)
+        for encoded_frames in model.inference_batch(items, **kw):
+            complete_tokens = torch.cat([complete_tokens, encoded_frames.transpose(2, 1).cpu()], dim=-1)
+        sentences = []
+    for sent in sentences:
         encoded_frames, text_tokens, enroll = _one_utterance(sent, audio_prompts, text_prompts, lang_pr, language,
                                                              accent, **infer_kw)
         complete_tokens = torch.cat([complete_tokens, encoded_frames.transpose(2, 1).cpu()], dim=-1)

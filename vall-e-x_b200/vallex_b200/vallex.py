@@ -26,6 +26,12 @@ def _device_index(device) -> int:
     return 0 if d.index is None else d.index
 
 
+def _resolve_seed(seed: Optional[int]) -> int:
+    if seed is None:
+        return int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+    return int(seed)
+
+
 class VALLE:
     def __init__(self, d_model: int, nhead: int, num_layers: int, norm_first: bool = True, add_prenet: bool = False,
                  prefix_mode: int = 0, share_embedding: bool = True, nar_scale_factor: float = 1.0,
@@ -114,8 +120,10 @@ class VALLE:
     def inference(self, x: torch.Tensor, x_lens: torch.Tensor, y: torch.Tensor, enroll_x_lens, top_k: int = -100,
                   temperature: float = 1.0, prompt_language: str = None, text_language=None, best_of: int = 1,
                   length_penalty: float = 1.0, return_worst: bool = False, *, max_new_tokens: int = 0,
-                  seed: int = 0, quiet: bool = False) -> torch.Tensor:
-        """models/vallex.py:458-686.  `max_new_tokens`, `seed`, `quiet` are engine extensions (keyword-only)."""
+                  seed: Optional[int] = None, quiet: bool = False) -> torch.Tensor:
+        """models/vallex.py:458-686.  `max_new_tokens`, `seed`, `quiet` are engine extensions (keyword-only).
+        `seed=None` draws the device sampler's Philox seed from torch's global CPU generator, so `torch.manual_seed`
+        governs reproducibility of sampled output as it does for the reference."""
         assert x.ndim == 2, x.shape
         assert x_lens.ndim == 1, x_lens.shape
         assert y.ndim == 3, y.shape
@@ -128,6 +136,7 @@ class VALLE:
         prompt = y[0].detach().to("cpu").numpy().astype(np.int32).reshape(P, NUM_QUANTIZERS)
         lang = self._lang_ids(S, Lp, prompt_language, text_language)
         eng = self.engine
+        seed = _resolve_seed(seed)
         nb = int(best_of)
         eng.set_batch([text] * nb, [lang] * nb, [prompt] * nb)
         eng.ar_prefill()
@@ -152,3 +161,44 @@ class VALLE:
         self.last_timing = dict(eng.timing(), ms_prefill=t_pre)
         out = torch.from_numpy(codes[:1, :T].astype(np.int64))
         return out.to(x.device) if x.is_cuda else out
+
+    def inference_batch(self, items, top_k: int = -100, temperature: float = 1.0, *, max_new_tokens: int = 0,
+                        seed: Optional[int] = None, quiet: bool = False) -> List[torch.Tensor]:
+        """Engine extension (the reference is batch-1 only, models/vallex.py:491): B independent
+        utterances as ONE ragged batch -- one prefill, one persistent decode launch, one NAR pass per `max_batch`
+        chunk.  `items` = sequence of `(x [1,S], y [1,P,8], enroll_x_lens, prompt_language, text_language)` with the
+        meaning of `.inference`'s arguments; returns one LongTensor[1,T_b,8] per item.  Every utterance keeps its own
+        EOS / 16*S cap and (sampling mode) its own Philox stream, so the batch is a vmap of B `.inference` calls."""
+        items = list(items)
+        seed = _resolve_seed(seed)
+        outs: List[Optional[torch.Tensor]] = [None] * len(items)
+        eng = self.engine
+        timing: dict = {}
+        for c0 in range(0, len(items), self._max_batch):
+            chunk = items[c0:c0 + self._max_batch]
+            texts, langs, prompts = [], [], []
+            for x, y, enroll_x_lens, prompt_language, text_language in chunk:
+                assert x.ndim == 2 and x.shape[0] == 1, x.shape
+                assert y.ndim == 3 and y.shape[0] == 1, y.shape
+                S, P = int(x.shape[1]), int(y.shape[1])
+                assert S > 0
+                texts.append(x[0].detach().to("cpu").numpy().astype(np.int32))
+                prompts.append(y[0].detach().to("cpu").numpy().astype(np.int32).reshape(P, NUM_QUANTIZERS))
+                langs.append(self._lang_ids(S, int(enroll_x_lens), prompt_language, text_language))
+            eng.set_batch(texts, langs, prompts)
+            eng.ar_prefill()
+            t_pre = eng.timing()["ms_prefill"]
+            _, lens, _ = eng.ar_decode(max_new=max_new_tokens, top_k=top_k, top_p=1.0, temperature=temperature,
+                                       seed=seed + c0)
+            codes = eng.nar(Tmax=int(lens.max()))
+            t = dict(eng.timing(), ms_prefill=t_pre)
+            for k, v in t.items():
+                timing[k] = timing.get(k, 0) + v if isinstance(v, (int, float)) else v
+            for b, (x, y, *_rest) in enumerate(chunk):
+                T = int(lens[b])
+                if not quiet:
+                    print(f"VALL-E EOS [{int(y.shape[1])} -> {int(y.shape[1]) + 1 + T}]")
+                out = torch.from_numpy(codes[b:b + 1, :T].astype(np.int64))
+                outs[c0 + b] = out.to(x.device) if x.is_cuda else out
+        self.last_timing = timing
+        return outs
