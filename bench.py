@@ -337,9 +337,10 @@ def main():
                 "ms_per_step": 1e3 * e2e_elapsed / a.steps, "rtf": (e2e_elapsed / a.steps) / (T_NEW / 75.0)},
         "gpu_launches": int(launches),
         "clocks": clk,
-        "roofline": {"kernel": "ar_decode_persistent_kernel (one launch = all decode steps; per-step figures)", "bound": "hbm",
+        "roofline": {"kernel": ("ar_decode_persistent_kernel" if os.environ.get("VX_DECODE_FUSED") == "0" or a.dtype != "bf16" else "ar_decode_fused_kernel")
+                               + " (one launch = all decode steps; per-step figures)", "bound": "hbm",
                      "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": (traffic or {}).get("dram_bytes_per_step"),
-                     "traffic_note": (None if traffic is None else f"per decode step, {traffic['capture']} ({traffic['source']}); algorithmic at that context: {traffic['algorithmic_bytes_per_step']:.0f} B"),
+                     "traffic_note": (None if traffic is None else f"per decode step, {traffic['capture']} ({traffic['source']}), kernel {traffic['kernel']}; algorithmic at that context: {traffic['algorithmic_bytes_per_step']:.0f} B"),
                      "peak_source": how, "bytes_per_step": bytes_step, "avg_step_us": t_step * 1e6, "mean_ctx": L_mean},
     }
     if not a.no_cpu_baseline:

@@ -164,6 +164,33 @@ def test_ring_decode_variant(monkeypatch):
     eng.close()
 
 
+@pytest.mark.parametrize("names", [["tiny_en"], ["mid_ja"], ["tiny_en", "noprompt_en"]])
+def test_fused_decode_variant(monkeypatch, names):
+    """VX_DECODE_FUSED=1 selects the 3-barrier persistent decode kernel (attention + out-proj and FFN1 + FFN2 fused,
+    cross-CTA sums on fixed-point integer atomics).  Same arithmetic up to summation order: teacher-forced agreement
+    with the reference's bf16-weight tokens wherever the reference's top-1/top-2 margin is binding; also ragged B=2."""
+    gs = [load_golden(n) for n in names]
+    monkeypatch.setenv("VX_DECODE_FUSED", "1")
+    m = _valle(state_dict_for(gs[0]["seed"]), "bf16", max_ctx=1024, max_batch=len(gs))
+    eng = m.engine
+    langs = [m._lang_ids(len(g["x"]), int(g["Lp"]), g["prompt_language_arg"], g["text_language_arg"]) for g in gs]
+    eng.set_batch([g["x"].astype(np.int32) for g in gs], langs, [g["prompt"].astype(np.int32) for g in gs])
+    eng.ar_prefill()
+    wants = [g["codes_bf16w"].astype(np.int64)[:, 0] for g in gs]
+    Tmax = max(len(w) for w in wants)
+    forced = np.zeros((len(gs), Tmax), np.int32)
+    for b, w in enumerate(wants):
+        forced[b, :len(w)] = w
+    toks, lens, _ = eng.ar_decode(max_new=Tmax, top_k=1, forced=forced, ignore_eos=True)
+    for b, (g, w) in enumerate(zip(gs, wants)):
+        T = len(w)
+        margin = g["ar_top2_bf16w"][:T, 0] - g["ar_top2_bf16w"][:T, 1]
+        match = toks[b, :T] == w
+        assert match[margin > MARGIN].all(), (names[b], margin[~match & (margin > MARGIN)][:5])
+        assert match.mean() > 0.97, (names[b], match.mean())
+    eng.close()
+
+
 def test_max_new_tokens_is_a_prefix():
     g = load_golden("mid_ja")
     got = _infer(model_for(g["seed"], "fp32"), g, max_new_tokens=20)[0].numpy()

@@ -29,7 +29,9 @@ t = eng.timing()
 print("B", B, "us/step", 1e3 * t["ms_decode"] / (t["decode_steps"] - 1))
 raw = eng.debug_read("decode_prof", 3 * 4096 * 2).view(np.int64).reshape(3, 2048, 2)
 mhz = 1965.0
-names = ["S0"] + [f"{n}" for l in range(12) for n in ("qkv", "attn", "out", "ff1", "ff2")] + ["PF"]
+fused = os.environ.get("VX_DECODE_FUSED", "") != "0" and B <= (8 if os.environ.get("VX_DECODE_FUSED") == "1" else 2)
+per_layer = ("qkv", "attn", "ffn") if fused else ("qkv", "attn", "out", "ff1", "ff2")   # fused: 38 barriers per step, else 62
+names = ["S0"] + [f"{n}" for l in range(12) for n in per_layer] + ["PF"]
 for c in range(3):
     ev = [(int(tag), int(clk)) for tag, clk in raw[c] if tag != 0]
     seg = collections.defaultdict(list)
@@ -37,7 +39,7 @@ for c in range(3):
     prev = None
     for tag, clk in ev:
         if prev is not None:
-            key = (names[phase % 62], f"{prev[0]}->{tag}")
+            key = (names[phase % len(names)], f"{prev[0]}->{tag}")
             seg[key].append((clk - prev[1]) / mhz)
         if tag == 2:
             phase += 1
@@ -48,6 +50,6 @@ for c in range(3):
         agg = collections.defaultdict(list)
         for (nm, k), v in seg.items():
             agg[(nm, k)] += v
-        for nm in ("S0", "qkv", "attn", "out", "ff1", "ff2", "PF"):
+        for nm in ("S0",) + per_layer + ("PF",):
             parts = "  ".join(f"{k}:{np.mean(v):5.2f}" for (n2, k), v in sorted(agg.items()) if n2 == nm)
             print(f"  {nm:5s} {parts}")

@@ -102,6 +102,6 @@ if __name__ == "__main__":
     tag = sys.argv[1]
     os.makedirs(OUT, exist_ok=True)
     launches(tag)
-    for n in ("prof_decode", "prof_gemm", "prof_attn"):
+    for n in ("prof_decode", "prof_gemm", "prof_attn", "prof_attn_t5"):
         kernel_report(tag, n)
     print(os.listdir(OUT))

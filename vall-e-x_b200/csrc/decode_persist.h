@@ -9,6 +9,7 @@ namespace vx {
 
 struct PLayer {
   const void *qkv_w, *out_w, *ff1_w, *ff2_w;
+  const void* ff2_t;          // bf16 [4096][1024]: FFN2 weight transposed (fused variant only, else null)
   const float *qkv_b, *out_b, *ff1_b, *ff2_b, *n1_g, *n1_b, *n2_g, *n2_b;
 };
 
@@ -28,6 +29,10 @@ struct PParams {
   float* att;                 // [B][1024]
   float* hid;                 // [B][4096]
   float* logits;              // [B][1025]
+  float* xb;                  // [B][1024] fused variant: residual stream after the attention block (xa holds the layer input)
+  long long* acc_out;         // [2][B][1024] fused variant: out-proj sums, 2^-30 fixed point, by layer parity
+  long long* acc_ffn;         // [2][B][1024] fused variant: FFN2 sums
+  int fused;                  // VX_DECODE_FUSED=1
   float* part;                // [B][16][nsplit][66]
   int32_t* tickets;           // [B*16]
   unsigned int* bar;          // grid barrier counter (zeroed by the host)

@@ -37,6 +37,20 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ in, bf16* __restric
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) out[i] = __float2bfloat16_rn(in[i]);
 }
+// out[c][r] = in[r][c] (bf16), 32x32 tiles through shared memory
+__global__ void transpose_bf16_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int rows, int cols) {
+  __shared__ bf16 tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[i][threadIdx.x] = in[(size_t)r * cols + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) out[(size_t)c * rows + r] = tile[threadIdx.x][i];
+  }
+}
 __global__ void write_cb0_kernel(Batch bt, const int32_t* __restrict__ cb0, const int32_t* __restrict__ tl, int Tmax) {
   const int b = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -60,6 +74,7 @@ struct Buf {
 struct LayerW {
   const void *qkv_w, *out_w, *ff1_w, *ff2_w;
   const void *qkv_i, *out_i, *ff1_i, *ff2_i;  // tile images (bf16 mode)
+  const void* ff2_t = nullptr;                // bf16 [4096][1024] transposed FFN2 weight (AR, fused decode variant)
   const float *qkv_b, *out_b, *ff1_b, *ff2_b, *n1_g, *n1_b, *n2_g, *n2_b;
   const float *ada1, *ada2;  // [7][2048] (NAR only)
 };
@@ -93,9 +108,13 @@ struct vx_engine {
   Buf x, xn, qkv, att, ffh, kc, vc;                 // prefill / NAR activations, KV cache
   Buf a_img, qkv16, att_img, h_img, t_img;           // bf16 mode: tile-image / bf16 activations
   Buf q_img, k_img, vt_img;                          // per-head attention operand images (tcgen05 attention)
+  bool decode_fused = true;                          // 3-barrier persistent decode variant (bf16); VX_DECODE_FUSED=0 disables
+  int decode_fused_maxb = 2;
+  void* ff2_t_blob = nullptr;                        // 12 x [4096][1024] bf16
   bool attn_t5 = false;                              // VX_ATTN_T5=1: tcgen05/TMEM attention instead of mma.sync
   int64_t full_rows = 0;                             // packed rows of the current full-sequence pass (128-aligned starts)
   Buf xs, xsn, qkvs, atts, ffs, logits, part, tick;  // decode-step scratch
+  Buf p_xb, p_acc;                                   // fused decode variant: mid-layer residual, fixed-point accumulators
   Buf p_pf, p_bar, p_prof;                                   // persistent decode: FFN2 partials, barrier counter + steps
   int num_sms = 148;
   bool decode_graph = false;                         // VX_DECODE_GRAPH=1: per-step CUDA-graph path instead of the persistent kernel
@@ -359,6 +378,9 @@ int vx_create(int device, int max_batch, int max_ctx, int dtype_mode, vx_engine*
   CK(cudaMallocHost(&e->h_pinned, 4096));
   const char* fs = getenv("VX_FORCE_SIMT");
   e->force_simt = fs && fs[0] == '1';
+  const char* fu = getenv("VX_DECODE_FUSED");   // unset: fused kernel for B <= 2 (validated sizes); 1: B <= 8; 0: never
+  e->decode_fused = !(fu && fu[0] == '0');
+  e->decode_fused_maxb = (fu && fu[0] == '1') ? 8 : 2;
   const char* t5 = getenv("VX_ATTN_T5");
   e->attn_t5 = t5 && t5[0] == '1';
   const char* dg = getenv("VX_DECODE_GRAPH");
@@ -379,13 +401,14 @@ void vx_destroy(vx_engine* e) {
   }
   Buf* bufs[] = {&e->d_text, &e->d_lang, &e->d_prompt, &e->d_S, &e->d_P, &e->d_ar_row0, &e->d_nar_row0, &e->d_T,
                  &e->d_ctx, &e->d_y, &e->d_budget, &e->d_fin, &e->d_slp, &e->d_nact, &e->x, &e->xn, &e->qkv, &e->att,
-                 &e->ffh, &e->kc, &e->vc, &e->a_img, &e->qkv16, &e->att_img, &e->h_img, &e->t_img, &e->q_img, &e->k_img, &e->vt_img, &e->xs, &e->xsn, &e->qkvs, &e->atts, &e->ffs, &e->logits, &e->part, &e->tick, &e->p_pf, &e->p_bar, &e->p_prof,
+                 &e->ffh, &e->kc, &e->vc, &e->a_img, &e->qkv16, &e->att_img, &e->h_img, &e->t_img, &e->q_img, &e->k_img, &e->vt_img, &e->xs, &e->xsn, &e->qkvs, &e->atts, &e->ffs, &e->logits, &e->part, &e->tick, &e->p_xb, &e->p_acc, &e->p_pf, &e->p_bar, &e->p_prof,
                  &e->lastmap, &e->out_tok, &e->forced, &e->yemb, &e->yrow0, &e->trow0, &e->tgtmap, &e->nlog, &e->codes,
                  &e->tl_dev, &e->cb0_dev, &e->v_codes, &e->v_feat, &e->v_col, &e->v_x, &e->v_h, &e->v_ff, &e->v_head,
                  &e->v_spec, &e->v_frames, &e->v_wave};
   for (Buf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (e->ada_all) cudaFree(e->ada_all);
+  if (e->ff2_t_blob) cudaFree(e->ff2_t_blob);
   if (e->dft_basis) cudaFree(e->dft_basis);
   if (e->h_pinned) cudaFreeHost(e->h_pinned);
   if (e->ev0) cudaEventDestroy(e->ev0);
@@ -528,6 +551,16 @@ int vx_finalize_weights(vx_engine* e) {
   e->nar_norm_b = vec(e, "nar_decoder.norm.norm.bias");
   e->nar_norm_ada = e->ada_all + (size_t)24 * 7 * 2 * kD;
   e->ar_predict = mat(e, "ar_predict_layer.weight");
+  if (e->decode_fused && e->mode == VX_BF16) {
+    // fused decode variant: hidden unit j's FFN2 column as a contiguous row (W2^T [4096][1024] per AR layer)
+    if (!e->ff2_t_blob) CK(cudaMalloc(&e->ff2_t_blob, (size_t)kL * kFF * kD * sizeof(bf16)));
+    for (int i = 0; i < kL; ++i) {
+      bf16* dst = (bf16*)e->ff2_t_blob + (size_t)i * kFF * kD;
+      transpose_bf16_kernel<<<dim3(kFF / 32, kD / 32), dim3(32, 8), 0, st>>>((const bf16*)e->ar[i].ff2_w, dst, kD, kFF);
+      e->ar[i].ff2_t = dst;
+    }
+    CK(cudaStreamSynchronize(st));
+  }
   for (int j = 0; j < 7; ++j) {
     e->nar_predict[j] = mat(e, "nar_predict_layers." + std::to_string(j) + ".weight");
     e->nar_predict_img[j] = matimg(e, "nar_predict_layers." + std::to_string(j) + ".weight");
@@ -786,7 +819,19 @@ int vx_ar_decode(vx_engine* e, int max_new, int top_k, float top_p, float temper
     pp.bt = e->bt;
     for (int l = 0; l < kL; ++l) {
       const LayerW& L = e->ar[l];
-      pp.layer[l] = PLayer{L.qkv_w, L.out_w, L.ff1_w, L.ff2_w, L.qkv_b, L.out_b, L.ff1_b, L.ff2_b, L.n1_g, L.n1_b, L.n2_g, L.n2_b};
+      pp.layer[l] = PLayer{L.qkv_w, L.out_w, L.ff1_w, L.ff2_w, L.ff2_t, L.qkv_b, L.out_b, L.ff1_b, L.ff2_b, L.n1_g, L.n1_b, L.n2_g, L.n2_b};
+    }
+    // 3-barrier variant: one attention unit per CTA, bf16 weights, B <= 8; anything else takes the 5-barrier kernel
+    pp.fused = (e->decode_fused && e->mode == VX_BF16 && B <= e->decode_fused_maxb && B * kH * ns <= e->num_sms &&
+                (kFF + e->num_sms - 1) / e->num_sms <= 64 && e->ar[0].ff2_t && !getenv("VX_DECODE_RING")) ? 1 : 0;
+    if (pp.fused) {
+      ENS(e->p_xb, (size_t)B * kD * 4);
+      ENS(e->p_acc, (size_t)4 * B * kD * 8);
+      CK(cudaMemsetAsync(e->p_acc.p, 0, (size_t)4 * B * kD * 8, st));
+      CK(cudaMemsetAsync(e->tick.p, 0, (size_t)B * kH * 4, st));
+      pp.xb = (float*)e->p_xb.p;
+      pp.acc_out = (long long*)e->p_acc.p;
+      pp.acc_ffn = (long long*)e->p_acc.p + (size_t)2 * B * kD;
     }
     pp.norm_g = e->ar_norm_g; pp.norm_b = e->ar_norm_b; pp.predict_w = e->ar_predict;
     pp.audio_emb = vec(e, "ar_audio_embedding.word_embeddings.weight"); pp.alpha = vec(e, "ar_audio_position.alpha"); pp.pe = e->pe;
