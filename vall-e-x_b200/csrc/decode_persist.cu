@@ -1529,6 +1529,697 @@ static cudaError_t fused_launch(const PParams& p, int grid, cudaStream_t st) {
   return cudaLaunchCooperativeKernel((void*)ar_decode_fused_kernel<MR>, dim3(grid), dim3(PNT), args, smem, st);
 }
 
+// =================================================================================================================
+// Two-barrier variant (bf16 weights, VX_DECODE_V4=1, experimental): 2 grid barriers per layer (26 per step).
+//   PA  stage x_l, LN1, the unit's share of ITS HEAD's q/k/v rows (192 rows of Wqkv split over the head's key-split
+//       CTAs) -> exchanged inside the head group through flag-carrying 8-byte stores (value + epoch in one store,
+//       readers poll the data itself: one L2 round trip, no fence, no ticket) -> attention on the unit's key split ->
+//       partials exchanged the same way -> fold -> out-proj share -> fixed-point accumulator      | grid barrier
+//   PB  residual + LN2 + FFN1 rows + ReLU + FFN2 share -> fixed-point accumulator                  | grid barrier
+// Only the two cross-head sums (out-proj, FFN2) need the whole grid; everything else is local to the <= 9 CTAs of a head.
+// =================================================================================================================
+__device__ __forceinline__ void ll_store(unsigned long long* p, float v, uint32_t epoch) {
+  const unsigned long long w = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(v);
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ unsigned long long ll_load(const unsigned long long* p) {
+  unsigned long long w;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+  return w;
+}
+// poll one element until its flag carries `epoch`
+__device__ __forceinline__ float ll_wait(const unsigned long long* p, uint32_t epoch) {
+  unsigned long long w;
+  unsigned int spins = 0;
+  do {
+    w = ll_load(p);
+    if (++spins > (1u << 24)) __trap();
+  } while ((uint32_t)(w >> 32) != epoch);
+  return __uint_as_float((uint32_t)w);
+}
+
+// row i (0..191) of head h's q|k|v block -> row of Wqkv [3072][1024]
+__device__ __forceinline__ int qkv_head_row(int h, int i) { return (i >> 6) * kD + h * kDH + (i & 63); }
+
+// attention unit of the two-barrier variant: q/k/v arrive through qkv_ll, partials leave through part_ll
+__device__ void attn_unit_v4(const PParams& p, int layer, int b, int h, int split, float* smem, uint32_t epoch,
+                             const WoPre& wp, const bf16* __restrict__ Wo, int r0, int r1, long long* accO) {
+  float* sq = smem;                  // [64]   (reused for the folded head output)
+  float* sknew = smem + 64;
+  float* svnew = smem + 128;
+  float* red = smem + 192;
+  float* sp = smem + 256;            // [PCHUNK]
+  float* sacc = sp + PCHUNK;         // [PNT/8][64]
+  const Batch& bt = p.bt;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ns = p.nsplit;
+  const int pos = bt.S[b] + bt.P[b] + ld_cg(bt.T + b);
+  const int n = pos + 1;
+  int chunk = (n + ns - 1) / ns;
+  chunk = (chunk + 31) & ~31;
+  const int j0 = split * chunk, j1 = min(n, j0 + chunk);
+  // ---- q/k/v of this head from the group's flag-carrying stores -------------------------------------------------
+  if (tid < 3 * kDH) {
+    const float v = ll_wait(p.qkv_ll + ((size_t)b * kH + h) * (3 * kDH) + tid, epoch);
+    if (tid < kDH) sq[tid] = v * 0.125f;
+    else smem[tid] = v;              // sknew | svnew are contiguous behind sq
+  }
+  __syncthreads();
+  bf16* kb = reinterpret_cast<bf16*>(p.kc) + (size_t)layer * p.kv_layer_elems + ((size_t)b * kH + h) * p.ctx_cap * kDH;
+  bf16* vb = reinterpret_cast<bf16*>(p.vc) + (size_t)layer * p.kv_layer_elems + ((size_t)b * kH + h) * p.ctx_cap * kDH;
+  if (split == 0 && tid < kDH) {
+    store_as(kb + (size_t)pos * kDH + tid, sknew[tid]);
+    store_as(vb + (size_t)pos * kDH + tid, svnew[tid]);
+  }
+  float mloc = -INFINITY;
+  for (int j = j0 + tid; j < j1; j += PNT) {
+    float s = 0.f;
+    if (j == pos) {
+#pragma unroll
+      for (int d = 0; d < kDH; ++d) s = fmaf(sq[d], kv_round<bf16>(sknew[d]), s);
+    } else {
+      const bf16* kr = kb + (size_t)j * kDH;
+#pragma unroll
+      for (int d = 0; d < kDH; d += 8) {
+        float w[8];
+        ldkv8(kr + d, w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s = fmaf(sq[d + i], w[i], s);
+      }
+    }
+    sp[j - j0] = s;
+    mloc = fmaxf(mloc, s);
+  }
+  const float m = block_max(mloc, red);
+  float lloc = 0.f;
+  for (int j = j0 + tid; j < j1; j += PNT) {
+    const float pr = expf(sp[j - j0] - m);
+    sp[j - j0] = pr;
+    lloc += pr;
+  }
+  const float l = block_sum(lloc, red);
+  constexpr int NG = PNT / 8;
+  const int g = tid >> 3, dc = (tid & 7) * 8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int j = j0 + g; j < j1; j += NG) {
+    const float pr = sp[j - j0];
+    float w[8];
+    if (j == pos) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w[i] = kv_round<bf16>(svnew[dc + i]);
+    } else {
+      ldkv8(vb + (size_t)j * kDH + dc, w);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = fmaf(pr, w[i], acc[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sacc[g * kDH + dc + i] = acc[i];
+  __syncthreads();
+  // ---- this split's partial (m, l, o[64]) to the group ---------------------------------------------------------------
+  unsigned long long* pg = p.part_ll + ((size_t)b * kH + h) * ns * (kDH + 2);
+  if (tid < kDH) {
+    float od = 0.f;
+    for (int q = 0; q < NG; ++q) od += sacc[q * kDH + tid];
+    ll_store(pg + (size_t)split * (kDH + 2) + 2 + tid, od, epoch);
+  }
+  if (tid == 0) {
+    ll_store(pg + (size_t)split * (kDH + 2), m, epoch);
+    ll_store(pg + (size_t)split * (kDH + 2) + 1, l, epoch);
+  }
+  // ---- fold all splits (fixed order); every load of a round is in flight at once, rounds repeat until all flags match --
+  if (tid < kDH) {
+    constexpr int U = 12;
+    float mv[U], lv[U], ov[U];
+    bool ok;
+    unsigned int spins = 0;
+    do {
+      ok = true;
+#pragma unroll
+      for (int s = 0; s < U; ++s) {
+        if (s < ns) {
+          const unsigned long long a = ll_load(pg + (size_t)s * (kDH + 2));
+          const unsigned long long c = ll_load(pg + (size_t)s * (kDH + 2) + 1);
+          const unsigned long long d = ll_load(pg + (size_t)s * (kDH + 2) + 2 + tid);
+          ok = ok && (uint32_t)(a >> 32) == epoch && (uint32_t)(c >> 32) == epoch && (uint32_t)(d >> 32) == epoch;
+          mv[s] = __uint_as_float((uint32_t)a); lv[s] = __uint_as_float((uint32_t)c); ov[s] = __uint_as_float((uint32_t)d);
+        } else {
+          mv[s] = -INFINITY; lv[s] = 0.f; ov[s] = 0.f;
+        }
+      }
+      if (++spins > (1u << 22)) __trap();
+    } while (!ok);
+    float M = -INFINITY;
+#pragma unroll
+    for (int s = 0; s < U; ++s) M = fmaxf(M, mv[s]);
+    float L = 0.f, O = 0.f;
+#pragma unroll
+    for (int s = 0; s < U; ++s) {
+      const float w = (mv[s] == -INFINITY) ? 0.f : expf(mv[s] - M);
+      L += w * lv[s];
+      O += w * ov[s];
+    }
+    sq[tid] = O / L;
+  }
+  __syncthreads();
+  // ---- out-proj share: rows [r0,r1) x this head's 64 columns -------------------------------------------------------
+  const int grp = lane >> 3, sub = lane & 7;
+  float xv[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) xv[i] = sq[sub * 8 + i];
+  for (int pass = 0; pass * 64 < r1 - r0; ++pass) {
+    const int nrow = r0 + pass * 64 + warp * 4 + grp;
+    const bool ok = nrow < r1;
+    uint4 raw;
+    if (pass < 2) raw = wp.r[pass];
+    else raw = ok ? ldw_raw(Wo + (size_t)nrow * kD + h * kDH + sub * 8) : make_uint4(0, 0, 0, 0);
+    float w[8];
+    raw_to_f32<bf16>(&raw, 0, w);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s = fmaf(w[i], xv[i], s);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (ok && sub == 0) fix_add(accO + (size_t)b * kD + nrow, s);
+  }
+}
+
+// request rows map(i), i = warp + j*16 < cnt, of W [.][1024]
+template <int MR, typename Map>
+__device__ __forceinline__ void gemv_issue_map(WPre<bf16, MR>& pre, const bf16* __restrict__ W, int cnt, const float* __restrict__ bias, Map map) {
+  const int warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int i = warp + j * PNW;
+    pre.bias[j] = 0.f;
+    if (i < cnt) {
+      const int n = map(i);
+      load_row_raw<bf16, MR>(W, kD, n, pre.r[j]);
+      if (bias) pre.bias[j] = bias[n];
+    }
+  }
+}
+// consume them (and any rows beyond 2 per warp); emit(i, m, value) by lane m
+template <int MR, typename Map, typename Emit>
+__device__ __forceinline__ void gemv_finish_map(WPre<bf16, MR>& pre, const bf16* __restrict__ W, int cnt, const float* __restrict__ sx,
+                                                int B, const float* __restrict__ bias, Map map, Emit emit) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i0 = warp, i1 = warp + PNW;
+  if (i0 < cnt) {  // warp-uniform
+    float a0[MR], a1[MR];
+#pragma unroll
+    for (int m = 0; m < MR; ++m) { a0[m] = 0.f; a1[m] = 0.f; }
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      float w0[8], w1[8];
+      raw_to_f32<bf16>(pre.r[0], it, w0);
+      raw_to_f32<bf16>(pre.r[1], it, w1);
+#pragma unroll
+      for (int m = 0; m < MR; ++m) {
+        const float4 x0 = *reinterpret_cast<const float4*>(&sx[m * kD + it * 256 + lane * 8]);
+        const float4 x1 = *reinterpret_cast<const float4*>(&sx[m * kD + it * 256 + lane * 8 + 4]);
+        const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a0[m] = fmaf(w0[i], xv[i], a0[m]); a1[m] = fmaf(w1[i], xv[i], a1[m]); }
+      }
+    }
+    float m0 = 0.f, m1 = 0.f;
+#pragma unroll
+    for (int m = 0; m < MR; ++m) {
+      const float s0 = warp_sum(a0[m]), s1 = warp_sum(a1[m]);
+      if (lane == m) { m0 = s0; m1 = s1; }
+    }
+    if (lane < B) {
+      emit(i0, lane, m0 + pre.bias[0]);
+      if (i1 < cnt) emit(i1, lane, m1 + pre.bias[1]);
+    }
+  }
+  for (int i = warp + 2 * PNW; i < cnt; i += PNW) {   // more than 32 rows per CTA (fewer key splits)
+    const int n = map(i);
+    uint4 raw[WPre<bf16, MR>::kVec];
+    load_row_raw<bf16, MR>(W, kD, n, raw);
+    float acc[MR];
+    row_dot<bf16, MR>(raw, sx, acc);
+    float mine = 0.f;
+#pragma unroll
+    for (int m = 0; m < MR; ++m)
+      if (lane == m) mine = acc[m];
+    if (lane < B) emit(i, lane, mine + (bias ? bias[n] : 0.f));
+  }
+}
+
+template <int MR>
+__global__ void __launch_bounds__(PNT, 1) ar_decode_v4_kernel(const PParams p) {
+  using WT = bf16;
+  extern __shared__ __align__(16) float dsm[];
+  float* sx = dsm;                       // [MR][1024]
+  float* hs = dsm + MR * kD;             // [MR][kHS]
+  float* scratch = hs + MR * kHS;
+  const Batch& bt = p.bt;
+  const int B = bt.B;
+  const int tid = threadIdx.x;
+  unsigned int epoch = 0;
+
+  int o0, o1, f0, f1, pr0, pr1;
+  slice(kD, o0, o1);
+  slice(kFF, f0, f1);
+  slice(kARLogits, pr0, pr1);
+  const int ns = p.nsplit;
+  const bool has_unit = (int)blockIdx.x < B * kH * ns;
+  const int u_split = blockIdx.x % ns, u_bh = blockIdx.x / ns, u_b = has_unit ? u_bh / kH : 0, u_h = u_bh % kH;
+  const int wr0 = (u_split * kD) / ns, wr1 = ((u_split + 1) * kD) / ns;            // out-proj rows of this unit
+  const int qi0 = (u_split * 3 * kDH) / ns, qi1 = ((u_split + 1) * 3 * kDH) / ns;   // its share of the head's q|k|v rows
+  const int qcnt = has_unit ? qi1 - qi0 : 0;
+  auto qmap = [&](int i) { return qkv_head_row(u_h, qi0 + i); };
+  long long* const accO2 = p.acc_out;
+  long long* const accF2 = p.acc_ffn;
+  const size_t accN = (size_t)B * kD;
+
+  WPre<WT, MR> pre;
+  WoPre wp;
+  LnPre lp;
+  gemv_issue_map<MR>(pre, reinterpret_cast<const WT*>(p.layer[0].qkv_w), qcnt, p.layer[0].qkv_b, qmap);
+  if (has_unit) wo_issue(wp, reinterpret_cast<const WT*>(p.layer[0].out_w), u_h, wr0, wr1);
+  ln_issue(lp, p.layer[0].n1_g, p.layer[0].n1_b, nullptr);
+  for (int i = tid; i < MR * kHS; i += PNT) hs[i] = 0.f;
+
+  long long* prof = nullptr;
+  const int prof_slot = (blockIdx.x == 0) ? 0 : (blockIdx.x == gridDim.x / 2) ? 1 : (blockIdx.x == gridDim.x - 1) ? 2 : -1;
+
+  int steps = 0;
+  for (int step = 0; step < p.max_steps; ++step) {
+    if (p.prof && prof_slot >= 0 && tid == 0) {
+      if (step == p.prof_step0) prof = p.prof + (size_t)prof_slot * 4096;
+      if (step == p.prof_step0 + 4) prof = nullptr;
+    }
+    // ---- S0: sample, append, embed (x_0 -> xa) ---------------------------------------------------------------------
+    for (int b = blockIdx.x; b < B; b += gridDim.x)
+      if (!ld_cg(bt.finished + b)) sample_utterance(p, b, scratch);
+    zero_slice(accF2 + accN, B, o0, o1);   // acc_ffn[1] was consumed by the previous step's PF
+    grid_barrier(p.bar, epoch, prof);
+    ++steps;
+    if (!p.ignore_eos && ld_cg(bt.n_active) <= 0) break;
+    if (step == p.max_steps - 1) break;
+
+    for (int l = 0; l < kL; ++l) {
+      const PLayer& L = p.layer[l];
+      const int par = l & 1;
+      long long* accO = accO2 + par * accN;
+      long long* accF = accF2 + par * accN;
+      long long* accO_prev = accO2 + (par ^ 1) * accN;
+      long long* accF_prev = accF2 + (par ^ 1) * accN;
+      const float* fb_prev = (l > 0) ? p.layer[l - 1].ff2_b : nullptr;
+      const WT* Wq = reinterpret_cast<const WT*>(L.qkv_w);
+      const WT* Wo = reinterpret_cast<const WT*>(L.out_w);
+      const WT* W1 = reinterpret_cast<const WT*>(L.ff1_w);
+      const WT* W2T = reinterpret_cast<const WT*>(L.ff2_t);
+      const uint32_t ll_epoch = (uint32_t)(step * kL + l + 1);
+      const bool unit_live = has_unit && !ld_cg(bt.finished + u_b);
+      // ---- PA ------------------------------------------------------------------------------------------------------
+      if (has_unit && tid == 0) {   // pull this unit's K/V range towards L2 while the q/k/v rows are computed
+        const int n = bt.S[u_b] + bt.P[u_b] + ld_cg(bt.T + u_b) + 1;
+        int chunk = (n + ns - 1) / ns;
+        chunk = (chunk + 31) & ~31;
+        const int j0 = u_split * chunk, j1 = min(n - 1, j0 + chunk);
+        if (j1 > j0) {
+          const size_t off = ((size_t)l * p.kv_layer_elems + ((size_t)u_b * kH + u_h) * p.ctx_cap * kDH + (size_t)j0 * kDH) * sizeof(WT);
+          l2_prefetch(reinterpret_cast<const char*>(p.kc) + off, (size_t)(j1 - j0) * kDH * sizeof(WT));
+          l2_prefetch(reinterpret_cast<const char*>(p.vc) + off, (size_t)(j1 - j0) * kDH * sizeof(WT));
+        }
+      }
+      ln_load(lp, L.n1_g, L.n1_b, fb_prev);
+      if (l == 0) {
+        stage_ln_x<MR>(sx, B, [&](int m, int c) { return __ldcg(p.xa + (size_t)m * kD + c); }, lp, scratch, nullptr, 0, 0);
+      } else {
+        stage_ln_x<MR>(sx, B, [&](int m, int c) { return __ldcg(p.xb + (size_t)m * kD + c) + fix_get(accF_prev + (size_t)m * kD + c); },
+                       lp, scratch, p.xa, o0, o1);
+      }
+      zero_slice(accO_prev, B, o0, o1);   // consumed by PB of the previous layer (layer 0: by PB of layer 11, re-zeroed twice: harmless)
+      PSTAMP(3);
+      // only this utterance's row of sx matters to the unit; all B rows are computed and row u_b is emitted
+      gemv_finish_map<MR>(pre, Wq, qcnt, sx, B, L.qkv_b, qmap, [&](int i, int m, float v) {
+        if (m == u_b && unit_live) ll_store(p.qkv_ll + ((size_t)u_b * kH + u_h) * (3 * kDH) + qi0 + i, v, ll_epoch);
+      });
+      PSTAMP(4);
+      gemv_issue<WT, MR>(pre, W1, kD, f0, f1, L.ff1_b, nullptr);   // FFN1 rows ride through the attention part
+      if (unit_live) attn_unit_v4(p, l, u_b, u_h, u_split, scratch, ll_epoch, wp, Wo, wr0, wr1, accO);
+      ln_issue(lp, L.n2_g, L.n2_b, L.out_b);
+      if (tid == 0) l2_prefetch(W2T + (size_t)f0 * kD, (size_t)(f1 - f0) * kD * sizeof(WT));
+      PSTAMP(5);
+      grid_barrier(p.bar, epoch, prof);
+      // ---- PB ------------------------------------------------------------------------------------------------------
+      ln_load(lp, L.n2_g, L.n2_b, L.out_b);
+      stage_ln_x<MR>(sx, B, [&](int m, int c) { return __ldcg(p.xa + (size_t)m * kD + c) + fix_get(accO + (size_t)m * kD + c); },
+                     lp, scratch, p.xb, o0, o1);
+      if (l > 0) zero_slice(accF_prev, B, o0, o1);   // consumed by PA of this layer
+      PSTAMP(3);
+      gemv_finish<WT, MR>(pre, W1, kD, f0, f1, sx, B, L.ff1_b, nullptr, [&](int, int) { return 0.f; },
+                          [&](int n, int m, float v) { hs[m * kHS + (n - f0)] = fmaxf(v, 0.f); });
+      __syncthreads();
+      PSTAMP(4);
+      ffn2_share<MR>(W2T, f0, f1, hs, B, accF);
+      if (l + 1 < kL) {
+        gemv_issue_map<MR>(pre, reinterpret_cast<const WT*>(p.layer[l + 1].qkv_w), qcnt, p.layer[l + 1].qkv_b, qmap);
+        if (has_unit) wo_issue(wp, reinterpret_cast<const WT*>(p.layer[l + 1].out_w), u_h, wr0, wr1);
+        ln_issue(lp, p.layer[l + 1].n1_g, p.layer[l + 1].n1_b, L.ff2_b);
+      } else {
+        gemv_issue<WT, MR>(pre, reinterpret_cast<const WT*>(p.predict_w), kD, pr0, pr1, nullptr, nullptr);
+        ln_issue(lp, p.norm_g, p.norm_b, L.ff2_b);
+      }
+      PSTAMP(5);
+      grid_barrier(p.bar, epoch, prof);
+    }
+    // ---- PF --------------------------------------------------------------------------------------------------------
+    ln_load(lp, p.norm_g, p.norm_b, p.layer[kL - 1].ff2_b);
+    stage_ln_x<MR>(sx, B, [&](int m, int c) { return __ldcg(p.xb + (size_t)m * kD + c) + fix_get(accF2 + accN + (size_t)m * kD + c); },
+                   lp, scratch, nullptr, 0, 0);
+    zero_slice(accO2 + accN, B, o0, o1);   // acc_out[1] was consumed by PB of layer 11
+    gemv_finish<WT, MR>(pre, reinterpret_cast<const WT*>(p.predict_w), kD, pr0, pr1, sx, B, nullptr, nullptr,
+                        [&](int, int) { return 0.f; },
+                        [&](int n, int m, float v) { p.logits[(size_t)m * kARLogits + n] = v; });
+    gemv_issue_map<MR>(pre, reinterpret_cast<const WT*>(p.layer[0].qkv_w), qcnt, p.layer[0].qkv_b, qmap);
+    if (has_unit) wo_issue(wp, reinterpret_cast<const WT*>(p.layer[0].out_w), u_h, wr0, wr1);
+    ln_issue(lp, p.layer[0].n1_g, p.layer[0].n1_b, nullptr);
+    grid_barrier(p.bar, epoch, prof);
+  }
+  if (blockIdx.x == 0 && tid == 0) *p.steps_done = steps;
+}
+
+template <int MR>
+static cudaError_t v4_launch(const PParams& p, int grid, cudaStream_t st) {
+  const size_t scratch_floats = 256 + PCHUNK + (PNT / 8) * kDH;
+  const size_t sample_floats = 1032 + PSORT + PSORT / 2 + PNT + 32 + 8;
+  const size_t smem = ((size_t)MR * kD + (size_t)MR * kHS + std::max(scratch_floats, sample_floats)) * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(ar_decode_v4_kernel<MR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ar_decode_v4_kernel<MR>, PNT, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+  void* args[] = {(void*)&p};
+  return cudaLaunchCooperativeKernel((void*)ar_decode_v4_kernel<MR>, dim3(grid), dim3(PNT), args, smem, st);
+}
+
+// =================================================================================================================
+// Batched variant (bf16 weights, 8 <= B <= 32, VX_DECODE_MMA=1, experimental): the five GEMV phases of the 62-barrier
+// kernel on tensor cores.  Weights are the M operand of mma.sync.m16n8k16 (a CTA's <= 32-row slice = two m-tiles),
+// the batch is N, activations are split into bf16 hi + lo halves (two MMAs, fp32 accumulate: fp32-grade activations).
+// The k index inside a 32-element chunk is permuted identically for A and B, so every lane loads 16 contiguous bytes
+// of a weight row (64-byte runs per row) and its B fragments are 16-byte shared-memory loads from a fragment-ordered
+// image written by the staging step.  16 warps = 2 m-tiles x 8 k-groups; the partial tiles are reduced through shared
+// memory in fixed order.  (The CUDA-core path re-reads B x 4 KB of activations per weight row and spills at MR >= 8.)
+// =================================================================================================================
+struct MPre { uint4 ra[4], rb[4]; };   // weight rows (g, g+8) of this warp's m-tile: 4 chunks of 32 k of its k-group
+
+__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// Fragment image of the activations (hi and lo separately): [k-group 8][chunk 4][n-tile MR/8][lane 32] x 16 B, the 16 B of
+// lane (g, q) = batch row nt*8+g, columns kg*128 + ch*32 + q*8 .. +7 in order (words 0,1 = (b0,b1) of the chunk's first
+// m16n8k16, words 2,3 = of its second).
+template <int MR>
+__device__ __forceinline__ void frag_store(uint16_t* fh, uint16_t* fl, int m, int c, float v) {
+  constexpr int NT = MR / 8;
+  const int kg = c >> 7, ch = (c >> 5) & 3, q = (c >> 3) & 3, e = c & 7;
+  const size_t idx = (((((size_t)kg * 4 + ch) * NT + (m >> 3)) * 32) + (m & 7) * 4 + q) * 8 + e;
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+  fh[idx] = __bfloat16_as_ushort(h);
+  fl[idx] = __bfloat16_as_ushort(l);
+}
+
+template <int MR, typename Val>
+__device__ __forceinline__ void stage_ln_frag(uint16_t* fh, uint16_t* fl, int B, Val value, const LnPre& lp, float* red) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int R = 8;
+  for (int mb = 0; mb < B; mb += R) {
+    const int nb = min(R, B - mb);
+    float v0[R], v1[R];
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+      v0[m] = (m < nb) ? value(mb + m, tid) + lp.f0 : 0.f;
+      v1[m] = (m < nb) ? value(mb + m, tid + PNT) + lp.f1 : 0.f;
+    }
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+      const float s = warp_sum(v0[m] + v1[m]);
+      if (lane == 0) red[warp * 8 + m] = s;
+    }
+    __syncthreads();
+    float mean[R];
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < PNW; ++w) s += red[w * 8 + m];
+      mean[m] = s / (float)kD;
+    }
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+      const float d0 = v0[m] - mean[m], d1 = v1[m] - mean[m];
+      const float s = warp_sum(d0 * d0 + d1 * d1);
+      if (lane == 0) red[PNW * 8 + warp * 8 + m] = s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+      if (m < nb) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < PNW; ++w) s += red[PNW * 8 + w * 8 + m];
+        const float rstd = 1.0f / sqrtf(s / (float)kD + 1e-5f);
+        frag_store<MR>(fh, fl, mb + m, tid, __fadd_rn(__fmul_rn((v0[m] - mean[m]) * rstd, lp.g0), lp.b0));
+        frag_store<MR>(fh, fl, mb + m, tid + PNT, __fadd_rn(__fmul_rn((v1[m] - mean[m]) * rstd, lp.g1), lp.b1));
+      }
+    }
+    __syncthreads();
+  }
+}
+template <int MR, typename Val>
+__device__ __forceinline__ void stage_plain_frag(uint16_t* fh, uint16_t* fl, int B, Val value) {
+  for (int i = threadIdx.x; i < B * kD; i += PNT) frag_store<MR>(fh, fl, i / kD, i % kD, value(i / kD, i % kD));
+  __syncthreads();
+}
+
+// request this warp's share of rows [r0,r1) (<= 32 rows) of W [.][ldw], k columns [0,1024)
+__device__ __forceinline__ void gemv_issue_mma(MPre& pre, const bf16* __restrict__ W, size_t ldw, int r0, int r1) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = warp & 1, kg = warp >> 1, g = lane >> 2, q = lane & 3;
+  const int ra = r0 + mt * 16 + g, rb = ra + 8;
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    const int k = kg * 128 + ch * 32 + q * 8;
+    pre.ra[ch] = (ra < r1) ? ldw_raw(W + (size_t)ra * ldw + k) : make_uint4(0, 0, 0, 0);
+    pre.rb[ch] = (rb < r1) ? ldw_raw(W + (size_t)rb * ldw + k) : make_uint4(0, 0, 0, 0);
+  }
+}
+
+// rows [r0,r1) x batch: tensor-core partial tiles, fixed-order reduction over the 8 k-groups, then
+// emit(n, m, dot + addend(n, m) + bias[n] + bias2[n]).  red: [8][32][MR] floats.
+template <int MR, typename Add, typename Emit>
+__device__ __forceinline__ void gemv_finish_mma(const MPre& pre, const uint16_t* fh, const uint16_t* fl, int r0, int r1, int B,
+                                                const float* __restrict__ bias, const float* __restrict__ bias2, float* red,
+                                                Add addend, Emit emit) {
+  constexpr int NT = MR / 8;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mt = warp & 1, kg = warp >> 1, g = lane >> 2, q = lane & 3;
+  float c[NT][4];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) { c[nt][0] = 0.f; c[nt][1] = 0.f; c[nt][2] = 0.f; c[nt][3] = 0.f; }
+  const uint4* H = reinterpret_cast<const uint4*>(fh);
+  const uint4* Lo = reinterpret_cast<const uint4*>(fl);
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int idx = ((kg * 4 + ch) * NT + nt) * 32 + lane;
+      const uint4 xh = H[idx], xl = Lo[idx];
+      mma_16816(c[nt], pre.ra[ch].x, pre.rb[ch].x, pre.ra[ch].y, pre.rb[ch].y, xh.x, xh.y);
+      mma_16816(c[nt], pre.ra[ch].x, pre.rb[ch].x, pre.ra[ch].y, pre.rb[ch].y, xl.x, xl.y);
+      mma_16816(c[nt], pre.ra[ch].z, pre.rb[ch].z, pre.ra[ch].w, pre.rb[ch].w, xh.z, xh.w);
+      mma_16816(c[nt], pre.ra[ch].z, pre.rb[ch].z, pre.ra[ch].w, pre.rb[ch].w, xl.z, xl.w);
+    }
+  }
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const int row = mt * 16 + g, n = nt * 8 + q * 2;
+    float* d0 = red + ((size_t)kg * 32 + row) * MR + n;
+    float* d1 = red + ((size_t)kg * 32 + row + 8) * MR + n;
+    d0[0] = c[nt][0]; d0[1] = c[nt][1];
+    d1[0] = c[nt][2]; d1[1] = c[nt][3];
+  }
+  __syncthreads();
+  for (int t = tid; t < 32 * MR; t += PNT) {
+    const int row = t / MR, m = t % MR, n = r0 + row;
+    if (n < r1 && m < B) {
+      float s = 0.f;
+#pragma unroll
+      for (int k8 = 0; k8 < 8; ++k8) s += red[((size_t)k8 * 32 + row) * MR + m];
+      emit(n, m, s + (addend(n, m) + (bias ? bias[n] : 0.f) + (bias2 ? bias2[n] : 0.f)));
+    }
+  }
+  __syncthreads();
+}
+
+template <int MR>
+__global__ void __launch_bounds__(PNT, 1) ar_decode_mma_kernel(const PParams p) {
+  using WT = bf16;
+  extern __shared__ __align__(16) float dsm[];
+  uint16_t* fh = reinterpret_cast<uint16_t*>(dsm);        // [MR*1024] hi halves, fragment order
+  uint16_t* fl = fh + MR * kD;                             // [MR*1024] lo halves
+  float* scratch = dsm + MR * kD;                          // attention / sampling / LN scratch
+  float* red = scratch;                                    // [8][32][MR] partial tiles (GEMV phases only)
+  const Batch& bt = p.bt;
+  const int B = bt.B;
+  const int tid = threadIdx.x;
+  unsigned int epoch = 0;
+  const size_t wsz = sizeof(WT);
+
+  int q0, q1, o0, o1, f0, f1, pr0, pr1;
+  slice(3 * kD, q0, q1);
+  slice(kD, o0, o1);
+  slice(kFF, f0, f1);
+  slice(kARLogits, pr0, pr1);
+  const int per = gridDim.x / 4;
+  const int kc = min((int)blockIdx.x / per, 3);
+  const int kc_first = kc * per;
+  const int kc_n = (kc == 3) ? (int)gridDim.x - kc_first : per;
+  const int g0 = (int)(((long long)(blockIdx.x - kc_first) * kD) / kc_n);
+  const int g1 = (int)(((long long)(blockIdx.x - kc_first + 1) * kD) / kc_n);
+
+  MPre pre;
+  LnPre lp;
+  const WT* Wqkv0 = reinterpret_cast<const WT*>(p.layer[0].qkv_w);
+  gemv_issue_mma(pre, Wqkv0, kD, q0, q1);
+  ln_issue(lp, p.layer[0].n1_g, p.layer[0].n1_b, nullptr);
+
+  long long* prof = nullptr;
+  const int prof_slot = (blockIdx.x == 0) ? 0 : (blockIdx.x == gridDim.x / 2) ? 1 : (blockIdx.x == gridDim.x - 1) ? 2 : -1;
+  auto zero = [](int, int) { return 0.f; };
+
+  int steps = 0;
+  for (int step = 0; step < p.max_steps; ++step) {
+    if (p.prof && prof_slot >= 0 && tid == 0) {
+      if (step == p.prof_step0) prof = p.prof + (size_t)prof_slot * 4096;
+      if (step == p.prof_step0 + 4) prof = nullptr;
+    }
+    for (int b = blockIdx.x; b < B; b += gridDim.x)
+      if (!ld_cg(bt.finished + b)) sample_utterance(p, b, scratch);
+    grid_barrier(p.bar, epoch, prof);
+    ++steps;
+    if (!p.ignore_eos && ld_cg(bt.n_active) <= 0) break;
+    if (step == p.max_steps - 1) break;
+
+    for (int l = 0; l < kL; ++l) {
+      const PLayer& L = p.layer[l];
+      const float* fb_prev = (l > 0) ? p.layer[l - 1].ff2_b : nullptr;
+      const WT* Wq = reinterpret_cast<const WT*>(L.qkv_w);
+      const WT* Wo = reinterpret_cast<const WT*>(L.out_w);
+      const WT* W1 = reinterpret_cast<const WT*>(L.ff1_w);
+      const WT* W2 = reinterpret_cast<const WT*>(L.ff2_w) + (size_t)kc * kD;
+      (void)Wq;
+      // ---- P1: LN1 + QKV rows ----------------------------------------------------------------------------------------
+      for (int u = blockIdx.x; u < B * kH * p.nsplit; u += gridDim.x) {
+        if (tid == 0) {
+          const int split = u % p.nsplit, bh = u / p.nsplit, b = bh / kH, h = bh % kH;
+          const int n = bt.S[b] + bt.P[b] + ld_cg(bt.T + b) + 1;
+          int chunk = (n + p.nsplit - 1) / p.nsplit;
+          chunk = (chunk + 31) & ~31;
+          const int j0 = split * chunk, j1 = min(n - 1, j0 + chunk);
+          if (j1 > j0) {
+            const size_t off = ((size_t)l * p.kv_layer_elems + ((size_t)b * kH + h) * p.ctx_cap * kDH + (size_t)j0 * kDH) * wsz;
+            l2_prefetch(reinterpret_cast<const char*>(p.kc) + off, (size_t)(j1 - j0) * kDH * wsz);
+            l2_prefetch(reinterpret_cast<const char*>(p.vc) + off, (size_t)(j1 - j0) * kDH * wsz);
+          }
+        }
+      }
+      ln_load(lp, L.n1_g, L.n1_b, fb_prev);
+      stage_ln_frag<MR>(fh, fl, B, [&](int m, int c) { return stream_dyn(p, l, m, c, B); }, lp, scratch);
+      PSTAMP(3);
+      gemv_finish_mma<MR>(pre, fh, fl, q0, q1, B, L.qkv_b, nullptr, red, zero,
+                          [&](int n, int m, float v) { p.qkv[(size_t)m * 3 * kD + n] = v; });
+      PSTAMP(4);
+      gemv_issue_mma(pre, Wo, kD, o0, o1);
+      PSTAMP(5);
+      grid_barrier(p.bar, epoch, prof);
+      // ---- P2: attention (ticket fold) -----------------------------------------------------------------------------------
+      for (int u = blockIdx.x; u < B * kH * p.nsplit; u += gridDim.x) {
+        const int split = u % p.nsplit, bh = u / p.nsplit;
+        const int b = bh / kH, h = bh % kH;
+        if (ld_cg(bt.finished + b)) continue;
+        attn_unit<bf16>(p, l, b, h, split, scratch);
+      }
+      grid_barrier(p.bar, epoch, prof);
+      // ---- P3: out-proj + residual -> xa ---------------------------------------------------------------------------------
+      stage_plain_frag<MR>(fh, fl, B, [&](int m, int c) {
+        if (ld_cg(bt.finished + m)) return 0.f;
+        return (p.dbg & 2) ? att_combined(p, m, c) : __ldcg(p.att + (size_t)m * kD + c);
+      });
+      PSTAMP(3);
+      gemv_finish_mma<MR>(pre, fh, fl, o0, o1, B, L.out_b, fb_prev, red, [&](int n, int m) { return stream_dyn(p, l, m, n, B); },
+                          [&](int n, int m, float v) { p.xa[(size_t)m * kD + n] = v; });
+      PSTAMP(4);
+      gemv_issue_mma(pre, W1, kD, f0, f1);
+      ln_issue(lp, L.n2_g, L.n2_b, nullptr);
+      PSTAMP(5);
+      grid_barrier(p.bar, epoch, prof);
+      // ---- P4: LN2 + FFN1 + ReLU -----------------------------------------------------------------------------------------
+      ln_load(lp, L.n2_g, L.n2_b, nullptr);
+      stage_ln_frag<MR>(fh, fl, B, [&](int m, int c) { return __ldcg(p.xa + (size_t)m * kD + c); }, lp, scratch);
+      PSTAMP(3);
+      gemv_finish_mma<MR>(pre, fh, fl, f0, f1, B, L.ff1_b, nullptr, red, zero,
+                          [&](int n, int m, float v) { p.hid[(size_t)m * kFF + n] = fmaxf(v, 0.f); });
+      PSTAMP(4);
+      gemv_issue_mma(pre, W2, kFF, g0, g1);
+      PSTAMP(5);
+      grid_barrier(p.bar, epoch, prof);
+      // ---- P5: FFN2, split-K -----------------------------------------------------------------------------------------------
+      stage_plain_frag<MR>(fh, fl, B, [&](int m, int c) { return __ldcg(p.hid + (size_t)m * kFF + kc * kD + c); });
+      PSTAMP(3);
+      gemv_finish_mma<MR>(pre, fh, fl, g0, g1, B, nullptr, nullptr, red, zero,
+                          [&](int n, int m, float v) { p.pf[((size_t)kc * B + m) * kD + n] = v; });
+      PSTAMP(4);
+      if (l + 1 < kL) {
+        gemv_issue_mma(pre, reinterpret_cast<const WT*>(p.layer[l + 1].qkv_w), kD, q0, q1);
+        ln_issue(lp, p.layer[l + 1].n1_g, p.layer[l + 1].n1_b, L.ff2_b);
+      } else {
+        gemv_issue_mma(pre, reinterpret_cast<const WT*>(p.predict_w), kD, pr0, pr1);
+        ln_issue(lp, p.norm_g, p.norm_b, L.ff2_b);
+      }
+      grid_barrier(p.bar, epoch, prof);
+    }
+    // ---- PF ------------------------------------------------------------------------------------------------------------------
+    ln_load(lp, p.norm_g, p.norm_b, p.layer[kL - 1].ff2_b);
+    stage_ln_frag<MR>(fh, fl, B, [&](int m, int c) { return stream_dyn(p, kL, m, c, B); }, lp, scratch);
+    gemv_finish_mma<MR>(pre, fh, fl, pr0, pr1, B, nullptr, nullptr, red, zero,
+                        [&](int n, int m, float v) { p.logits[(size_t)m * kARLogits + n] = v; });
+    gemv_issue_mma(pre, Wqkv0, kD, q0, q1);
+    ln_issue(lp, p.layer[0].n1_g, p.layer[0].n1_b, nullptr);
+    grid_barrier(p.bar, epoch, prof);
+  }
+  if (blockIdx.x == 0 && tid == 0) *p.steps_done = steps;
+}
+
+template <int MR>
+static cudaError_t mma_launch(const PParams& p, int grid, cudaStream_t st) {
+  const size_t scratch_floats = 256 + PCHUNK + (PNT / 8) * kDH;
+  const size_t sample_floats = 1032 + PSORT + PSORT / 2 + PNT + 32 + 8;
+  const size_t red_floats = (size_t)8 * 32 * MR;
+  const size_t smem = ((size_t)MR * kD + std::max(std::max(scratch_floats, sample_floats), red_floats)) * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(ar_decode_mma_kernel<MR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ar_decode_mma_kernel<MR>, PNT, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+  void* args[] = {(void*)&p};
+  return cudaLaunchCooperativeKernel((void*)ar_decode_mma_kernel<MR>, dim3(grid), dim3(PNT), args, smem, st);
+}
+
 template <int MR>
 static cudaError_t ring_launch(const PParams& p, int grid, cudaStream_t st) {
   const size_t smem = 2 * (size_t)RSTAGE_BYTES + (size_t)MR * kD * 4 + 32768 + 64;
@@ -1557,6 +2248,22 @@ static cudaError_t persist_launch(const PParams& p, int grid, cudaStream_t st) {
 int launch_decode_persistent(const void* params, int wt, int B, int grid, cudaStream_t st) {
   const PParams& p = *reinterpret_cast<const PParams*>(params);
   const int mr = B <= 1 ? 1 : B <= 2 ? 2 : B <= 4 ? 4 : B <= 8 ? 8 : B <= 16 ? 16 : 32;
+  if (wt == 1 && mr >= 8 && grid >= 128 && getenv("VX_DECODE_MMA")) {  // experimental tensor-core batched variant (<= 32 rows per CTA slice)
+    switch (mr) {
+      case 8: return (int)mma_launch<8>(p, grid, st);
+      case 16: return (int)mma_launch<16>(p, grid, st);
+      default: return (int)mma_launch<32>(p, grid, st);
+    }
+  }
+  if (wt == 1 && p.fused == 2) {  // experimental two-barrier variant (VX_DECODE_V4=1): same preconditions as the 3-barrier one
+    if (mr > 8 || B * kH * p.nsplit > grid || (kFF + grid - 1) / grid > kHS) return (int)cudaErrorInvalidConfiguration;
+    switch (mr) {
+      case 1: return (int)v4_launch<1>(p, grid, st);
+      case 2: return (int)v4_launch<2>(p, grid, st);
+      case 4: return (int)v4_launch<4>(p, grid, st);
+      default: return (int)v4_launch<8>(p, grid, st);
+    }
+  }
   if (wt == 1 && p.fused) {  // 3-barrier variant: requires one attention unit per CTA and <= kHS hidden units per CTA
     if (mr > 8 || B * kH * p.nsplit > grid || (kFF + grid - 1) / grid > kHS) return (int)cudaErrorInvalidConfiguration;
     switch (mr) {

@@ -114,7 +114,7 @@ struct vx_engine {
   bool attn_t5 = false;                              // VX_ATTN_T5=1: tcgen05/TMEM attention instead of mma.sync
   int64_t full_rows = 0;                             // packed rows of the current full-sequence pass (128-aligned starts)
   Buf xs, xsn, qkvs, atts, ffs, logits, part, tick;  // decode-step scratch
-  Buf p_xb, p_acc;                                   // fused decode variant: mid-layer residual, fixed-point accumulators
+  Buf p_xb, p_acc, p_ll;                                 // fused decode variant: mid-layer residual, fixed-point accumulators
   Buf p_pf, p_bar, p_prof;                                   // persistent decode: FFN2 partials, barrier counter + steps
   int num_sms = 148;
   bool decode_graph = false;                         // VX_DECODE_GRAPH=1: per-step CUDA-graph path instead of the persistent kernel
@@ -401,7 +401,7 @@ void vx_destroy(vx_engine* e) {
   }
   Buf* bufs[] = {&e->d_text, &e->d_lang, &e->d_prompt, &e->d_S, &e->d_P, &e->d_ar_row0, &e->d_nar_row0, &e->d_T,
                  &e->d_ctx, &e->d_y, &e->d_budget, &e->d_fin, &e->d_slp, &e->d_nact, &e->x, &e->xn, &e->qkv, &e->att,
-                 &e->ffh, &e->kc, &e->vc, &e->a_img, &e->qkv16, &e->att_img, &e->h_img, &e->t_img, &e->q_img, &e->k_img, &e->vt_img, &e->xs, &e->xsn, &e->qkvs, &e->atts, &e->ffs, &e->logits, &e->part, &e->tick, &e->p_xb, &e->p_acc, &e->p_pf, &e->p_bar, &e->p_prof,
+                 &e->ffh, &e->kc, &e->vc, &e->a_img, &e->qkv16, &e->att_img, &e->h_img, &e->t_img, &e->q_img, &e->k_img, &e->vt_img, &e->xs, &e->xsn, &e->qkvs, &e->atts, &e->ffs, &e->logits, &e->part, &e->tick, &e->p_xb, &e->p_acc, &e->p_ll, &e->p_pf, &e->p_bar, &e->p_prof,
                  &e->lastmap, &e->out_tok, &e->forced, &e->yemb, &e->yrow0, &e->trow0, &e->tgtmap, &e->nlog, &e->codes,
                  &e->tl_dev, &e->cb0_dev, &e->v_codes, &e->v_feat, &e->v_col, &e->v_x, &e->v_h, &e->v_ff, &e->v_head,
                  &e->v_spec, &e->v_frames, &e->v_wave};
@@ -832,6 +832,15 @@ int vx_ar_decode(vx_engine* e, int max_new, int top_k, float top_p, float temper
       pp.xb = (float*)e->p_xb.p;
       pp.acc_out = (long long*)e->p_acc.p;
       pp.acc_ffn = (long long*)e->p_acc.p + (size_t)2 * B * kD;
+      const char* v4 = getenv("VX_DECODE_V4");
+      if (v4 && v4[0] == '1' && ns <= 12) {   // experimental two-barrier kernel: flag-carrying exchange buffers, epochs restart per launch
+        const size_t nq = (size_t)B * kH * 3 * kDH, np = (size_t)B * kH * ns * (kDH + 2);
+        ENS(e->p_ll, (nq + np) * 8);
+        CK(cudaMemsetAsync(e->p_ll.p, 0, (nq + np) * 8, st));
+        pp.qkv_ll = (unsigned long long*)e->p_ll.p;
+        pp.part_ll = (unsigned long long*)e->p_ll.p + nq;
+        pp.fused = 2;
+      }
     }
     pp.norm_g = e->ar_norm_g; pp.norm_b = e->ar_norm_b; pp.predict_w = e->ar_predict;
     pp.audio_emb = vec(e, "ar_audio_embedding.word_embeddings.weight"); pp.alpha = vec(e, "ar_audio_position.alpha"); pp.pe = e->pe;
