@@ -2248,7 +2248,8 @@ static cudaError_t persist_launch(const PParams& p, int grid, cudaStream_t st) {
 int launch_decode_persistent(const void* params, int wt, int B, int grid, cudaStream_t st) {
   const PParams& p = *reinterpret_cast<const PParams*>(params);
   const int mr = B <= 1 ? 1 : B <= 2 ? 2 : B <= 4 ? 4 : B <= 8 ? 8 : B <= 16 ? 16 : 32;
-  if (wt == 1 && mr >= 8 && grid >= 128 && getenv("VX_DECODE_MMA")) {  // experimental tensor-core batched variant (<= 32 rows per CTA slice)
+  const char* mma_env = getenv("VX_DECODE_MMA");   // tensor-core batched variant (<= 32 rows per CTA slice); VX_DECODE_MMA=0 -> CUDA-core GEMV
+  if (wt == 1 && mr >= 8 && grid >= 128 && !(mma_env && mma_env[0] == '0')) {
     switch (mr) {
       case 8: return (int)mma_launch<8>(p, grid, st);
       case 16: return (int)mma_launch<16>(p, grid, st);
