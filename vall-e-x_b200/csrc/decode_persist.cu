@@ -1906,6 +1906,317 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_v4_kernel(const PParams p) {
   if (blockIdx.x == 0 && tid == 0) *p.steps_done = steps;
 }
 
+// =================================================================================================================
+// Cluster variant (bf16 weights, B = 1, VX_DECODE_CLUSTER=1, experimental): the two-barrier layout of the v4 kernel with
+// the head group mapped onto a thread-block CLUSTER: 16 clusters x 8 CTAs = 128 CTAs (8 GPCs x two 8-CTA clusters is what
+// fits co-resident on the 148 SMs), cluster c = head c, rank = key split.  q/k/v of the head and the attention partials
+// are written to the producer's own shared memory and read by the other ranks through distributed shared memory behind
+// barrier.cluster (~0.2 us) instead of through L2 flags (~1.5-2 us per exchange).  Grid barriers as before.
+// =================================================================================================================
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// read a float from the same shared-memory offset in cluster rank `rank`
+__device__ __forceinline__ float dsmem_ld(const float* local, uint32_t rank) {
+  const uint32_t la = (uint32_t)__cvta_generic_to_shared(local);
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
+
+constexpr int kCS = 8;                 // cluster size = key splits per head
+constexpr int kQShare = 3 * kDH / kCS; // 24 of the head's 192 q|k|v rows per CTA
+
+// xchg: [0,24) this CTA's q|k|v values, [32, 32+66) its attention partial (m, l, o[64]); read by the other ranks via DSMEM
+__device__ void attn_unit_cluster(const PParams& p, int layer, int h, int split, float* smem, float* xchg,
+                                  const WoPre& wp, const bf16* __restrict__ Wo, int r0, int r1, long long* accO) {
+  float* sq = smem;                  // [64]   (reused for the folded head output)
+  float* sknew = smem + 64;
+  float* svnew = smem + 128;
+  float* red = smem + 192;
+  float* sp = smem + 256;            // [PCHUNK]
+  float* sacc = sp + PCHUNK;         // [PNT/8][64]
+  const Batch& bt = p.bt;
+  const int b = 0;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int pos = bt.S[b] + bt.P[b] + ld_cg(bt.T + b);
+  const int n = pos + 1;
+  int chunk = (n + kCS - 1) / kCS;
+  chunk = (chunk + 31) & ~31;
+  const int j0 = split * chunk, j1 = min(n, j0 + chunk);
+  // ---- q/k/v of this head: element i lives in rank i / 24 at xchg[i % 24] -----------------------------------------------
+  cluster_sync_all();                // every rank's q|k|v share is in its xchg[0,24)
+  if (tid < 3 * kDH) {
+    const float v = dsmem_ld(xchg + (tid % kQShare), (uint32_t)(tid / kQShare));
+    if (tid < kDH) sq[tid] = v * 0.125f;
+    else smem[tid] = v;              // sknew | svnew are contiguous behind sq
+  }
+  __syncthreads();
+  bf16* kb = reinterpret_cast<bf16*>(p.kc) + (size_t)layer * p.kv_layer_elems + ((size_t)b * kH + h) * p.ctx_cap * kDH;
+  bf16* vb = reinterpret_cast<bf16*>(p.vc) + (size_t)layer * p.kv_layer_elems + ((size_t)b * kH + h) * p.ctx_cap * kDH;
+  if (split == 0 && tid < kDH) {
+    store_as(kb + (size_t)pos * kDH + tid, sknew[tid]);
+    store_as(vb + (size_t)pos * kDH + tid, svnew[tid]);
+  }
+  float mloc = -INFINITY;
+  for (int j = j0 + tid; j < j1; j += PNT) {
+    float s = 0.f;
+    if (j == pos) {
+#pragma unroll
+      for (int d = 0; d < kDH; ++d) s = fmaf(sq[d], kv_round<bf16>(sknew[d]), s);
+    } else {
+      const bf16* kr = kb + (size_t)j * kDH;
+#pragma unroll
+      for (int d = 0; d < kDH; d += 8) {
+        float w[8];
+        ldkv8(kr + d, w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s = fmaf(sq[d + i], w[i], s);
+      }
+    }
+    sp[j - j0] = s;
+    mloc = fmaxf(mloc, s);
+  }
+  const float m = block_max(mloc, red);
+  float lloc = 0.f;
+  for (int j = j0 + tid; j < j1; j += PNT) {
+    const float pr = expf(sp[j - j0] - m);
+    sp[j - j0] = pr;
+    lloc += pr;
+  }
+  const float l = block_sum(lloc, red);
+  constexpr int NG = PNT / 8;
+  const int g = tid >> 3, dc = (tid & 7) * 8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int j = j0 + g; j < j1; j += NG) {
+    const float pr = sp[j - j0];
+    float w[8];
+    if (j == pos) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w[i] = kv_round<bf16>(svnew[dc + i]);
+    } else {
+      ldkv8(vb + (size_t)j * kDH + dc, w);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = fmaf(pr, w[i], acc[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sacc[g * kDH + dc + i] = acc[i];
+  __syncthreads();
+  // ---- this split's partial into its own xchg[32..98) ------------------------------------------------------------------
+  float* mypart = xchg + 32;
+  if (tid < kDH) {
+    float od = 0.f;
+    for (int q = 0; q < NG; ++q) od += sacc[q * kDH + tid];
+    mypart[2 + tid] = od;
+  }
+  if (tid == 0) { mypart[0] = m; mypart[1] = l; }
+  cluster_sync_all();                // every rank's partial is visible cluster-wide
+  // ---- fold the 8 splits (fixed order) ---------------------------------------------------------------------------------------
+  if (tid < kDH) {
+    float mv[kCS], lv[kCS], ov[kCS];
+#pragma unroll
+    for (int s = 0; s < kCS; ++s) {
+      mv[s] = dsmem_ld(mypart, (uint32_t)s);
+      lv[s] = dsmem_ld(mypart + 1, (uint32_t)s);
+      ov[s] = dsmem_ld(mypart + 2 + tid, (uint32_t)s);
+    }
+    float M = -INFINITY;
+#pragma unroll
+    for (int s = 0; s < kCS; ++s) M = fmaxf(M, mv[s]);
+    float L = 0.f, O = 0.f;
+#pragma unroll
+    for (int s = 0; s < kCS; ++s) {
+      const float w = (mv[s] == -INFINITY) ? 0.f : expf(mv[s] - M);
+      L += w * lv[s];
+      O += w * ov[s];
+    }
+    sq[tid] = O / L;
+  }
+  __syncthreads();
+  // ---- out-proj share: rows [r0,r1) (128 rows) x this head's 64 columns -------------------------------------------------------
+  const int grp = lane >> 3, sub = lane & 7;
+  float xv[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) xv[i] = sq[sub * 8 + i];
+  for (int pass = 0; pass * 64 < r1 - r0; ++pass) {
+    const int nrow = r0 + pass * 64 + warp * 4 + grp;
+    const bool ok = nrow < r1;
+    uint4 raw;
+    if (pass < 2) raw = wp.r[pass];
+    else raw = ok ? ldw_raw(Wo + (size_t)nrow * kD + h * kDH + sub * 8) : make_uint4(0, 0, 0, 0);
+    float w[8];
+    raw_to_f32<bf16>(&raw, 0, w);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s = fmaf(w[i], xv[i], s);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (ok && sub == 0) fix_add(accO + (size_t)b * kD + nrow, s);
+  }
+  // the partial / q|k|v slots are rewritten two grid barriers from now, long after every rank has read them
+}
+
+__global__ void __launch_bounds__(PNT, 1) ar_decode_cluster_kernel(const PParams p) {
+  using WT = bf16;
+  constexpr int MR = 1;
+  extern __shared__ __align__(16) float dsm[];
+  float* sx = dsm;                       // [1024]
+  float* hs = dsm + MR * kD;             // [kHS]
+  float* xchg = hs + MR * kHS;           // [128] cluster exchange slots (same offset in every CTA of the cluster)
+  float* scratch = xchg + 128;
+  const Batch& bt = p.bt;
+  const int B = 1;
+  const int tid = threadIdx.x;
+  unsigned int epoch = 0;
+
+  int o0, o1, f0, f1, pr0, pr1;
+  slice(kD, o0, o1);
+  slice(kFF, f0, f1);
+  slice(kARLogits, pr0, pr1);
+  const int u_h = blockIdx.x / kCS, u_split = (int)cluster_rank();   // cluster c = head c (blocks 8c .. 8c+7), rank = key split
+  const int wr0 = (u_split * kD) / kCS, wr1 = ((u_split + 1) * kD) / kCS;
+  const int qi0 = u_split * kQShare;
+  auto qmap = [&](int i) { return qkv_head_row(u_h, qi0 + i); };
+  long long* const accO2 = p.acc_out;
+  long long* const accF2 = p.acc_ffn;
+  const size_t accN = (size_t)B * kD;
+
+  WPre<WT, MR> pre;
+  WoPre wp;
+  LnPre lp;
+  gemv_issue_map<MR>(pre, reinterpret_cast<const WT*>(p.layer[0].qkv_w), kQShare, p.layer[0].qkv_b, qmap);
+  wo_issue(wp, reinterpret_cast<const WT*>(p.layer[0].out_w), u_h, wr0, wr1);
+  ln_issue(lp, p.layer[0].n1_g, p.layer[0].n1_b, nullptr);
+  for (int i = tid; i < MR * kHS; i += PNT) hs[i] = 0.f;
+
+  long long* prof = nullptr;
+  const int prof_slot = (blockIdx.x == 0) ? 0 : (blockIdx.x == gridDim.x / 2) ? 1 : (blockIdx.x == gridDim.x - 1) ? 2 : -1;
+
+  int steps = 0;
+  bool live = true;
+  for (int step = 0; step < p.max_steps && live; ++step) {
+    if (p.prof && prof_slot >= 0 && tid == 0) {
+      if (step == p.prof_step0) prof = p.prof + (size_t)prof_slot * 4096;
+      if (step == p.prof_step0 + 4) prof = nullptr;
+    }
+    if (blockIdx.x == 0 && !ld_cg(bt.finished)) sample_utterance(p, 0, scratch);
+    zero_slice(accF2 + accN, B, o0, o1);
+    grid_barrier(p.bar, epoch, prof);
+    ++steps;
+    if (!p.ignore_eos && ld_cg(bt.n_active) <= 0) break;
+    if (step == p.max_steps - 1) break;
+
+    for (int l = 0; l < kL; ++l) {
+      const PLayer& L = p.layer[l];
+      const int par = l & 1;
+      long long* accO = accO2 + par * accN;
+      long long* accF = accF2 + par * accN;
+      long long* accO_prev = accO2 + (par ^ 1) * accN;
+      long long* accF_prev = accF2 + (par ^ 1) * accN;
+      const float* fb_prev = (l > 0) ? p.layer[l - 1].ff2_b : nullptr;
+      const WT* Wq = reinterpret_cast<const WT*>(L.qkv_w);
+      const WT* Wo = reinterpret_cast<const WT*>(L.out_w);
+      const WT* W1 = reinterpret_cast<const WT*>(L.ff1_w);
+      const WT* W2T = reinterpret_cast<const WT*>(L.ff2_t);
+      // ---- PA ------------------------------------------------------------------------------------------------------
+      if (tid == 0) {
+        const int n = bt.S[0] + bt.P[0] + ld_cg(bt.T) + 1;
+        int chunk = (n + kCS - 1) / kCS;
+        chunk = (chunk + 31) & ~31;
+        const int j0 = u_split * chunk, j1 = min(n - 1, j0 + chunk);
+        if (j1 > j0) {
+          const size_t off = ((size_t)l * p.kv_layer_elems + (size_t)u_h * p.ctx_cap * kDH + (size_t)j0 * kDH) * sizeof(WT);
+          l2_prefetch(reinterpret_cast<const char*>(p.kc) + off, (size_t)(j1 - j0) * kDH * sizeof(WT));
+          l2_prefetch(reinterpret_cast<const char*>(p.vc) + off, (size_t)(j1 - j0) * kDH * sizeof(WT));
+        }
+      }
+      ln_load(lp, L.n1_g, L.n1_b, fb_prev);
+      if (l == 0) {
+        stage_ln_x<MR>(sx, B, [&](int m, int c) { return __ldcg(p.xa + (size_t)m * kD + c); }, lp, scratch, nullptr, 0, 0);
+      } else {
+        stage_ln_x<MR>(sx, B, [&](int m, int c) { return __ldcg(p.xb + (size_t)m * kD + c) + fix_get(accF_prev + (size_t)m * kD + c); },
+                       lp, scratch, p.xa, o0, o1);
+      }
+      zero_slice(accO_prev, B, o0, o1);
+      PSTAMP(3);
+      gemv_finish_map<MR>(pre, Wq, kQShare, sx, B, L.qkv_b, qmap, [&](int i, int, float v) { xchg[i] = v; });
+      PSTAMP(4);
+      gemv_issue<WT, MR>(pre, W1, kD, f0, f1, L.ff1_b, nullptr);
+      attn_unit_cluster(p, l, u_h, u_split, scratch, xchg, wp, Wo, wr0, wr1, accO);
+      ln_issue(lp, L.n2_g, L.n2_b, L.out_b);
+      if (tid == 0) l2_prefetch(W2T + (size_t)f0 * kD, (size_t)(f1 - f0) * kD * sizeof(WT));
+      PSTAMP(5);
+      grid_barrier(p.bar, epoch, prof);
+      // ---- PB ------------------------------------------------------------------------------------------------------
+      ln_load(lp, L.n2_g, L.n2_b, L.out_b);
+      stage_ln_x<MR>(sx, B, [&](int m, int c) { return __ldcg(p.xa + (size_t)m * kD + c) + fix_get(accO + (size_t)m * kD + c); },
+                     lp, scratch, p.xb, o0, o1);
+      if (l > 0) zero_slice(accF_prev, B, o0, o1);
+      PSTAMP(3);
+      gemv_finish<WT, MR>(pre, W1, kD, f0, f1, sx, B, L.ff1_b, nullptr, [&](int, int) { return 0.f; },
+                          [&](int n, int m, float v) { hs[m * kHS + (n - f0)] = fmaxf(v, 0.f); });
+      __syncthreads();
+      PSTAMP(4);
+      ffn2_share<MR>(W2T, f0, f1, hs, B, accF);
+      if (l + 1 < kL) {
+        gemv_issue_map<MR>(pre, reinterpret_cast<const WT*>(p.layer[l + 1].qkv_w), kQShare, p.layer[l + 1].qkv_b, qmap);
+        wo_issue(wp, reinterpret_cast<const WT*>(p.layer[l + 1].out_w), u_h, wr0, wr1);
+        ln_issue(lp, p.layer[l + 1].n1_g, p.layer[l + 1].n1_b, L.ff2_b);
+      } else {
+        gemv_issue<WT, MR>(pre, reinterpret_cast<const WT*>(p.predict_w), kD, pr0, pr1, nullptr, nullptr);
+        ln_issue(lp, p.norm_g, p.norm_b, L.ff2_b);
+      }
+      PSTAMP(5);
+      grid_barrier(p.bar, epoch, prof);
+    }
+    // ---- PF --------------------------------------------------------------------------------------------------------
+    ln_load(lp, p.norm_g, p.norm_b, p.layer[kL - 1].ff2_b);
+    stage_ln_x<MR>(sx, B, [&](int m, int c) { return __ldcg(p.xb + (size_t)m * kD + c) + fix_get(accF2 + accN + (size_t)m * kD + c); },
+                   lp, scratch, nullptr, 0, 0);
+    zero_slice(accO2 + accN, B, o0, o1);
+    gemv_finish<WT, MR>(pre, reinterpret_cast<const WT*>(p.predict_w), kD, pr0, pr1, sx, B, nullptr, nullptr,
+                        [&](int, int) { return 0.f; },
+                        [&](int n, int m, float v) { p.logits[(size_t)m * kARLogits + n] = v; });
+    gemv_issue_map<MR>(pre, reinterpret_cast<const WT*>(p.layer[0].qkv_w), kQShare, p.layer[0].qkv_b, qmap);
+    wo_issue(wp, reinterpret_cast<const WT*>(p.layer[0].out_w), u_h, wr0, wr1);
+    ln_issue(lp, p.layer[0].n1_g, p.layer[0].n1_b, nullptr);
+    grid_barrier(p.bar, epoch, prof);
+  }
+  if (blockIdx.x == 0 && tid == 0) *p.steps_done = steps;
+  cluster_sync_all();   // no CTA of the cluster leaves while a peer may still read its shared memory
+}
+
+static cudaError_t cluster_launch(const PParams& p, cudaStream_t st) {
+  const size_t scratch_floats = 256 + PCHUNK + (PNT / 8) * kDH;
+  const size_t sample_floats = 1032 + PSORT + PSORT / 2 + PNT + 32 + 8;
+  const size_t smem = ((size_t)kD + kHS + 128 + std::max(scratch_floats, sample_floats)) * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(ar_decode_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kH * kCS);
+  cfg.blockDim = dim3(PNT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = kCS; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+  attrs[1].id = cudaLaunchAttributeCooperative;
+  attrs[1].val.cooperative = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 2;
+  int nclusters = 0;
+  e = cudaOccupancyMaxActiveClusters(&nclusters, ar_decode_cluster_kernel, &cfg);
+  if (e != cudaSuccess) return e;
+  if (nclusters < kH) return cudaErrorLaunchOutOfResources;   // all 16 clusters must be co-resident (grid barrier)
+  return cudaLaunchKernelEx(&cfg, ar_decode_cluster_kernel, p);
+}
+
 template <int MR>
 static cudaError_t v4_launch(const PParams& p, int grid, cudaStream_t st) {
   const size_t scratch_floats = 256 + PCHUNK + (PNT / 8) * kDH;
@@ -2255,6 +2566,10 @@ int launch_decode_persistent(const void* params, int wt, int B, int grid, cudaSt
       case 16: return (int)mma_launch<16>(p, grid, st);
       default: return (int)mma_launch<32>(p, grid, st);
     }
+  }
+  if (wt == 1 && p.fused == 3) {  // experimental cluster variant (VX_DECODE_CLUSTER=1): B = 1, 16 clusters x 8 CTAs
+    if (B != 1 || p.nsplit != kCS || (kFF + kH * kCS - 1) / (kH * kCS) > kHS) return (int)cudaErrorInvalidConfiguration;
+    return (int)cluster_launch(p, st);
   }
   if (wt == 1 && p.fused == 2) {  // experimental two-barrier variant (VX_DECODE_V4=1): same preconditions as the 3-barrier one
     if (mr > 8 || B * kH * p.nsplit > grid || (kFF + grid - 1) / grid > kHS) return (int)cudaErrorInvalidConfiguration;

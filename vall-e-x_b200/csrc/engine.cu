@@ -832,8 +832,12 @@ int vx_ar_decode(vx_engine* e, int max_new, int top_k, float top_p, float temper
       pp.xb = (float*)e->p_xb.p;
       pp.acc_out = (long long*)e->p_acc.p;
       pp.acc_ffn = (long long*)e->p_acc.p + (size_t)2 * B * kD;
+      const char* cl = getenv("VX_DECODE_CLUSTER");
+      if (cl && cl[0] == '1' && B == 1 && final_ctx <= 8 * 2048) {   // experimental cluster kernel: 8 key splits = one cluster per head
+        pp.fused = 3;
+      }
       const char* v4 = getenv("VX_DECODE_V4");
-      if (v4 && v4[0] == '1' && ns <= 12) {   // experimental two-barrier kernel: flag-carrying exchange buffers, epochs restart per launch
+      if (pp.fused != 3 && v4 && v4[0] == '1' && ns <= 12) {   // experimental two-barrier kernel: flag-carrying exchange buffers, epochs restart per launch
         const size_t nq = (size_t)B * kH * 3 * kDH, np = (size_t)B * kH * ns * (kDH + 2);
         ENS(e->p_ll, (nq + np) * 8);
         CK(cudaMemsetAsync(e->p_ll.p, 0, (nq + np) * 8, st));
@@ -847,7 +851,7 @@ int vx_ar_decode(vx_engine* e, int max_new, int top_k, float top_p, float temper
     pp.kc = e->kc.p; pp.vc = e->vc.p; pp.kv_layer_elems = e->kv_layer_elems; pp.ctx_cap = e->ctx_cap;
     pp.xa = (float*)e->xs.p; pp.pf = (float*)e->p_pf.p; pp.qkv = (float*)e->qkvs.p; pp.att = (float*)e->atts.p;
     pp.hid = (float*)e->ffs.p; pp.logits = (float*)e->logits.p; pp.part = (float*)e->part.p; pp.tickets = (int32_t*)e->tick.p;
-    pp.bar = (unsigned int*)e->p_bar.p; pp.nsplit = ns;
+    pp.bar = (unsigned int*)e->p_bar.p; pp.nsplit = (pp.fused == 3) ? 8 : ns;
     pp.top_k = top_k; pp.top_p = top_p; pp.temperature = temperature; pp.seed = seed; pp.ignore_eos = ignore_eos;
     pp.forced = forced_dev; pp.forced_stride = max_steps; pp.out_tokens = (int32_t*)e->out_tok.p; pp.out_stride = max_steps;
     pp.max_steps = max_steps; pp.steps_done = (int32_t*)((char*)e->p_bar.p + 32);
