@@ -65,3 +65,16 @@ def test_cluster_decode_variant(monkeypatch, name):
     monkeypatch.setenv("VX_DECODE_CLUSTER", "1")
     m = _valle(state_dict_for(g["seed"]), "bf16", max_ctx=1024, max_batch=1)
     _teacher_forced(m, [g], [name])
+
+
+@pytest.mark.skipif(os.environ.get("VX_TEST_EXPERIMENTAL") != "1",
+                    reason="trimmed 3-barrier decode kernel: written after the round-1 GPU budget ran out, not yet run on a B200")
+@pytest.mark.parametrize("bits", [1, 2, 4, 7])
+def test_trimmed_fused_decode_variant(monkeypatch, bits):
+    """VX_DECODE_TRIM=<bits>: A/B switches on the 3-barrier kernel (1 V with K, 2 W2^T share in registers, 4 flag-carrying
+    attention partials)."""
+    names = ["tiny_en", "noprompt_en"]
+    gs = [load_golden(n) for n in names]
+    monkeypatch.setenv("VX_DECODE_TRIM", str(bits))
+    m = _valle(state_dict_for(gs[0]["seed"]), "bf16", max_ctx=1024, max_batch=2)
+    _teacher_forced(m, gs, names)

@@ -34,7 +34,8 @@ struct PParams {
   long long* acc_ffn;         // [2][B][1024] fused variant: FFN2 sums
   unsigned long long* qkv_ll; // [B][16][192] two-barrier variant: q|k|v of a head, (epoch << 32 | float bits) per element
   unsigned long long* part_ll;// [B][16][nsplit][66] two-barrier variant: attention partials, same packing
-  int fused;                  // 0: 5-barrier kernel, 1: 3-barrier kernel (default for B <= 2), 2: two-barrier kernel (VX_DECODE_V4=1), 3: cluster/DSMEM two-barrier kernel (VX_DECODE_CLUSTER=1, B = 1)
+  int trim;                   // VX_DECODE_TRIM bit mask (fused == 4)
+  int fused;                  // 0: 5-barrier kernel, 1: 3-barrier kernel (default for B <= 2), 2: two-barrier kernel (VX_DECODE_V4=1), 3: cluster/DSMEM two-barrier kernel (VX_DECODE_CLUSTER=1, B = 1), 4: trimmed 3-barrier kernel (VX_DECODE_TRIM=<bits>)
   float* part;                // [B][16][nsplit][66]
   int32_t* tickets;           // [B*16]
   unsigned int* bar;          // grid barrier counter (zeroed by the host)

@@ -832,12 +832,21 @@ int vx_ar_decode(vx_engine* e, int max_new, int top_k, float top_p, float temper
       pp.xb = (float*)e->p_xb.p;
       pp.acc_out = (long long*)e->p_acc.p;
       pp.acc_ffn = (long long*)e->p_acc.p + (size_t)2 * B * kD;
+      const char* tr = getenv("VX_DECODE_TRIM");
+      if (tr && atoi(tr) > 0 && ns <= 12) {   // experimental trimmed 3-barrier kernel (A/B switches)
+        const size_t np = (size_t)B * kH * ns * (kDH + 2);
+        ENS(e->p_ll, np * 8);
+        CK(cudaMemsetAsync(e->p_ll.p, 0, np * 8, st));
+        pp.part_ll = (unsigned long long*)e->p_ll.p;
+        pp.trim = atoi(tr);
+        pp.fused = 4;
+      }
       const char* cl = getenv("VX_DECODE_CLUSTER");
-      if (cl && cl[0] == '1' && B == 1 && final_ctx <= 8 * 2048) {   // experimental cluster kernel: 8 key splits = one cluster per head
+      if (pp.fused == 1 && cl && cl[0] == '1' && B == 1 && final_ctx <= 8 * 2048) {   // experimental cluster kernel: 8 key splits = one cluster per head
         pp.fused = 3;
       }
       const char* v4 = getenv("VX_DECODE_V4");
-      if (pp.fused != 3 && v4 && v4[0] == '1' && ns <= 12) {   // experimental two-barrier kernel: flag-carrying exchange buffers, epochs restart per launch
+      if (pp.fused == 1 && v4 && v4[0] == '1' && ns <= 12) {   // experimental two-barrier kernel: flag-carrying exchange buffers, epochs restart per launch
         const size_t nq = (size_t)B * kH * 3 * kDH, np = (size_t)B * kH * ns * (kDH + 2);
         ENS(e->p_ll, (nq + np) * 8);
         CK(cudaMemsetAsync(e->p_ll.p, 0, (nq + np) * 8, st));
