@@ -137,3 +137,69 @@ def test_long_text_fixed_prompt_batches_sentences(tmp_path, monkeypatch):
     with pytest.raises(ValueError, match="fixed-prompt"):
         generation.generate_audio_from_long_text(sents, prompt=str(tmp_path / "p.npz"), language="en",
                                                  mode="sliding-window", batch_sentences=True)
+
+
+class _FakeEngine:
+    """Stands in for vallex_b200.engine.Engine: records the batches the host layer forms; utterance b of a batch 'generates'
+    T_b = S_b frames whose codes are (b, t)-dependent."""
+    def __init__(self):
+        self.batches, self.seeds = [], []
+
+    def set_batch(self, texts, langs, prompts):
+        self.cur = (texts, langs, prompts)
+        self.batches.append([int(len(t)) for t in texts])
+
+    def ar_prefill(self):
+        pass
+
+    def timing(self):
+        return {"ms_prefill": 1.0, "ms_decode": 2.0, "ms_nar": 3.0, "decode_steps": 4, "kernel_launches": 5}
+
+    def ar_decode(self, max_new=0, top_k=-100, top_p=1.0, temperature=1.0, seed=0, **kw):
+        self.seeds.append(seed)
+        lens = np.asarray([len(t) for t in self.cur[0]], np.int32)
+        if max_new:
+            lens = np.minimum(lens, max_new)
+        self.lens = lens
+        return np.zeros((len(lens), int(lens.max())), np.int32), lens, np.zeros(len(lens), np.float32)
+
+    def nar(self, Tmax=None, **kw):
+        B = len(self.lens)
+        codes = np.zeros((B, Tmax, 8), np.int32)
+        for b in range(B):
+            codes[b, :, :] = (int(self.cur[0][b][0]) * 10 + np.arange(Tmax)[:, None]) % 1024
+        return codes
+
+
+def test_inference_batch_chunks_orders_and_lengths():
+    """VALLE.inference_batch: max_batch-sized ragged chunks, per-item outputs in input order with their own lengths,
+    per-chunk sampler seeds, the same argument checks as .inference (models/vallex.py:485-493)."""
+    m = VALLE(1024, 16, 12, norm_first=True, add_prenet=False, prefix_mode=1, share_embedding=True, nar_scale_factor=1.0,
+              prepend_bos=True, num_quantizers=8, max_batch=2)
+    fake = _FakeEngine()
+    m._engine = fake
+    S = [5, 3, 7, 4, 6]
+    items = [(torch.full((1, s), 10 + i, dtype=torch.long), torch.zeros(1, 2, 8, dtype=torch.long), 1, "en", "zh")
+             for i, s in enumerate(S)]
+    outs = m.inference_batch(items, top_k=1, seed=100, quiet=True)
+    assert fake.batches == [[5, 3], [7, 4], [6]]
+    assert fake.seeds == [100, 102, 104]
+    assert [tuple(o.shape) for o in outs] == [(1, s, 8) for s in S]
+    for i, o in enumerate(outs):
+        assert o.dtype == torch.int64
+        assert int(o[0, 0, 0]) == ((10 + i) * 10) % 1024 and int(o[0, -1, 3]) == ((10 + i) * 10 + S[i] - 1) % 1024
+    assert m.last_timing["ms_decode"] == 6.0 and m.last_timing["ms_prefill"] == 3.0     # summed over the three chunks
+    short = m.inference_batch(items[:2], top_k=1, max_new_tokens=2, quiet=True)
+    assert [tuple(o.shape) for o in short] == [(1, 2, 8), (1, 2, 8)]
+    with pytest.raises(AssertionError):
+        m.inference_batch([(torch.zeros(4, dtype=torch.long), torch.zeros(1, 2, 8), 1, "en", "en")], quiet=True)
+    with pytest.raises(AssertionError):
+        m.inference_batch([(torch.zeros(1, 4, dtype=torch.long), torch.zeros(2, 2, 8), 1, "en", "en")], quiet=True)
+    # seed=None follows torch's global generator (reproducible under torch.manual_seed, like the reference's sampling)
+    torch.manual_seed(7)
+    fake.seeds.clear()
+    m.inference_batch(items[:1], quiet=True)
+    a = fake.seeds[0]
+    torch.manual_seed(7)
+    m.inference_batch(items[:1], quiet=True)
+    assert fake.seeds[1] == a
