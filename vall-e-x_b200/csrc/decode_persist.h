@@ -54,4 +54,13 @@ struct PParams {
 // wt: 0 fp32 / 1 bf16 (weights and KV cache).  B <= 32.  Returns a cudaError_t as int.
 int launch_decode_persistent(const void* params, int wt, int B, int grid, cudaStream_t st);
 
+// launchers of the kernel variants (one translation unit each); mr = padded batch rows
+cudaError_t launch_decode_fused(const PParams& p, int mr, int grid, cudaStream_t st);     // decode_fused.cu
+cudaError_t launch_decode_fused2(const PParams& p, int mr, int grid, cudaStream_t st);    // decode_fused.cu
+cudaError_t launch_decode_v4(const PParams& p, int mr, int grid, cudaStream_t st);        // decode_exchange.cu
+cudaError_t launch_decode_cluster(const PParams& p, cudaStream_t st);                     // decode_exchange.cu
+cudaError_t launch_decode_mma(const PParams& p, int mr, int grid, cudaStream_t st);       // decode_mma.cu
+constexpr int kDecodeHS = 64;   // max hidden units per CTA of the fused kernels (kHS in decode_fused_common.cuh)
+constexpr int kDecodeCS = 8;    // cluster size of the cluster variant (kCS in decode_exchange.cu)
+
 }  // namespace vx
