@@ -14,7 +14,8 @@ AdaLayerNorm), `heads.py` (ISTFTHead), `spectral_ops.py` (ISTFT, padding="same")
 config of the `charactr/vocos-encodec-24khz` checkpoint (input 128, dim 384, intermediate 1152,
 8 layers, 4 bandwidth embeddings, n_fft 1280, hop 320).  Waveform parity of the B200 engine is
 checked against THIS restatement only; re-verify against the real package where `import vocos`
-works.  Only tests/, smoke() and bench.py's cpu_baseline leg may import this module.
+works.  One stage has an independent pin: the iSTFT (`istft_same`) is checked against `torch.istft` in
+tests/test_oracle_golden.py.  Only tests/, smoke() and bench.py's cpu_baseline leg may import this module.
 """
 from __future__ import annotations
 
@@ -79,7 +80,13 @@ class OracleVocos:
         mag, p = x.chunk(2, dim=1)
         mag = torch.clip(torch.exp(mag), max=1e2)
         S = mag * (torch.cos(p) + 1j * torch.sin(p))
-        window = sd["head.istft.window"]
+        return self.istft_same(S)
+
+    @torch.no_grad()
+    def istft_same(self, S: torch.Tensor) -> torch.Tensor:
+        """vocos spectral_ops.py `ISTFT.forward`, padding='same': complex [B,641,T] -> [B, 320*T].  (Pinned on its own by
+        tests/test_oracle_golden.py against torch.istft, which differs only in how much it trims from both ends.)"""
+        window = self.sd["head.istft.window"]
         pad = (N_FFT - HOP) // 2
         B, N, T = S.shape
         ifft = torch.fft.irfft(S, N_FFT, dim=1, norm="backward") * window[None, :, None]

@@ -86,3 +86,23 @@ def test_oracle_live_against_reference():
     # the synthetic checkpoint has exactly the reference's key set / shapes (strict load above) and its
     # tied tensors stay tied
     assert set(ref.state_dict().keys()) == set(sd.keys())
+
+
+def test_vocos_oracle_istft_against_torch_istft():
+    """The iSTFT of the Vocos restatement (V4, 'same' padding: trim (n_fft - hop)/2 = 480 per side) against torch's own
+    istft (center=True: trims n_fft/2 = 640 per side): identical overlap-add and window-envelope normalisation, so
+    torch.istft(S) == oracle(S)[160 : 160 + hop*(T-1)].  An independent pin for that part of the unpinned oracle."""
+    import torch
+    from oracle.vocos_oracle import HOP, N_FFT, OracleVocos
+    from vallex_b200.weights import synthetic_vocos_state_dict
+    ov = OracleVocos(synthetic_vocos_state_dict(0))
+    g = torch.Generator().manual_seed(3)
+    for B, T in ((1, 9), (2, 40)):
+        S = torch.complex(torch.randn(B, N_FFT // 2 + 1, T, generator=g), torch.randn(B, N_FFT // 2 + 1, T, generator=g))
+        S[:, 0].imag.zero_()
+        S[:, -1].imag.zero_()          # DC and Nyquist bins of a real signal are real (irfft ignores their imaginary part)
+        mine = ov.istft_same(S)
+        ref = torch.istft(S, n_fft=N_FFT, hop_length=HOP, win_length=N_FFT, window=ov.sd["head.istft.window"], center=True)
+        assert mine.shape == (B, HOP * T) and ref.shape == (B, HOP * (T - 1))
+        off = (N_FFT // 2) - (N_FFT - HOP) // 2
+        torch.testing.assert_close(mine[:, off:off + ref.shape[1]], ref, rtol=1e-4, atol=1e-4)
