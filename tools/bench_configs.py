@@ -81,7 +81,7 @@ def main():
                           "ms_prefill": t["ms_prefill"], "us_per_step": t_step * 1e6, "ar_tokens_per_s": B / t_step,
                           "mean_ctx": float(Lmean.mean()), "bytes_per_step": bytes_step,
                           "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "peak_source": how},
-                          "lens_ok": bool((lens == min(a.steps, 16 * int(S.min()))).all() or True)}))
+                          "lens_ok": bool((lens == np.minimum(a.steps, 16 * S)).all())}))
     elif a.config == 5:
         from vallex_b200 import generation as g
         from vallex_b200.vallex import VALLE
