@@ -78,3 +78,14 @@ def test_trimmed_fused_decode_variant(monkeypatch, bits):
     monkeypatch.setenv("VX_DECODE_TRIM", str(bits))
     m = _valle(state_dict_for(gs[0]["seed"]), "bf16", max_ctx=1024, max_batch=2)
     _teacher_forced(m, gs, names)
+
+
+@pytest.mark.skipif(os.environ.get("VX_TEST_EXPERIMENTAL") != "1",
+                    reason="pipelined P.V loads in the batched kernel's attention phase: not yet run on a B200")
+@pytest.mark.parametrize("B", [8, 32])
+def test_tensor_core_batched_decode_pipelined_attention(monkeypatch, B):
+    names = (["tiny_en", "noprompt_en"] * 16)[:B]
+    gs = [load_golden(n) for n in names]
+    monkeypatch.setenv("VX_DECODE_MMA", "2")
+    m = _valle(state_dict_for(gs[0]["seed"]), "bf16", max_ctx=512, max_batch=B)
+    _teacher_forced(m, gs, names)

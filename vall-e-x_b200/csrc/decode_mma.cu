@@ -147,7 +147,123 @@ __device__ __forceinline__ void gemv_finish_mma(const MPre& pre, const uint16_t*
   __syncthreads();
 }
 
-template <int MR>
+// attention unit of the batched kernel with a pipelined P.V loop (PIPE = true; VX_DECODE_MMA=2).  Same arithmetic and
+// summation order as attn_unit<bf16>: a lane still walks its keys in increasing order, only the loads are issued ahead.
+__device__ void attn_unit_pipe(const PParams& p, int layer, int b, int h, int split, float* smem) {
+  float* sq = smem;                  // [64]
+  float* sknew = smem + 64;          // [64]
+  float* svnew = smem + 128;         // [64]
+  float* red = smem + 192;           // [32]
+  int* s_last = reinterpret_cast<int*>(smem + 224);
+  float* sp = smem + 256;            // [PCHUNK]
+  float* sacc = sp + PCHUNK;         // [PNT/8][64]
+  const Batch& bt = p.bt;
+  const int tid = threadIdx.x;
+  const int pos = bt.S[b] + bt.P[b] + ld_cg(bt.T + b);
+  const int n = pos + 1;
+  int chunk = (n + p.nsplit - 1) / p.nsplit;
+  chunk = (chunk + 31) & ~31;
+  const int j0 = split * chunk, j1 = min(n, j0 + chunk);
+  const float* row = p.qkv + (size_t)b * (3 * kD) + h * kDH;
+  __syncthreads();  // smem reuse across units
+  if (tid < kDH) {
+    sq[tid] = __ldcg(row + tid) * 0.125f;
+    sknew[tid] = __ldcg(row + kD + tid);
+    svnew[tid] = __ldcg(row + 2 * kD + tid);
+  }
+  __syncthreads();
+  bf16* kb = reinterpret_cast<bf16*>(p.kc) + (size_t)layer * p.kv_layer_elems + ((size_t)b * kH + h) * p.ctx_cap * kDH;
+  bf16* vb = reinterpret_cast<bf16*>(p.vc) + (size_t)layer * p.kv_layer_elems + ((size_t)b * kH + h) * p.ctx_cap * kDH;
+  if (split == 0 && tid < kDH) {
+    store_as(kb + (size_t)pos * kDH + tid, sknew[tid]);
+    store_as(vb + (size_t)pos * kDH + tid, svnew[tid]);
+  }
+  float mloc = -INFINITY;
+  for (int j = j0 + tid; j < j1; j += PNT) {
+    float s = 0.f;
+    if (j == pos) {
+#pragma unroll
+      for (int d = 0; d < kDH; ++d) s = fmaf(sq[d], kv_round<bf16>(sknew[d]), s);
+    } else {
+      const bf16* kr = kb + (size_t)j * kDH;
+#pragma unroll
+      for (int d = 0; d < kDH; d += 8) {
+        float w[8];
+        ldkv8(kr + d, w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s = fmaf(sq[d + i], w[i], s);
+      }
+    }
+    sp[j - j0] = s;
+    mloc = fmaxf(mloc, s);
+  }
+  const float m = block_max(mloc, red);
+  float lloc = 0.f;
+  for (int j = j0 + tid; j < j1; j += PNT) {
+    const float pr = expf(sp[j - j0] - m);
+    sp[j - j0] = pr;
+    lloc += pr;
+  }
+  const float l = block_sum(lloc, red);
+  constexpr int NG = PNT / 8;
+  const int g = tid >> 3, dc = (tid & 7) * 8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // P.V with 8 value chunks in flight per lane (a batched unit holds ALL keys of its head: ~20 keys per lane group; one
+  // load per loop trip would put 20 dependent memory round trips on the critical path)
+  constexpr int UV = 8;
+  for (int jb = j0 + g; jb < j1; jb += NG * UV) {
+    uint4 raw[UV];
+    float prs[UV];
+#pragma unroll
+    for (int u = 0; u < UV; ++u) {
+      const int j = jb + u * NG;
+      const bool ok = j < j1;
+      raw[u] = (ok && j != pos) ? __ldcg(reinterpret_cast<const uint4*>(vb + (size_t)j * kDH + dc)) : make_uint4(0, 0, 0, 0);
+      prs[u] = ok ? sp[j - j0] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < UV; ++u) {
+      const int j = jb + u * NG;
+      float w[8];
+      if (j == pos) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = kv_round<bf16>(svnew[dc + i]);
+      } else {
+        raw_to_f32<bf16>(&raw[u], 0, w);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(prs[u], w[i], acc[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sacc[g * kDH + dc + i] = acc[i];
+  __syncthreads();
+  float od = 0.f;
+  if (tid < kDH) {
+    for (int q = 0; q < NG; ++q) od += sacc[q * kDH + tid];
+  }
+  // partial (m, l, o[64]) of this split.  The LAST split of (b, h) to arrive (ticket) folds all of them in fixed split
+  // order -- deterministic whoever is last -- into att[b][h*64 ..], so the out-proj phase stages 4 KB per utterance
+  // instead of every CTA gathering all partials.
+  float* pp = p.part + (((size_t)b * kH + h) * p.nsplit + split) * (kDH + 2);
+  if (tid < kDH) pp[2 + tid] = od;
+  if (tid == 0) { pp[0] = m; pp[1] = l; }
+  if (p.dbg & 2) return;   // bisecting aid: the out-proj phase folds the splits itself
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();       // the CTA's partial is visible device-wide before the ticket is taken
+    *s_last = (atomicAdd(p.tickets + b * kH + h, 1) == p.nsplit - 1);
+  }
+  __syncthreads();
+  if (*s_last) {
+    __threadfence();
+    if (tid < kDH) p.att[(size_t)b * kD + h * kDH + tid] = att_combined(p, b, h * kDH + tid);
+    if (tid == 0) p.tickets[b * kH + h] = 0;   // next use is behind a grid barrier
+  }
+}
+
+
+template <int MR, bool PIPE>
 __global__ void __launch_bounds__(PNT, 1) ar_decode_mma_kernel(const PParams p) {
   using WT = bf16;
   extern __shared__ __align__(16) float dsm[];
@@ -233,7 +349,8 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_mma_kernel(const PParams p) 
         const int split = u % p.nsplit, bh = u / p.nsplit;
         const int b = bh / kH, h = bh % kH;
         if (ld_cg(bt.finished + b)) continue;
-        attn_unit<bf16>(p, l, b, h, split, scratch);
+        if constexpr (PIPE) attn_unit_pipe(p, l, b, h, split, scratch);
+        else attn_unit<bf16>(p, l, b, h, split, scratch);
       }
       grid_barrier(p.bar, epoch, prof);
       // ---- P3: out-proj + residual -> xa ---------------------------------------------------------------------------------
@@ -286,30 +403,38 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_mma_kernel(const PParams p) 
   if (blockIdx.x == 0 && tid == 0) *p.steps_done = steps;
 }
 
-template <int MR>
+template <int MR, bool PIPE>
 static cudaError_t mma_launch(const PParams& p, int grid, cudaStream_t st) {
   const size_t scratch_floats = 256 + PCHUNK + (PNT / 8) * kDH;
   const size_t sample_floats = 1032 + PSORT + PSORT / 2 + PNT + 32 + 8;
   const size_t red_floats = (size_t)8 * 32 * MR;
   const size_t smem = ((size_t)MR * kD + std::max(std::max(scratch_floats, sample_floats), red_floats)) * sizeof(float);
-  cudaError_t e = cudaFuncSetAttribute(ar_decode_mma_kernel<MR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(ar_decode_mma_kernel<MR, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ar_decode_mma_kernel<MR>, PNT, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ar_decode_mma_kernel<MR, PIPE>, PNT, smem);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) return cudaErrorLaunchOutOfResources;
   void* args[] = {(void*)&p};
-  return cudaLaunchCooperativeKernel((void*)ar_decode_mma_kernel<MR>, dim3(grid), dim3(PNT), args, smem, st);
+  return cudaLaunchCooperativeKernel((void*)ar_decode_mma_kernel<MR, PIPE>, dim3(grid), dim3(PNT), args, smem, st);
 }
 
 
 }  // namespace
 
 cudaError_t launch_decode_mma(const PParams& p, int mr, int grid, cudaStream_t st) {
+  const char* env = getenv("VX_DECODE_MMA");
+  if (env && env[0] == '2') {   // experimental: pipelined P.V loads in the attention phase
+    switch (mr) {
+      case 8: return mma_launch<8, true>(p, grid, st);
+      case 16: return mma_launch<16, true>(p, grid, st);
+      default: return mma_launch<32, true>(p, grid, st);
+    }
+  }
   switch (mr) {
-    case 8: return mma_launch<8>(p, grid, st);
-    case 16: return mma_launch<16>(p, grid, st);
-    default: return mma_launch<32>(p, grid, st);
+    case 8: return mma_launch<8, false>(p, grid, st);
+    case 16: return mma_launch<16, false>(p, grid, st);
+    default: return mma_launch<32, false>(p, grid, st);
   }
 }
 
