@@ -69,10 +69,10 @@ def test_cluster_decode_variant(monkeypatch, name):
 
 @pytest.mark.skipif(os.environ.get("VX_TEST_EXPERIMENTAL") != "1",
                     reason="trimmed 3-barrier decode kernel: written after the round-1 GPU budget ran out, not yet run on a B200")
-@pytest.mark.parametrize("bits", [1, 2, 4, 7])
+@pytest.mark.parametrize("bits", [1, 2, 4, 8, 15])
 def test_trimmed_fused_decode_variant(monkeypatch, bits):
     """VX_DECODE_TRIM=<bits>: A/B switches on the 3-barrier kernel (1 V with K, 2 W2^T share in registers, 4 flag-carrying
-    attention partials)."""
+    attention partials, 8 one-pass LayerNorm statistics)."""
     names = ["tiny_en", "noprompt_en"]
     gs = [load_golden(n) for n in names]
     monkeypatch.setenv("VX_DECODE_TRIM", str(bits))

@@ -153,11 +153,59 @@ static cudaError_t fused_launch(const PParams& p, int grid, cudaStream_t st) {
   return cudaLaunchCooperativeKernel((void*)ar_decode_fused_kernel<MR>, dim3(grid), dim3(PNT), args, smem, st);
 }
 
+// one-pass LayerNorm staging (trim bit 8): sum and sum of squares in ONE block reduction (one __syncthreads less per
+// staging than the two-pass form; variance = E[x^2] - mean^2, clamped at 0)
+template <int MR, typename Val>
+__device__ __forceinline__ void stage_ln_x1(float* sx, int B, Val value, const LnPre& lp, float* red, float* xout, int c0, int c1) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int R = MR < 8 ? MR : 8;
+  for (int mb = 0; mb < B; mb += R) {
+    const int nb = min(R, B - mb);
+    float v0[R], v1[R];
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+      v0[m] = (m < nb) ? value(mb + m, tid) + lp.f0 : 0.f;
+      v1[m] = (m < nb) ? value(mb + m, tid + PNT) + lp.f1 : 0.f;
+    }
+    if (xout) {
+#pragma unroll
+      for (int m = 0; m < R; ++m) {
+        if (m < nb) {
+          if (tid >= c0 && tid < c1) xout[(size_t)(mb + m) * kD + tid] = v0[m];
+          if (tid + PNT >= c0 && tid + PNT < c1) xout[(size_t)(mb + m) * kD + tid + PNT] = v1[m];
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+      const float s1 = warp_sum(v0[m] + v1[m]);
+      const float s2 = warp_sum(v0[m] * v0[m] + v1[m] * v1[m]);
+      if (lane == 0) { red[warp * 8 + m] = s1; red[PNW * 8 + warp * 8 + m] = s2; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+      if (m < nb) {
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < PNW; ++w) { s1 += red[w * 8 + m]; s2 += red[PNW * 8 + w * 8 + m]; }
+        const float mean = s1 / (float)kD;
+        const float var = fmaxf(s2 / (float)kD - mean * mean, 0.f);
+        const float rstd = 1.0f / sqrtf(var + 1e-5f);
+        sx[(mb + m) * kD + tid] = __fadd_rn(__fmul_rn((v0[m] - mean) * rstd, lp.g0), lp.b0);
+        sx[(mb + m) * kD + tid + PNT] = __fadd_rn(__fmul_rn((v1[m] - mean) * rstd, lp.g1), lp.b1);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // =================================================================================================================
 // Trimmed 3-barrier variant (VX_DECODE_TRIM=<bits>, experimental A/B switches on top of ar_decode_fused_kernel):
 //   1  V chunks of the attention unit requested together with the K rows (one memory round trip less)
 //   2  the CTA's W2^T share prefetched into registers at the start of the FFN phase
 //   4  attention partials exchanged through flag-carrying stores instead of fence + ticket + spin + reload
+//   8  one-pass LayerNorm statistics (one block reduction per staging instead of two)
 // =================================================================================================================
 __device__ void attn_unit_fused2(const PParams& p, int layer, int b, int h, int split, float* smem, int& att_epoch, uint32_t ll_epoch,
                                 const WoPre& wp, const bf16* __restrict__ Wo, int r0, int r1, long long* accO) {
@@ -473,10 +521,19 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_fused2_kernel(const PParams 
       }
       ln_load(lp, L.n1_g, L.n1_b, fb_prev);
       if (l == 0) {
-        stage_ln_x<MR>(sx, B, [&](int m, int c) { return __ldcg(p.xa + (size_t)m * kD + c); }, lp, scratch, nullptr, 0, 0);
+        if (p.trim & 8) {
+          stage_ln_x1<MR>(sx, B, [&](int m, int c) { return __ldcg(p.xa + (size_t)m * kD + c); }, lp, scratch, nullptr, 0, 0);
+        } else {
+          stage_ln_x<MR>(sx, B, [&](int m, int c) { return __ldcg(p.xa + (size_t)m * kD + c); }, lp, scratch, nullptr, 0, 0);
+        }
       } else {
-        stage_ln_x<MR>(sx, B, [&](int m, int c) { return __ldcg(p.xb + (size_t)m * kD + c) + fix_get(accF_prev + (size_t)m * kD + c); },
-                       lp, scratch, p.xa, o0, o1);
+        if (p.trim & 8) {
+          stage_ln_x1<MR>(sx, B, [&](int m, int c) { return __ldcg(p.xb + (size_t)m * kD + c) + fix_get(accF_prev + (size_t)m * kD + c); },
+                         lp, scratch, p.xa, o0, o1);
+        } else {
+          stage_ln_x<MR>(sx, B, [&](int m, int c) { return __ldcg(p.xb + (size_t)m * kD + c) + fix_get(accF_prev + (size_t)m * kD + c); },
+                         lp, scratch, p.xa, o0, o1);
+        }
         zero_slice(accO_prev, B, o0, o1);   // consumed by P3 of layer l-1
       }
       PSTAMP(3);
@@ -497,8 +554,13 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_fused2_kernel(const PParams 
       // ---- P3: xmid_l = x_l + out-proj (+bias); LN2; FFN1 rows + ReLU; FFN2 share --------------------------------------
       if (p.trim & 2) ffn2_issue(wp2, W2T, f0, f1);   // trim bit 2: the W2^T share rides under staging + LN2 + FFN1
       ln_load(lp, L.n2_g, L.n2_b, L.out_b);
-      stage_ln_x<MR>(sx, B, [&](int m, int c) { return __ldcg(p.xa + (size_t)m * kD + c) + fix_get(accO + (size_t)m * kD + c); },
-                     lp, scratch, p.xb, o0, o1);
+      if (p.trim & 8) {
+        stage_ln_x1<MR>(sx, B, [&](int m, int c) { return __ldcg(p.xa + (size_t)m * kD + c) + fix_get(accO + (size_t)m * kD + c); },
+                       lp, scratch, p.xb, o0, o1);
+      } else {
+        stage_ln_x<MR>(sx, B, [&](int m, int c) { return __ldcg(p.xa + (size_t)m * kD + c) + fix_get(accO + (size_t)m * kD + c); },
+                       lp, scratch, p.xb, o0, o1);
+      }
       PSTAMP(3);
       gemv_finish<WT, MR>(pre, W1, kD, f0, f1, sx, B, L.ff1_b, nullptr, [&](int, int) { return 0.f; },
                           [&](int n, int m, float v) { hs[m * kHS + (n - f0)] = fmaxf(v, 0.f); });
@@ -518,8 +580,13 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_fused2_kernel(const PParams 
     }
     // ---- PF: x_12 = xmid_11 + FFN2_11 (+bias); final LayerNorm; predict rows -> logits -----------------------------
     ln_load(lp, p.norm_g, p.norm_b, p.layer[kL - 1].ff2_b);
-    stage_ln_x<MR>(sx, B, [&](int m, int c) { return __ldcg(p.xb + (size_t)m * kD + c) + fix_get(accF2 + accN + (size_t)m * kD + c); },
-                   lp, scratch, nullptr, 0, 0);
+    if (p.trim & 8) {
+      stage_ln_x1<MR>(sx, B, [&](int m, int c) { return __ldcg(p.xb + (size_t)m * kD + c) + fix_get(accF2 + accN + (size_t)m * kD + c); },
+                     lp, scratch, nullptr, 0, 0);
+    } else {
+      stage_ln_x<MR>(sx, B, [&](int m, int c) { return __ldcg(p.xb + (size_t)m * kD + c) + fix_get(accF2 + accN + (size_t)m * kD + c); },
+                     lp, scratch, nullptr, 0, 0);
+    }
     zero_slice(accO2 + accN, B, o0, o1);   // acc_out[1] was consumed by P3 of layer 11
     gemv_finish<WT, MR>(pre, reinterpret_cast<const WT*>(p.predict_w), kD, pr0, pr1, sx, B, nullptr, nullptr,
                         [&](int, int) { return 0.f; },
