@@ -48,10 +48,11 @@ for c in range(3):
         prev = (tag, clk)
     tot = sum(np.sum(v) for v in seg.values()) / 4.0
     print(f"CTA slot {c}: {len(ev)} stamps, {tot:.1f} us/step accounted")
-    if c == 0:
+    if c == 0 or os.environ.get("VX_TIMELINE_ALL") == "1":   # VX_TIMELINE_ALL=1: CTAs grid/2 and grid-1 too (skew between CTAs)
         agg = collections.defaultdict(list)
         for (nm, k), v in seg.items():
             agg[(nm, k)] += v
         for nm in ("S0",) + per_layer + ("PF",):
             parts = "  ".join(f"{k}:{np.mean(v):5.2f}" for (n2, k), v in sorted(agg.items()) if n2 == nm)
-            print(f"  {nm:5s} {parts}")
+            tot_nm = sum(np.mean(v) for (n2, k), v in agg.items() if n2 == nm)
+            print(f"  {nm:5s} {parts}   | {tot_nm:5.2f} us per phase")
