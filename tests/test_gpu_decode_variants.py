@@ -1,4 +1,5 @@
-"""GPU tests of the decode-kernel variants beyond the default batch-1 kernel (all run green on a B200 in round 1):
+"""GPU tests of the decode-kernel variants beyond the default batch-1 kernel.  The batched tensor-core kernel is a product
+path (default for 8 <= B <= 32) and always tested; the opt-in experiments need VX_TEST_EXPERIMENTAL=1:
 
   VX_DECODE_V4=1  : two-barrier persistent decode kernel (q/k/v and attention partials exchanged inside a head group
                     through flag-carrying stores) -- correct but not faster than the default 3-barrier kernel, opt-in
@@ -37,6 +38,8 @@ def _teacher_forced(m, gs, names):
     eng.close()
 
 
+@pytest.mark.skipif(os.environ.get("VX_TEST_EXPERIMENTAL") != "1",
+                    reason="opt-in kernel, not a product path (ran green on a B200 in round 1); set VX_TEST_EXPERIMENTAL=1")
 @pytest.mark.parametrize("names", [["tiny_en"], ["mid_ja"], ["tiny_en", "noprompt_en"]])
 def test_two_barrier_decode_variant(monkeypatch, names):
     gs = [load_golden(n) for n in names]
