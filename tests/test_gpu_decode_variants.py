@@ -92,3 +92,15 @@ def test_tensor_core_batched_decode_pipelined_attention(monkeypatch, B):
     monkeypatch.setenv("VX_DECODE_MMA", "2")
     m = _valle(state_dict_for(gs[0]["seed"]), "bf16", max_ctx=512, max_batch=B)
     _teacher_forced(m, gs, names)
+
+
+@pytest.mark.skipif(os.environ.get("VX_TEST_EXPERIMENTAL") != "1",
+                    reason="TMA-staged-weights decode kernel: written after the round-1 GPU budget ran out, not yet run on a B200")
+@pytest.mark.parametrize("names", [["tiny_en"], ["mid_ja"], ["tiny_en", "noprompt_en"]])
+def test_tma_staged_decode_variant(monkeypatch, names):
+    """VX_DECODE_TMA=1: the 3-barrier kernel with every weight slice copied by the TMA engine into its own shared-memory slot
+    one layer ahead of its use."""
+    gs = [load_golden(n) for n in names]
+    monkeypatch.setenv("VX_DECODE_TMA", "1")
+    m = _valle(state_dict_for(gs[0]["seed"]), "bf16", max_ctx=1024, max_batch=len(gs))
+    _teacher_forced(m, gs, names)

@@ -513,6 +513,10 @@ int launch_decode_persistent(const void* params, int wt, int B, int grid, cudaSt
   if (wt == 1 && mr >= 8 && grid >= 128 && !(mma_env && mma_env[0] == '0')) {
     return (int)launch_decode_mma(p, mr, grid, st);
   }
+  if (wt == 1 && p.fused == 5) {  // experimental: 3-barrier kernel with TMA-staged weights (VX_DECODE_TMA=1)
+    if (B * kH * p.nsplit > grid || (kFF + grid - 1) / grid > kDecodeHS) return (int)cudaErrorInvalidConfiguration;
+    return (int)launch_decode_tma(p, mr, grid, st);
+  }
   if (wt == 1 && p.fused == 4) {  // experimental trimmed 3-barrier variant (VX_DECODE_TRIM=<bits>)
     if (mr > 8 || B * kH * p.nsplit > grid || (kFF + grid - 1) / grid > kDecodeHS || p.nsplit > 12) return (int)cudaErrorInvalidConfiguration;
     return (int)launch_decode_fused2(p, mr, grid, st);

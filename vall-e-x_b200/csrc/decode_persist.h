@@ -35,7 +35,7 @@ struct PParams {
   unsigned long long* qkv_ll; // [B][16][192] two-barrier variant: q|k|v of a head, (epoch << 32 | float bits) per element
   unsigned long long* part_ll;// [B][16][nsplit][66] two-barrier variant: attention partials, same packing
   int trim;                   // VX_DECODE_TRIM bit mask (fused == 4)
-  int fused;                  // 0: 5-barrier kernel, 1: 3-barrier kernel (default for B <= 2), 2: two-barrier kernel (VX_DECODE_V4=1), 3: cluster/DSMEM two-barrier kernel (VX_DECODE_CLUSTER=1, B = 1), 4: trimmed 3-barrier kernel (VX_DECODE_TRIM=<bits>)
+  int fused;                  // 0: 5-barrier kernel, 1: 3-barrier kernel (default for B <= 2), 2: two-barrier kernel (VX_DECODE_V4=1), 3: cluster/DSMEM two-barrier kernel (VX_DECODE_CLUSTER=1, B = 1), 4: trimmed 3-barrier kernel (VX_DECODE_TRIM=<bits>), 5: 3-barrier kernel with TMA-staged weights (VX_DECODE_TMA=1)
   float* part;                // [B][16][nsplit][66]
   int32_t* tickets;           // [B*16]
   unsigned int* bar;          // grid barrier counter (zeroed by the host)
@@ -60,6 +60,7 @@ cudaError_t launch_decode_fused2(const PParams& p, int mr, int grid, cudaStream_
 cudaError_t launch_decode_v4(const PParams& p, int mr, int grid, cudaStream_t st);        // decode_exchange.cu
 cudaError_t launch_decode_cluster(const PParams& p, cudaStream_t st);                     // decode_exchange.cu
 cudaError_t launch_decode_mma(const PParams& p, int mr, int grid, cudaStream_t st);       // decode_mma.cu
+cudaError_t launch_decode_tma(const PParams& p, int mr, int grid, cudaStream_t st);       // decode_tma.cu
 constexpr int kDecodeHS = 64;   // max hidden units per CTA of the fused kernels (kHS in decode_fused_common.cuh)
 constexpr int kDecodeCS = 8;    // cluster size of the cluster variant (kCS in decode_exchange.cu)
 

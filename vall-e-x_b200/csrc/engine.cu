@@ -832,8 +832,10 @@ int vx_ar_decode(vx_engine* e, int max_new, int top_k, float top_p, float temper
       pp.xb = (float*)e->p_xb.p;
       pp.acc_out = (long long*)e->p_acc.p;
       pp.acc_ffn = (long long*)e->p_acc.p + (size_t)2 * B * kD;
+      const char* tm = getenv("VX_DECODE_TMA");
+      if (tm && tm[0] == '1' && B <= 2) pp.fused = 5;   // experimental: weights staged by the TMA engine, one layer ahead
       const char* tr = getenv("VX_DECODE_TRIM");
-      if (tr && atoi(tr) > 0 && ns <= 12) {   // experimental trimmed 3-barrier kernel (A/B switches)
+      if (pp.fused == 1 && tr && atoi(tr) > 0 && ns <= 12) {   // experimental trimmed 3-barrier kernel (A/B switches)
         const size_t np = (size_t)B * kH * ns * (kDH + 2);
         ENS(e->p_ll, np * 8);
         CK(cudaMemsetAsync(e->p_ll.p, 0, np * 8, st));
