@@ -343,7 +343,7 @@ def main():
                      "traffic_note": (None if traffic is None else f"per decode step, {traffic['capture']} ({traffic['source']}), kernel {traffic['kernel']}; algorithmic at that context: {traffic['algorithmic_bytes_per_step']:.0f} B"),
                      "peak_source": how, "bytes_per_step": bytes_step, "avg_step_us": t_step * 1e6, "mean_ctx": L_mean},
     }
-    if not a.no_cpu_baseline:
+    if not a.no_cpu_baseline and world == 1:   # the CPU baseline leg is timed on rank 0 at N=1 only
         out["cpu_baseline"] = cpu_reference_sample(a.cpu_sample_tokens)
     print(json.dumps(out), flush=True)
     if world > 1:
