@@ -22,6 +22,8 @@
 #include "kernels.h"
 #include "tc_common.cuh"
 
+#include <cstdlib>
+
 namespace vx {
 using namespace tc;
 
@@ -76,6 +78,9 @@ __device__ __forceinline__ uint32_t t5_pack(float a, float b) {  // cvt.rn.bf16x
 // 256 threads: warps 0-3 own rows 0..127 x key columns [0,32) of every 64-key tile, warps 4-7 the same rows x [32,64).
 // S is double-buffered in TMEM so the MMA of tile j+1 runs under the softmax of tile j; P is double-buffered in shared
 // memory so O += P_j V_j runs under the softmax of tile j+1.
+// MAXONLY (VX_ATTN_T5=2, experimental): pass 1 tracks only the row maximum (no exponentials), pass 2 accumulates the row sum
+// while it forms P = exp2(S - m) and the epilogue scales O by 1/l -- half the MUFU work of the statistics pass.
+template <bool MAXONLY>
 __global__ void __launch_bounds__(256, 2) attn_t5_kernel(Batch bt, const uint8_t* __restrict__ q_img,
                                                          const uint8_t* __restrict__ k_img,
                                                          const uint8_t* __restrict__ vt_img, int64_t R,
@@ -196,7 +201,9 @@ __global__ void __launch_bounds__(256, 2) attn_t5_kernel(Batch bt, const uint8_t
       }
     }
     const float m_new = fmaxf(m_run, mx * sl2);
-    if (m_new != -INFINITY) {
+    if constexpr (MAXONLY) {
+      m_run = m_new;
+    } else if (m_new != -INFINITY) {
       float s = 0.f;
 #pragma unroll
       for (int i = 0; i < 32; ++i) s += t5_ex2(fmaf(v[i], sl2, -m_new));
@@ -216,7 +223,8 @@ __global__ void __launch_bounds__(256, 2) attn_t5_kernel(Batch bt, const uint8_t
     m_run = m;
     l_run = l;
   }
-  const float inv_l = 1.0f / l_run;
+  const float inv_l = MAXONLY ? 1.0f : 1.0f / l_run;
+  float l_acc = 0.f;   // MAXONLY: row sum of this thread's column half, accumulated in pass 2
   // ---------------- pass 2: P = exp2(S - m) / l, O += P V ---------------------------------------------------------
   if (tid == 0) {
     for (int j = 0; j < 3 && j < nkt; ++j) issue_k(j);
@@ -238,13 +246,17 @@ __global__ void __launch_bounds__(256, 2) attn_t5_kernel(Batch bt, const uint8_t
     uint32_t pk[16];
     if (tile_full(j)) {
 #pragma unroll
-      for (int i = 0; i < 32; i += 2)
-        pk[i >> 1] = t5_pack(t5_ex2(fmaf(v[i], sl2, -m_run)) * inv_l, t5_ex2(fmaf(v[i + 1], sl2, -m_run)) * inv_l);
+      for (int i = 0; i < 32; i += 2) {
+        const float p0 = t5_ex2(fmaf(v[i], sl2, -m_run)) * inv_l, p1 = t5_ex2(fmaf(v[i + 1], sl2, -m_run)) * inv_l;
+        if constexpr (MAXONLY) l_acc += p0 + p1;
+        pk[i >> 1] = t5_pack(p0, p1);
+      }
     } else {
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
         const float p0 = visible(kb + i) ? t5_ex2(fmaf(v[i], sl2, -m_run)) * inv_l : 0.f;
         const float p1 = visible(kb + i + 1) ? t5_ex2(fmaf(v[i + 1], sl2, -m_run)) * inv_l : 0.f;
+        if constexpr (MAXONLY) l_acc += p0 + p1;
         pk[i >> 1] = t5_pack(p0, p1);
       }
     }
@@ -270,10 +282,22 @@ __global__ void __launch_bounds__(256, 2) attn_t5_kernel(Batch bt, const uint8_t
   }
   for (int j = max(nkt - 2, 0); j < nkt; ++j) wait_pv(j & 1);  // the last two P V products
   tc_fence_after();
-  // ---------------- epilogue: O (already normalised) -> bf16 tile image ---------------------------------------------
+  // ---------------- epilogue: O (already normalised unless MAXONLY) -> bf16 tile image ------------------------------------
+  float o_scale = 1.0f;
+  if constexpr (MAXONLY) {   // row sum = the two column halves together
+    __syncthreads();
+    sstat[tid] = make_float2(l_acc, 0.f);
+    __syncthreads();
+    const float l = l_acc + sstat[tid ^ 128].x;
+    o_scale = (l > 0.f) ? 1.0f / l : 0.f;
+  }
   {
     float v[32];
     tmem_ld32(tO + lane_addr + half * 32, v);
+    if constexpr (MAXONLY) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] *= o_scale;
+    }
     if (qi < len) {
       const int64_t grow = r0 + qi;
       uint8_t* slot = out_img + tile_image_offset(grow, h * kDH, kD) - (((int)(grow & 7)) << 4);  // start of the 128-byte row slot
@@ -299,12 +323,20 @@ void launch_attn_t5(const Batch& bt, const void* q_img, const void* k_img, const
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_done[dev & 63]) {
-    cudaFuncSetAttribute(attn_t5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_BYTES);
+    cudaFuncSetAttribute(attn_t5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_BYTES);
+    cudaFuncSetAttribute(attn_t5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_BYTES);
     attr_done[dev & 63] = true;
   }
-  attn_t5_kernel<<<dim3((max_len + 127) / 128, kH, bt.B), 256, T5_BYTES, st>>>(bt, (const uint8_t*)q_img, (const uint8_t*)k_img,
+  const char* env = getenv("VX_ATTN_T5");
+  if (env && env[0] == '2') {
+    attn_t5_kernel<true><<<dim3((max_len + 127) / 128, kH, bt.B), 256, T5_BYTES, st>>>(bt, (const uint8_t*)q_img, (const uint8_t*)k_img,
                                                                              (const uint8_t*)vt_img, R, row0, mode,
                                                                              (uint8_t*)out_img);
+  } else {
+    attn_t5_kernel<false><<<dim3((max_len + 127) / 128, kH, bt.B), 256, T5_BYTES, st>>>(bt, (const uint8_t*)q_img, (const uint8_t*)k_img,
+                                                                             (const uint8_t*)vt_img, R, row0, mode,
+                                                                             (uint8_t*)out_img);
+  }
 }
 
 }  // namespace vx

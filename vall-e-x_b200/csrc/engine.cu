@@ -382,7 +382,7 @@ int vx_create(int device, int max_batch, int max_ctx, int dtype_mode, vx_engine*
   e->decode_fused = !(fu && fu[0] == '0');
   e->decode_fused_maxb = (fu && fu[0] == '1') ? 8 : 2;
   const char* t5 = getenv("VX_ATTN_T5");
-  e->attn_t5 = t5 && t5[0] == '1';
+  e->attn_t5 = t5 && (t5[0] == '1' || t5[0] == '2');   // 2: max-only statistics pass (experimental)
   const char* dg = getenv("VX_DECODE_GRAPH");
   e->decode_graph = dg && dg[0] == '1';
   e->num_sms = prop.multiProcessorCount;
