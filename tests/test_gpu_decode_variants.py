@@ -104,3 +104,33 @@ def test_tma_staged_decode_variant(monkeypatch, names):
     monkeypatch.setenv("VX_DECODE_TMA", "1")
     m = _valle(state_dict_for(gs[0]["seed"]), "bf16", max_ctx=1024, max_batch=len(gs))
     _teacher_forced(m, gs, names)
+
+
+@pytest.mark.skipif(os.environ.get("VX_TEST_EXPERIMENTAL") != "1",
+                    reason="engine-level parity of the tcgen05 attention paths: not yet run on a B200")
+@pytest.mark.parametrize("t5", ["1", "2", "3"])
+@pytest.mark.parametrize("name", ["tiny_en", "mid_ja"])
+def test_nar_and_prefill_with_tcgen05_attention(monkeypatch, name, t5):
+    """VX_ATTN_T5=1: tcgen05/TMEM attention (+ pack kernel) in prefill and NAR; 2: max-only statistics pass; 3: + per-head
+    operand images written by the QKV GEMM epilogue.  Same bar as test_bf16_teacher_forced_tokens."""
+    g = load_golden(name)
+    monkeypatch.setenv("VX_ATTN_T5", t5)
+    m = _valle(state_dict_for(g["seed"]), "bf16", max_ctx=1024, max_batch=1)
+    want = g["codes_bf16w"].astype(np.int64)
+    T = want.shape[0]
+    eng = m.engine
+    lang = m._lang_ids(len(g["x"]), int(g["Lp"]), g["prompt_language_arg"], g["text_language_arg"])
+    eng.set_batch([g["x"].astype(np.int32)], [lang], [g["prompt"].astype(np.int32)])
+    eng.ar_prefill()
+    toks, lens, _ = eng.ar_decode(top_k=1, forced=want[None, :, 0].astype(np.int32), ignore_eos=True)
+    ar_margin = g["ar_top2_bf16w"][:T, 0] - g["ar_top2_bf16w"][:T, 1]
+    ar_match = toks[0, :T] == want[:, 0]
+    assert ar_match[ar_margin > MARGIN].all() and ar_match.mean() > 0.97     # exercises the prefill attention (KV cache)
+    codes = eng.nar(cb0=want[None, :, 0].astype(np.int32), t_lens=np.asarray([T], np.int32))[0]
+    nar_margin = (g["nar_top2_bf16w"][..., 0] - g["nar_top2_bf16w"][..., 1]).T
+    nar_match = codes[:, 1:] == want[:, 1:]
+    upstream_ok = np.cumprod(np.concatenate([np.ones((T, 1), bool), nar_match[:, :-1]], axis=1), axis=1).astype(bool)
+    binding = nar_margin > MARGIN
+    assert nar_match.mean() > 0.90
+    assert nar_match[binding & upstream_ok.all(axis=1, keepdims=True)].mean() > 0.995
+    eng.close()

@@ -10,7 +10,7 @@ say() { echo "== $*" | tee -a "$out"; }
 
 say "parity of the variants that have not run on a GPU yet (VX_TEST_EXPERIMENTAL=1)"
 VX_TEST_EXPERIMENTAL=1 timeout 240 python -m pytest tests/test_gpu_decode_variants.py tests/test_gpu_kernels.py -m gpu -q \
-  -k "tma or cluster or trimmed or pipelined or two_barrier or t5max" 2>&1 | tail -15 >> "$out"
+  -k "tma or cluster or trimmed or pipelined or two_barrier or t5max or tcgen05_attention" 2>&1 | tail -15 >> "$out"
 
 say "batch-1 decode, us/step (default = 3-barrier fused kernel)"
 for v in "" "VX_DECODE_FUSED=0" "VX_DECODE_TMA=1" "VX_DECODE_CLUSTER=1" "VX_DECODE_V4=1" \
@@ -29,8 +29,8 @@ done
 if [ "$mode" = "full" ]; then
   say "where the batched step goes (in-kernel timeline)"
   for b in 8 32; do timeout 90 python tools/decode_timeline.py $b 2>&1 | grep -E "us/step|us per phase" | head -8 >> "$out"; done
-  say "NAR + Vocos (config 4): mma.sync attention vs tcgen05 attention (1: two statistics passes with exponentials, 2: max-only first pass)"
-  for v in "" "VX_ATTN_T5=1" "VX_ATTN_T5=2"; do
+  say "NAR + Vocos (config 4): mma.sync attention vs tcgen05 attention (1: statistics pass with exponentials, 2: max-only first pass, 3: + head images from the QKV GEMM epilogue)"
+  for v in "" "VX_ATTN_T5=1" "VX_ATTN_T5=2" "VX_ATTN_T5=3"; do
     echo "-- ${v:-default}" >> "$out"
     env $v timeout 120 python tools/bench_configs.py --config 4 --batch 8 --reps 1 2>&1 | tail -1 | cut -c1-260 >> "$out"
   done

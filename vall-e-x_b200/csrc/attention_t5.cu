@@ -328,7 +328,7 @@ void launch_attn_t5(const Batch& bt, const void* q_img, const void* k_img, const
     attr_done[dev & 63] = true;
   }
   const char* env = getenv("VX_ATTN_T5");
-  if (env && env[0] == '2') {
+  if (env && (env[0] == '2' || env[0] == '3')) {
     attn_t5_kernel<true><<<dim3((max_len + 127) / 128, kH, bt.B), 256, T5_BYTES, st>>>(bt, (const uint8_t*)q_img, (const uint8_t*)k_img,
                                                                              (const uint8_t*)vt_img, R, row0, mode,
                                                                              (uint8_t*)out_img);

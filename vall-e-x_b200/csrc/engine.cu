@@ -111,7 +111,8 @@ struct vx_engine {
   bool decode_fused = true;                          // 3-barrier persistent decode variant (bf16); VX_DECODE_FUSED=0 disables
   int decode_fused_maxb = 2;
   void* ff2_t_blob = nullptr;                        // 12 x [4096][1024] bf16
-  bool attn_t5 = false;                              // VX_ATTN_T5=1: tcgen05/TMEM attention instead of mma.sync
+  bool attn_t5 = false;
+  bool attn_t5_fuse = false;                         // VX_ATTN_T5=3: QKV GEMM epilogue writes the per-head operand images (NAR layers)                              // VX_ATTN_T5=1: tcgen05/TMEM attention instead of mma.sync
   int64_t full_rows = 0;                             // packed rows of the current full-sequence pass (128-aligned starts)
   Buf xs, xsn, qkvs, atts, ffs, logits, part, tick;  // decode-step scratch
   Buf p_xb, p_acc, p_ll;                                 // fused decode variant: mid-layer residual, fixed-point accumulators
@@ -306,12 +307,22 @@ int full_layer(vx_engine* e, const LayerW& L, int64_t R, const int32_t* row0, in
   void* vc = kv_layer >= 0 ? (char*)e->vc.p + (size_t)kv_layer * e->kv_layer_elems * kvb : nullptr;
   if (e->mode == VX_BF16 && !e->force_simt) {
     launch_layernorm_image(x, nullptr, R, L.n1_g, L.n1_b, ada1, ada1 ? ada1 + kD : nullptr, 1e-5f, e->a_img.p, st);
-    launch_gemm_tc(e->a_img.p, L.qkv_i, L.qkv_b, e->qkv16.p, 3 * kD, R, 3 * kD, kD, TC_EPI_BF16_ROW, st);
+    // VX_ATTN_T5=3 (experimental): NAR layers (no KV scatter) write the per-head operand images straight from the QKV GEMM
+    const bool heads_epi = e->attn_t5 && e->attn_t5_fuse && kv_layer < 0;
+    void *q_i = e->q_img.p, *k_i = e->k_img.p, *vt_i = e->vt_img.p;
+    if (e->attn_t5 && e->attn_t5_fuse) {   // one allocation [q | k | v^T], each full_rows x 1024 bf16
+      k_i = (char*)q_i + (size_t)e->full_rows * kD * 2;
+      vt_i = (char*)q_i + (size_t)2 * e->full_rows * kD * 2;
+    }
+    if (heads_epi) {
+      launch_gemm_tc(e->a_img.p, L.qkv_i, L.qkv_b, q_i, e->full_rows, R, 3 * kD, kD, TC_EPI_QKV_HEADS, st);
+    } else {
+      launch_gemm_tc(e->a_img.p, L.qkv_i, L.qkv_b, e->qkv16.p, 3 * kD, R, 3 * kD, kD, TC_EPI_BF16_ROW, st);
+    }
     if (kv_layer >= 0) { launch_kv_scatter_bf16(bt, e->qkv16.p, kc, vc, maxlen, e->ctx_cap, st); e->launches++; }
     if (e->attn_t5) {
-      launch_pack_qkv_heads(e->qkv16.p, e->full_rows, e->q_img.p, e->k_img.p, e->vt_img.p, st);
-      launch_attn_t5(bt, e->q_img.p, e->k_img.p, e->vt_img.p, e->full_rows, row0, attn_mode, maxlen, e->att_img.p, st);
-      e->launches++;
+      if (!heads_epi) { launch_pack_qkv_heads(e->qkv16.p, e->full_rows, q_i, k_i, vt_i, st); e->launches++; }
+      launch_attn_t5(bt, q_i, k_i, vt_i, e->full_rows, row0, attn_mode, maxlen, e->att_img.p, st);
     } else {
       launch_attn_tc(bt, e->qkv16.p, row0, attn_mode, maxlen, e->att_img.p, st);
     }
@@ -341,7 +352,8 @@ int ensure_full_buffers(vx_engine* e, int64_t R) {
   ENS(e->x, Rp * kD * 4);
   if (e->mode == VX_BF16 && !e->force_simt) {
     ENS(e->a_img, Rp * kD * 2); ENS(e->qkv16, Rp * 3 * kD * 2); ENS(e->att_img, Rp * kD * 2); ENS(e->h_img, Rp * kFF * 2);
-    if (e->attn_t5) { ENS(e->q_img, Rp * kD * 2); ENS(e->k_img, Rp * kD * 2); ENS(e->vt_img, Rp * kD * 2); }
+    if (e->attn_t5 && e->attn_t5_fuse) { ENS(e->q_img, (size_t)3 * Rp * kD * 2); }
+    else if (e->attn_t5) { ENS(e->q_img, Rp * kD * 2); ENS(e->k_img, Rp * kD * 2); ENS(e->vt_img, Rp * kD * 2); }
     e->full_rows = Rp;
     ENS(e->xn, (size_t)std::max<int64_t>(e->max_batch, 1) * kD * 4);
   } else {
@@ -382,7 +394,8 @@ int vx_create(int device, int max_batch, int max_ctx, int dtype_mode, vx_engine*
   e->decode_fused = !(fu && fu[0] == '0');
   e->decode_fused_maxb = (fu && fu[0] == '1') ? 8 : 2;
   const char* t5 = getenv("VX_ATTN_T5");
-  e->attn_t5 = t5 && (t5[0] == '1' || t5[0] == '2');   // 2: max-only statistics pass (experimental)
+  e->attn_t5 = t5 && (t5[0] == '1' || t5[0] == '2' || t5[0] == '3');   // 2: max-only statistics pass; 3: + head images from the GEMM epilogue
+  e->attn_t5_fuse = t5 && t5[0] == '3';
   const char* dg = getenv("VX_DECODE_GRAPH");
   e->decode_graph = dg && dg[0] == '1';
   e->num_sms = prop.multiProcessorCount;

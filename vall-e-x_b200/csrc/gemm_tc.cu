@@ -18,7 +18,7 @@
 namespace vx {
 using namespace tc;
 
-enum TcEpi { TC_BF16_ROW = 0, TC_F32_RESIDUAL = 1, TC_BF16_IMAGE_RELU = 2, TC_F32 = 3 };
+enum TcEpi { TC_BF16_ROW = 0, TC_F32_RESIDUAL = 1, TC_BF16_IMAGE_RELU = 2, TC_F32 = 3, TC_QKV_HEADS = 4 };
 
 template <int BN>
 struct TcCfg {
@@ -154,6 +154,32 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const bf16* __restrict_
               p.x = pk(v[i], v[i + 1]); p.y = pk(v[i + 2], v[i + 3]); p.z = pk(v[i + 4], v[i + 5]); p.w = pk(v[i + 6], v[i + 7]);
               *reinterpret_cast<uint4*>(img + tile_image_offset(row, n0 + i, N)) = p;
             }
+          } else if constexpr (EPI == TC_QKV_HEADS) {
+            // N = 3 x 1024: columns n0..n0+31 belong to q|k|v `which`, head h, dims d0..d0+31.  q and k: per-head K-major tile
+            // images [R,64]; v: transposed per 64-key block, [64 d rows x 64 keys] (the B operand of P V) -- same layouts as
+            // pack_qkv_heads_kernel (attention_t5.cu), written straight from the accumulator.  ldc = R (multiple of 128).
+            const int which = n0 / kD, hc = n0 % kD, h = hc >> 6, d0 = hc & 63;
+            uint8_t* base = reinterpret_cast<uint8_t*>(out) + (size_t)which * ((size_t)ldc * kD * 2);
+            auto pk = [](float a, float b) {
+              return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(b)) << 16);
+            };
+            if (which < 2) {
+              uint8_t* img = base + (size_t)h * ((size_t)ldc * 128);
+#pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                uint4 p;
+                p.x = pk(v[i], v[i + 1]); p.y = pk(v[i + 2], v[i + 3]); p.z = pk(v[i + 4], v[i + 5]); p.w = pk(v[i + 6], v[i + 7]);
+                *reinterpret_cast<uint4*>(img + tile_image_offset(row, d0 + i, 64)) = p;
+              }
+            } else {
+              uint8_t* vb = base + ((size_t)h * (size_t)(ldc / 64) + (size_t)(row >> 6)) * 8192;
+              const int kc = (int)((row & 63) >> 3), kl = (int)(row & 7);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const int d = d0 + i;
+                *reinterpret_cast<uint16_t*>(vb + d * 128 + ((kc ^ (d & 7)) << 4) + kl * 2) = __bfloat16_as_ushort(__float2bfloat16_rn(v[i]));
+              }
+            }
           } else if constexpr (EPI == TC_F32_RESIDUAL) {
             float* o = reinterpret_cast<float*>(out) + row * ldc + n0;
 #pragma unroll
@@ -208,6 +234,7 @@ void launch_gemm_tc(const void* A_img, const void* W_img, const float* bias, voi
     case TC_BF16_ROW: tc_launch<BN_, TC_BF16_ROW>(A, W, bias, out, ldc, M, N, K, st); break;            \
     case TC_F32_RESIDUAL: tc_launch<BN_, TC_F32_RESIDUAL>(A, W, bias, out, ldc, M, N, K, st); break;    \
     case TC_BF16_IMAGE_RELU: tc_launch<BN_, TC_BF16_IMAGE_RELU>(A, W, bias, out, ldc, M, N, K, st); break; \
+    case TC_QKV_HEADS: tc_launch<BN_, TC_QKV_HEADS>(A, W, bias, out, ldc, M, N, K, st); break;          \
     default: tc_launch<BN_, TC_F32>(A, W, bias, out, ldc, M, N, K, st); break;                         \
   }
   // 128x256 tiles keep the operand read rate under the shared-memory limit, but a small problem needs enough tiles to

@@ -80,7 +80,9 @@ void launch_attn_decode(const Batch& bt, const float* qkv_step, void* kcache, vo
                         float* out, float* partial, int32_t* tickets, int nsplit, cudaStream_t st);
 
 // ---- bf16 tensor-core path (tcgen05 GEMM, mma.sync attention); operands are "tile images" (tc_common.cuh) ----
-enum TcEpilogue { TC_EPI_BF16_ROW = 0, TC_EPI_F32_RESIDUAL = 1, TC_EPI_BF16_IMAGE_RELU = 2, TC_EPI_F32 = 3 };
+enum TcEpilogue { TC_EPI_BF16_ROW = 0, TC_EPI_F32_RESIDUAL = 1, TC_EPI_BF16_IMAGE_RELU = 2, TC_EPI_F32 = 3,
+                  TC_EPI_QKV_HEADS = 4 };   // 4: N = 3072 QKV projection written as the per-head operand images of attention_t5.cu
+                                            //    (out = [q_img | k_img | vt_img], ldc = padded row count R)
 void launch_gemm_tc(const void* A_img, const void* W_img, const float* bias, void* out, int64_t ldc, int64_t M, int N,
                     int K, int epi, cudaStream_t st);
 void launch_pack_tile_image(const float* src, int64_t rows, int K, void* img, cudaStream_t st);
