@@ -139,6 +139,80 @@ def test_long_text_fixed_prompt_batches_sentences(tmp_path, monkeypatch):
                                                  mode="sliding-window", batch_sentences=True)
 
 
+class _RecordingModel:
+    """Records (x, y, enroll, prompt_language) of every inference call; output frames depend on the call index so a
+    handed-off prompt is recognisable."""
+    def __init__(self):
+        self.calls = []
+
+    def inference(self, x, x_lens, y, enroll_x_lens, **kw):
+        k = len(self.calls)
+        self.calls.append((x.clone(), y.clone(), int(enroll_x_lens), kw.get("prompt_language"), int(x_lens[0])))
+        T = int(x.shape[1]) - int(enroll_x_lens) + 1
+        return (torch.arange(T * 8, dtype=torch.long).reshape(1, T, 8) + 100 * (k + 1)) % 1024
+
+
+def _reference_sliding_window(sentences, audio_prompts, text_prompts, model_fn, seed):
+    """The control flow of utils/generation.py:228-269 restated: (x, y, enroll) each sentence receives."""
+    torch.manual_seed(seed)
+    original_audio_prompts, original_text_prompts = audio_prompts, text_prompts
+    seen = []
+    for k, phones in enumerate(sentences):
+        enroll = text_prompts.shape[-1]
+        text_tokens = torch.cat([text_prompts.long(), torch.tensor([list(phones)], dtype=torch.long)], dim=-1)
+        seen.append((text_tokens, audio_prompts, enroll))
+        frames = model_fn(k, text_tokens, enroll)
+        if torch.rand(1) < 0.5:
+            audio_prompts = frames[:, :, -8:]
+            text_prompts = text_tokens[:, enroll:]
+        else:
+            audio_prompts = original_audio_prompts
+            text_prompts = original_text_prompts
+    return seen
+
+
+@pytest.mark.parametrize("with_prompt", [True, False])
+def test_long_text_sliding_window_prompt_sequence(tmp_path, monkeypatch, with_prompt):
+    """utils/generation.py:228-269: after every sentence a coin flip either hands the sentence's output over as the next
+    prompt or RESETS to the original prompt.  The exact (text, audio prompt, enroll length, prompt language) sequence is
+    compared with a restatement of the reference's loop under the same torch seed."""
+    np.savez(tmp_path / "p.npz", audio_tokens=(np.arange(7 * 8).reshape(1, 7, 8) % 1024).astype(np.int64),
+             text_tokens=np.full((1, 3), 9, np.int64), lang_code=np.int32(0))
+    sents = [np.arange(5, 9), np.arange(10, 16), np.arange(20, 23), np.arange(30, 41), np.arange(12, 14), np.arange(40, 47),
+             np.arange(5, 12), np.arange(21, 25)]
+    prompt = str(tmp_path / "p.npz") if with_prompt else None
+    a0, t0, lang0 = generation._load_prompt(prompt)
+    for seed in (0, 1, 2, 3):
+        mdl = _RecordingModel()
+        monkeypatch.setattr(generation, "model", mdl, raising=False)
+        monkeypatch.setattr(generation, "vocos", _StubVocos(), raising=False)
+        torch.manual_seed(seed)
+        generation.generate_audio_from_long_text(sents, prompt=prompt, language="ja", mode="sliding-window")
+
+        def model_fn(k, x, enroll):
+            T = int(x.shape[1]) - enroll + 1
+            return (torch.arange(T * 8, dtype=torch.long).reshape(1, T, 8) + 100 * (k + 1)) % 1024
+        want = _reference_sliding_window(sents, a0, t0, model_fn, seed)
+        assert len(mdl.calls) == len(want) == len(sents)
+        resets = handoffs = 0
+        for k, ((x, y, enroll, lp, xl), (wx, wy, wenroll)) in enumerate(zip(mdl.calls, want)):
+            assert torch.equal(x, wx) and torch.equal(y.long(), wy.long()) and enroll == wenroll and xl == wx.shape[1], (seed, k)
+            assert lp == ("zh" if with_prompt else "ja")        # lang_pr never changes (utils/generation.py:182-192)
+            if k > 0:
+                if torch.equal(y.long(), a0.long()) and enroll == t0.shape[-1]:
+                    resets += 1
+                else:
+                    handoffs += 1
+        if seed == 0:
+            assert resets > 0 and handoffs > 0                   # both branches of utils/generation.py:264-269 exercised
+    # fixed-prompt: every sentence sees the original prompt (utils/generation.py:199-224)
+    if with_prompt:
+        mdl = _RecordingModel()
+        monkeypatch.setattr(generation, "model", mdl, raising=False)
+        generation.generate_audio_from_long_text(sents, prompt=prompt, language="ja", mode="fixed-prompt")
+        assert all(torch.equal(y.long(), a0.long()) and enroll == 3 for _, y, enroll, _, _ in mdl.calls)
+
+
 class _FakeEngine:
     """Stands in for vallex_b200.engine.Engine: records the batches the host layer forms; utterance b of a batch 'generates'
     T_b = S_b frames whose codes are (b, t)-dependent."""

@@ -195,16 +195,20 @@ def generate_audio_from_long_text(text, prompt=None, language="auto", accent="no
         for encoded_frames in model.inference_batch(items, **kw):
             complete_tokens = torch.cat([complete_tokens, encoded_frames.transpose(2, 1).cpu()], dim=-1)
         sentences = []
+    if lang_pr is None:  # no prompt: utils/generation.py:192 (fixed for the whole request)
+        lang_pr = language if language != "mix" else "en"
+    original_audio_prompts, original_text_prompts = audio_prompts, text_prompts  # utils/generation.py:230-231
     for sent in sentences:
         encoded_frames, text_tokens, enroll = _one_utterance(sent, audio_prompts, text_prompts, lang_pr, language,
                                                              accent, **infer_kw)
         complete_tokens = torch.cat([complete_tokens, encoded_frames.transpose(2, 1).cpu()], dim=-1)
-        if mode == "sliding-window" and torch.rand(1) < 0.5:  # utils/generation.py:264-269
-            audio_prompts = encoded_frames[:, :, -NUM_QUANTIZERS:].type(torch.int32).cpu()
-            text_prompts = text_tokens[:, enroll:].type(torch.int32)
-            if lang_pr is None:
-                lang_pr = token2lang[lang2token[language]]
-                lang_pr = lang_pr if lang_pr != "mix" else "en"
+        if mode == "sliding-window":  # utils/generation.py:264-269: a coin flip per sentence, hand-off or reset
+            if torch.rand(1) < 0.5:
+                audio_prompts = encoded_frames[:, :, -NUM_QUANTIZERS:].type(torch.int32).cpu()
+                text_prompts = text_tokens[:, enroll:].type(torch.int32)
+            else:
+                audio_prompts = original_audio_prompts
+                text_prompts = original_text_prompts
     # one Vocos pass over the concatenation (utils/generation.py:225-227,271-273)
     features = vocos.codes_to_features(complete_tokens.permute(1, 0, 2))
     samples = vocos.decode(features, bandwidth_id=torch.tensor([2]))
