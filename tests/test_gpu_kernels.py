@@ -61,3 +61,44 @@ def test_tensor_core_attention(S, length, mode, variant, monkeypatch):
     err = (out.double() - ref).abs().max().item()
     print(f"attn_{variant} S={S} len={length} mode={mode}: max abs err {err:.3e}")
     assert err < 3e-2
+
+
+def test_engine_rejects_out_of_range_ids():
+    """the kernels index embedding tables with the caller's ids; the C ABI must refuse ids the reference's
+    F.embedding would raise IndexError for (models/vallex.py:497-507,605-632) instead of reading out of bounds."""
+    from conftest import state_dict_for
+    from vallex_b200._capi import VallexB200Error
+    from vallex_b200.engine import Engine
+    from vallex_b200.weights import synthetic_vocos_state_dict
+    eng = Engine(0, 2, 128, "fp32")
+    eng.load_valle_state_dict(state_dict_for(0))
+    eng.load_vocos_state_dict(synthetic_vocos_state_dict(0))
+    eng.finalize()
+    good_t, good_l = np.arange(5, 11, dtype=np.int32), np.zeros(6, np.int32)
+    good_p = np.zeros((4, 8), np.int32)
+    for bad in ("text", "lang", "prompt"):
+        t, l, p = good_t.copy(), good_l.copy(), good_p.copy()
+        if bad == "text":
+            t[3] = 2048
+        elif bad == "lang":
+            l[2] = 3
+        else:
+            p[1, 7] = 1024
+        with pytest.raises(VallexB200Error, match="out of range"):
+            eng.set_batch([good_t, t], [good_l, l], [good_p, p])
+    eng.set_batch([good_t], [good_l], [good_p])          # padded tails beyond the lengths are not inspected
+    eng.ar_prefill()
+    eng.ar_decode(max_new=3, top_k=1)
+    with pytest.raises(VallexB200Error, match="cb0"):
+        eng.nar(cb0=np.asarray([[1, 5000, 2]], np.int32), t_lens=np.asarray([3], np.int32))
+    codes = eng.nar(cb0=np.asarray([[1, 2, 3]], np.int32), t_lens=np.asarray([3], np.int32))
+    assert codes.shape == (1, 3, 8) and codes.min() >= 0 and codes.max() < 1024
+    bad_codes = np.ascontiguousarray(codes.transpose(2, 0, 1)).copy()
+    bad_codes[5, 0, 1] = -7
+    with pytest.raises(VallexB200Error, match="code out of range"):
+        eng.vocos_decode(bad_codes)
+    wave = eng.vocos_decode(np.ascontiguousarray(codes.transpose(2, 0, 1)))
+    assert np.isfinite(wave).all()
+    eng.close()
+    with pytest.raises(VallexB200Error):
+        Engine(0, 5000, 128, "fp32")                      # max_batch bound (pinned scratch holds max_batch + 1 ints)

@@ -49,6 +49,42 @@ def test_inference_asserts_like_reference():
         m.inference(x, torch.tensor([0]), torch.zeros(1, 3, 8), 0, prompt_language="en", text_language="en")
 
 
+def test_load_state_dict_is_strict_at_call_time():
+    """utils/generation.py:79-83: `missing_keys, unexpected_keys = model.load_state_dict(checkpoint["model"], strict=True)`."""
+    m = _model()
+    sd = synthetic_state_dict(1)
+    r = m.load_state_dict(sd, strict=True)
+    assert r.missing_keys == [] and r.unexpected_keys == []
+    bad = dict(sd)
+    del bad["ar_predict_layer.weight"]
+    bad["bogus.weight"] = torch.zeros(1)
+    with pytest.raises(RuntimeError, match="Missing key"):
+        m.load_state_dict(bad, strict=True)
+    r = m.load_state_dict(bad, strict=False)                       # keeps the previously loaded tensor for the missing key
+    assert r.missing_keys == ["ar_predict_layer.weight"] and r.unexpected_keys == ["bogus.weight"]
+    assert m._sd["ar_predict_layer.weight"] is sd["ar_predict_layer.weight"] and "bogus.weight" not in m._sd
+    wrong = dict(sd)
+    wrong["ar_decoder.norm.weight"] = torch.zeros(7)
+    with pytest.raises(RuntimeError, match="size mismatch"):
+        m.load_state_dict(wrong, strict=False)
+
+
+def test_out_of_range_ids_raise_index_error_like_embedding():
+    """F.embedding raises IndexError in the reference (models/vallex.py:497,529,605-632); the engine must never see such ids."""
+    m = _model()
+    m.load_state_dict(synthetic_state_dict(1))
+    kw = dict(prompt_language="en", text_language="en")
+    with pytest.raises(IndexError):
+        m.inference(torch.tensor([[5, 2048]]), torch.tensor([2]), torch.zeros(1, 3, 8, dtype=torch.long), 0, **kw)
+    with pytest.raises(IndexError):
+        m.inference(torch.tensor([[5, 6]]), torch.tensor([2]), torch.full((1, 3, 8), 1024, dtype=torch.long), 0, **kw)
+    with pytest.raises(IndexError):
+        m.inference(torch.tensor([[5, -1]]), torch.tensor([2]), torch.zeros(1, 3, 8, dtype=torch.long), 0, **kw)
+    from vallex_b200.vocos import Vocos
+    with pytest.raises(IndexError):
+        Vocos(synthetic_vocos_state_dict(0)).codes_to_features(torch.full((8, 1, 4), 1024, dtype=torch.long))
+
+
 def test_generation_errors(tmp_path, monkeypatch):
     monkeypatch.chdir(tmp_path)
     with pytest.raises(ValueError, match="Cannot find prompt"):

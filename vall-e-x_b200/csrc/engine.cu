@@ -58,6 +58,20 @@ __global__ void write_cb0_kernel(Batch bt, const int32_t* __restrict__ cb0, cons
   if (t < tl[b]) bt.y[(size_t)b * bt.ymax + 1 + bt.P[b] + t] = cb0[(size_t)b * Tmax + t];
 }
 
+// ids index embedding tables directly: flag |= bit when a[b*stride + i] (i < lens[b]*inner, or i < count when lens is null)
+// lies outside [lo, hi).  The reference's F.embedding raises IndexError for those (models/vallex.py:497-507,605-632).
+__global__ void check_range_kernel(const int32_t* __restrict__ a, int64_t stride, const int32_t* __restrict__ lens, int inner,
+                                   int64_t count, int lo, int hi, int bit, int32_t* __restrict__ flag) {
+  const int b = blockIdx.y;
+  const int64_t n = lens ? (int64_t)lens[b] * inner : count;
+  bool bad = false;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = a[(size_t)b * stride + i];
+    bad |= (v < lo || v >= hi);
+  }
+  if (bad) atomicOr(flag, bit);
+}
+
 struct Weight {
   std::vector<int64_t> shape;
   float* f32 = nullptr;  // device fp32 (always present until finalize may drop it for bf16 matrices)
@@ -104,6 +118,7 @@ struct vx_engine {
   std::vector<int> hS, hP, hT, h_ar_row0;
   int ar_rows = 0, ar_maxlen = 0;
   Batch bt{};
+  Buf d_flag;                                        // [4] id range-check flags
   Buf d_text, d_lang, d_prompt, d_S, d_P, d_ar_row0, d_nar_row0, d_T, d_ctx, d_y, d_budget, d_fin, d_slp, d_nact;
   Buf x, xn, qkv, att, ffh, kc, vc;                 // prefill / NAR activations, KV cache
   Buf a_img, qkv16, att_img, h_img, t_img;           // bf16 mode: tile-image / bf16 activations
@@ -370,8 +385,8 @@ const char* vx_version(void) { return "vallex_b200 0.1 sm_100a"; }
 const char* vx_last_error(void) { return g_err.c_str(); }
 
 int vx_create(int device, int max_batch, int max_ctx, int dtype_mode, vx_engine** out) {
-  if (!out || max_batch < 1 || max_ctx < 8 || (dtype_mode != VX_F32 && dtype_mode != VX_BF16))
-    return fail(VX_ERR_ARG, "vx_create: bad arguments");
+  if (!out || max_batch < 1 || max_batch > 1000 || max_ctx < 8 || (dtype_mode != VX_F32 && dtype_mode != VX_BF16))
+    return fail(VX_ERR_ARG, "vx_create: bad arguments (1 <= max_batch <= 1000, max_ctx >= 8)");   // h_pinned holds max_batch + 1 ints
   int ndev = 0;
   CK(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return fail(VX_ERR_ARG, "vx_create: no such CUDA device");
@@ -412,7 +427,7 @@ void vx_destroy(vx_engine* e) {
     if (kv.second.b16) cudaFree(kv.second.b16);
     if (kv.second.img) cudaFree(kv.second.img);
   }
-  Buf* bufs[] = {&e->d_text, &e->d_lang, &e->d_prompt, &e->d_S, &e->d_P, &e->d_ar_row0, &e->d_nar_row0, &e->d_T,
+  Buf* bufs[] = {&e->d_flag, &e->d_text, &e->d_lang, &e->d_prompt, &e->d_S, &e->d_P, &e->d_ar_row0, &e->d_nar_row0, &e->d_T,
                  &e->d_ctx, &e->d_y, &e->d_budget, &e->d_fin, &e->d_slp, &e->d_nact, &e->x, &e->xn, &e->qkv, &e->att,
                  &e->ffh, &e->kc, &e->vc, &e->a_img, &e->qkv16, &e->att_img, &e->h_img, &e->t_img, &e->q_img, &e->k_img, &e->vt_img, &e->xs, &e->xsn, &e->qkvs, &e->atts, &e->ffs, &e->logits, &e->part, &e->tick, &e->p_xb, &e->p_acc, &e->p_ll, &e->p_pf, &e->p_bar, &e->p_prof,
                  &e->lastmap, &e->out_tok, &e->forced, &e->yemb, &e->yrow0, &e->trow0, &e->tgtmap, &e->nlog, &e->codes,
@@ -662,7 +677,20 @@ int vx_set_batch(vx_engine* e, int B, const int32_t* text_ids, const int32_t* te
   CK(cudaMemcpyAsync(e->d_S.p, e->hS.data(), B * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(e->d_P.p, e->hP.data(), B * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(e->d_ar_row0.p, e->h_ar_row0.data(), B * 4, cudaMemcpyHostToDevice, st));
+  ENS(e->d_flag, 16);
+  CK(cudaMemsetAsync(e->d_flag.p, 0, 16, st));
+  check_range_kernel<<<dim3(4, B), 256, 0, st>>>((const int32_t*)e->d_text.p, Smax, (const int32_t*)e->d_S.p, 1, 0, 0, kTextVocab, 1, (int32_t*)e->d_flag.p);
+  check_range_kernel<<<dim3(4, B), 256, 0, st>>>((const int32_t*)e->d_lang.p, Smax, (const int32_t*)e->d_S.p, 1, 0, 0, 3, 2, (int32_t*)e->d_flag.p);
+  if (Pmax > 0)
+    check_range_kernel<<<dim3(8, B), 256, 0, st>>>((const int32_t*)e->d_prompt.p, (int64_t)Pmax * kNQ, (const int32_t*)e->d_P.p, kNQ, 0, 0, kVocab, 4, (int32_t*)e->d_flag.p);
+  CK(cudaMemcpyAsync(e->h_pinned, e->d_flag.p, 4, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));  // hS/hP/h_ar_row0 are reused by later calls
+  if (e->h_pinned[0] != 0) {
+    e->batch_set = false;
+    const int f = e->h_pinned[0];
+    return fail(VX_ERR_ARG, std::string("vx_set_batch: index out of range in") + ((f & 1) ? " text_ids (0..2047)" : "") +
+                            ((f & 2) ? " lang_ids (0..2)" : "") + ((f & 4) ? " prompt_codes (0..1023)" : ""));
+  }
   Batch& bt = e->bt;
   bt.B = B; bt.Smax = Smax; bt.Pmax = std::max(Pmax, 1);
   bt.text_ids = (const int32_t*)e->d_text.p; bt.lang_ids = (const int32_t*)e->d_lang.p;
@@ -984,6 +1012,14 @@ int vx_nar(vx_engine* e, const int32_t* cb0, const int32_t* t_lens, int Tmax, in
     for (int b = 0; b < B; ++b)
       if (e->hT[b] < 0 || e->hT[b] > Tmax || e->hS[b] + e->hP[b] + e->hT[b] + 1 > e->max_ctx)
         return fail(VX_ERR_CAPACITY, "vx_nar: t_lens out of range for max_ctx");
+    if (Tmax > 0) {
+      ENS(e->d_flag, 16);
+      CK(cudaMemsetAsync(e->d_flag.p, 0, 16, st));
+      check_range_kernel<<<dim3(8, B), 256, 0, st>>>((const int32_t*)e->cb0_dev.p, Tmax, (const int32_t*)e->tl_dev.p, 1, 0, 0, kVocab, 1, (int32_t*)e->d_flag.p);
+      CK(cudaMemcpyAsync(e->h_pinned, e->d_flag.p, 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if (e->h_pinned[0] != 0) return fail(VX_ERR_ARG, "vx_nar: cb0 token out of range (0..1023)");
+    }
     launch_init_y(bt, st);
     if (Tmax > 0) write_cb0_kernel<<<dim3((Tmax + 255) / 256, B), 256, 0, st>>>(bt, (const int32_t*)e->cb0_dev.p, (const int32_t*)e->tl_dev.p, Tmax);
     else CK(cudaMemsetAsync(e->d_T.p, 0, B * 4, st));
@@ -1071,6 +1107,9 @@ int vx_vocos_decode(vx_engine* e, const int32_t* codes, int B, int T, int bandwi
   CK(cudaEventRecord(e->ev0, st));
   int r;
   if ((r = copy_in(e->v_codes.p, codes, (size_t)kNQ * R * 4, mem, st))) return r;
+  ENS(e->d_flag, 16);
+  CK(cudaMemsetAsync(e->d_flag.p, 0, 16, st));   // checked after the pass (the gather clamps, so a bad code cannot fault)
+  check_range_kernel<<<dim3(148, 1), 256, 0, st>>>((const int32_t*)e->v_codes.p, 0, nullptr, 1, (int64_t)kNQ * R, 0, 1024, 1, (int32_t*)e->d_flag.p);
   auto V = [&](const std::string& k) { return vec(e, "vocos." + k); };
   float* feat = (float*)e->v_feat.p; float* col = (float*)e->v_col.p; float* x = (float*)e->v_x.p;
   float* h = (float*)e->v_h.p; float* ff = (float*)e->v_ff.p; float* head = (float*)e->v_head.p;
@@ -1100,9 +1139,11 @@ int vx_vocos_decode(vx_engine* e, const int32_t* codes, int B, int T, int bandwi
   e->launches += 5;
   if ((r = copy_out(wave, wv, (size_t)R * 320 * 4, mem, st))) return r;
   CK(cudaEventRecord(e->ev1, st));
+  CK(cudaMemcpyAsync(e->h_pinned, e->d_flag.p, 4, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   CK(cudaEventElapsedTime(&e->ms_vocos, e->ev0, e->ev1));
   CK(cudaGetLastError());
+  if (e->h_pinned[0] != 0) return fail(VX_ERR_ARG, "vx_vocos_decode: code out of range (0..1023)");
   return VX_OK;
 }
 

@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(128) vocos_features_kernel(const int32_t* __re
   float s = 0.f;
 #pragma unroll
   for (int k = 0; k < kNQ; ++k) {
-    const int code = codes[(size_t)k * B * T + r];
+    const int code = min(max(codes[(size_t)k * B * T + r], 0), 1023);   // range is checked by the caller (engine.cu); never index out of the table
     s = __fadd_rn(s, table[((size_t)code + 1024 * k) * VC_IN + c]);
   }
   feats[r * VC_IN + c] = s;

@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from .engine import Engine
-from .macros import LANGUAGE_ID, N_DIM, NUM_AUDIO_TOKENS, NUM_HEAD, NUM_LAYERS, NUM_QUANTIZERS
+from .macros import LANGUAGE_ID, N_DIM, NUM_AUDIO_TOKENS, NUM_HEAD, NUM_LAYERS, NUM_QUANTIZERS, NUM_TEXT_TOKENS
 
 _IncompatibleKeys = namedtuple("_IncompatibleKeys", ["missing_keys", "unexpected_keys"])
 
@@ -30,6 +30,15 @@ def _resolve_seed(seed: Optional[int]) -> int:
     if seed is None:
         return int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
     return int(seed)
+
+
+def _check_ids(text: np.ndarray, prompt: np.ndarray):
+    """The reference's embedding lookups raise IndexError on an out-of-range id (F.embedding; models/vallex.py:497,
+    529,605-632); the engine indexes its tables with these ids, so the same error is raised before anything runs."""
+    if text.size and (int(text.min()) < 0 or int(text.max()) >= NUM_TEXT_TOKENS):
+        raise IndexError("index out of range in self (text token id outside the 2048-entry text embedding)")
+    if prompt.size and (int(prompt.min()) < 0 or int(prompt.max()) >= NUM_AUDIO_TOKENS):
+        raise IndexError("index out of range in self (audio prompt code outside 0..1023)")
 
 
 class VALLE:
@@ -55,11 +64,34 @@ class VALLE:
 
     # -- nn.Module-like surface ----------------------------------------------------------------
     def load_state_dict(self, state_dict, strict: bool = True):
-        self._sd = {k: v for k, v in state_dict.items()}
+        """torch.nn.Module.load_state_dict semantics (utils/generation.py:79-83 calls it with strict=True and asserts
+        `not missing_keys`): returns (missing_keys, unexpected_keys); with strict=True any missing / unexpected key or a
+        shape mismatch raises RuntimeError right here, not at first engine use."""
+        from .weights import expected_state_dict_shapes
+        want = expected_state_dict_shapes()
+        missing = [k for k in want if k not in state_dict]
+        unexpected = [k for k in state_dict if k not in want]
+        errors = []
+        for k, shp in want.items():
+            if k in state_dict and tuple(state_dict[k].shape) != shp:
+                errors.append(f"size mismatch for {k}: copying a param with shape {tuple(state_dict[k].shape)} from checkpoint, "
+                              f"the shape in current model is {shp}.")
+        if strict:
+            if unexpected:
+                errors.insert(0, "Unexpected key(s) in state_dict: " + ", ".join(f'"{k}"' for k in unexpected) + ". ")
+            if missing:
+                errors.insert(0, "Missing key(s) in state_dict: " + ", ".join(f'"{k}"' for k in missing) + ". ")
+        if errors:
+            raise RuntimeError("Error(s) in loading state_dict for VALLE:\n\t" + "\n\t".join(errors))
+        if missing and self._sd is None:
+            raise RuntimeError("load_state_dict(strict=False) with missing keys needs a previously loaded checkpoint")
+        base = dict(self._sd) if (missing and self._sd is not None) else {}
+        base.update({k: v for k, v in state_dict.items() if k in want})
+        self._sd = base
         if self._engine is not None:
             self._engine.close()
             self._engine = None
-        return _IncompatibleKeys([], [])
+        return _IncompatibleKeys(missing, unexpected)
 
     def eval(self):
         return self
@@ -135,6 +167,7 @@ class VALLE:
         text = x[0, :S].detach().to("cpu").numpy().astype(np.int32)
         prompt = y[0].detach().to("cpu").numpy().astype(np.int32).reshape(P, NUM_QUANTIZERS)
         lang = self._lang_ids(S, Lp, prompt_language, text_language)
+        _check_ids(text, prompt)
         eng = self.engine
         seed = _resolve_seed(seed)
         nb = int(best_of)
@@ -184,6 +217,7 @@ class VALLE:
                 assert S > 0
                 texts.append(x[0].detach().to("cpu").numpy().astype(np.int32))
                 prompts.append(y[0].detach().to("cpu").numpy().astype(np.int32).reshape(P, NUM_QUANTIZERS))
+                _check_ids(texts[-1], prompts[-1])
                 langs.append(self._lang_ids(S, int(enroll_x_lens), prompt_language, text_language))
             eng.set_batch(texts, langs, prompts)
             eng.ar_prefill()

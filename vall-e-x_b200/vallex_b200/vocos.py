@@ -79,6 +79,8 @@ class Vocos:
     def codes_to_features(self, codes: torch.Tensor) -> CodesFeatures:
         if codes.dim() == 2:
             codes = codes.unsqueeze(1)
+        if codes.numel() and (int(codes.min()) < 0 or int(codes.max()) >= 1024):   # F.embedding raises the same in the vocos package
+            raise IndexError("index out of range in self (EnCodec code outside 0..1023)")
         return CodesFeatures(np.ascontiguousarray(codes.detach().to("cpu").numpy().astype(np.int32)))
 
     def decode(self, features_input, bandwidth_id: Optional[torch.Tensor] = None, **kwargs) -> torch.Tensor:

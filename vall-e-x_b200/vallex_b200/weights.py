@@ -132,6 +132,18 @@ def synthetic_vocos_state_dict(seed: int = 0) -> "OrderedDict[str, torch.Tensor]
     return sd
 
 
+_EXPECTED = None
+
+
+def expected_state_dict_shapes() -> "OrderedDict[str, tuple]":
+    """Key -> shape of the reference model's `state_dict()` (374 keys); used by the strict
+    `VALLE.load_state_dict` check (utils/generation.py:79-83)."""
+    global _EXPECTED
+    if _EXPECTED is None:
+        _EXPECTED = OrderedDict((k, tuple(v.shape)) for k, v in synthetic_state_dict(0).items())
+    return _EXPECTED
+
+
 _BF16_PAT = __import__("re").compile(
     r"(self_attn\.in_proj_weight|self_attn\.out_proj\.weight|linear1\.weight|linear2\.weight"
     r"|^ar_predict_layer\.weight|^nar_predict_layers\.\d+\.weight|^nar_audio_embeddings\.[2-7]\.word_embeddings\.weight)$")
