@@ -58,6 +58,20 @@ def test_tensor_core_batched_decode_variant(monkeypatch, B):
     _teacher_forced(m, gs, names)
 
 
+@pytest.mark.parametrize("B", [5, 8, 13])
+def test_tensor_core_batched_decode_ragged_long(monkeypatch, B):
+    """Ragged batch with very different context lengths (BASELINE config 1's S=122, P=225, T=1952 next to 6-phoneme utterances
+    that finish after 80 / 96 tokens): the balanced attention phase cuts the flattened key space of all (utterance, head)
+    pairs into equal warp ranges, so heads are split into many pieces for the long utterances and several heads share one
+    warp for the short ones; finished utterances drop out of the plan."""
+    names = (["cfg1_librispeech", "tiny_en", "noprompt_en", "tiny_en", "cfg1_librispeech", "noprompt_en"] * 3)[:B]
+    gs = [load_golden(n) for n in names]
+    monkeypatch.delenv("VX_DECODE_MMA", raising=False)
+    monkeypatch.delenv("VX_DECODE_ATTN", raising=False)
+    m = _valle(state_dict_for(0), "bf16", max_ctx=2400, max_batch=B)
+    _teacher_forced(m, gs, names)
+
+
 @pytest.mark.skipif(os.environ.get("VX_TEST_EXPERIMENTAL") != "1",
                     reason="cluster/DSMEM decode kernel: written after the round-1 GPU budget ran out, not yet run on a B200")
 @pytest.mark.parametrize("name", ["tiny_en", "mid_ja"])

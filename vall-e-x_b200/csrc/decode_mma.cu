@@ -263,6 +263,204 @@ __device__ void attn_unit_pipe(const PParams& p, int layer, int b, int h, int sp
 }
 
 
+// =================================================================================================================
+// Balanced warp-level attention phase of the batched kernel (modules/activation.py:142-167 for one new query row).
+// The keys of all (utterance, head) pairs form one flattened space of 32-key blocks; every warp of the grid takes an
+// equal contiguous range of it, so the KV cache streams once at HBM rate whatever the mix of context lengths (the
+// CTA-per-head units before left 148 CTAs with 3.5 waves of unequal units).  A warp walks its range with 4 key rows per
+// load instruction (8 lanes x 16 B = one 128-byte row; 512 contiguous bytes per instruction), keeps up to 16 x 16 B per
+// lane in flight (K of block n+1 and V of block n are requested before block n's arithmetic), carries a running
+// (max, sum, o[64]) per (utterance, head) segment and writes ONE partial record per segment.  The last segment of a head
+// to arrive (ticket) folds the records in piece order -- deterministic whoever is last.
+// =================================================================================================================
+constexpr int kRec = kDH + 4;       // partial record: m, l, pad, pad, o[64]  (16-byte aligned rows)
+constexpr int kPerMin = 2;          // at least 64 keys per warp (bounds the pieces per head when B is small)
+
+struct AttnPlan {                   // per step, in registers: lane b owns utterance b
+  int n, nblk, pb;                  // keys incl. the new one (0: finished / no such utterance), 32-key blocks, exclusive prefix of 16*nblk
+  int tb, per;                      // total blocks, blocks per warp (warp-uniform)
+};
+__device__ __forceinline__ AttnPlan attn_plan(const Batch& bt) {
+  const int lane = threadIdx.x & 31;
+  AttnPlan pl;
+  pl.n = 0;
+  if (lane < bt.B && !ld_cg(bt.finished + lane)) pl.n = bt.S[lane] + bt.P[lane] + ld_cg(bt.T + lane) + 1;
+  pl.nblk = (pl.n + 31) >> 5;
+  int incl = kH * pl.nblk;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  pl.pb = incl - kH * pl.nblk;
+  pl.tb = __shfl_sync(0xffffffffu, incl, 31);
+  const int nw = gridDim.x * PNW;
+  pl.per = max(kPerMin, (pl.tb + nw - 1) / nw);
+  return pl;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& r, float (&w)[8]) {
+  const uint32_t u[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { w[2 * i] = __uint_as_float(u[i] << 16); w[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u); }
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(b)) << 16);
+}
+
+__device__ void attn_phase_balanced(const PParams& p, int layer, const AttnPlan& pl) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gw = blockIdx.x * PNW + warp;
+  const int g = lane >> 3, sub = lane & 7;
+  if ((long long)gw * pl.per >= pl.tb) return;
+  int gb = gw * pl.per;
+  const int gb1 = min(pl.tb, gb + pl.per);
+  while (gb < gb1) {
+    // utterance of flattened block gb: the last one whose range starts at or before it
+    const unsigned cand = __ballot_sync(0xffffffffu, pl.nblk > 0 && pl.pb <= gb);
+    const int b = 31 - __clz(cand);
+    const int nb = __shfl_sync(0xffffffffu, pl.nblk, b), pbb = __shfl_sync(0xffffffffu, pl.pb, b), n = __shfl_sync(0xffffffffu, pl.n, b);
+    const int r = gb - pbb, h = r / nb, blk0 = r - h * nb;
+    const int cnt = min(gb1 - gb, nb - blk0);
+    const int s_first = pbb + h * nb;
+    const int w_first = s_first / pl.per, npieces = (s_first + nb - 1) / pl.per - w_first + 1;
+    const int piece = gw - w_first;
+    const int ja = blk0 * 32, jb = min(n, (blk0 + cnt) * 32), pos = n - 1;
+    gb += cnt;
+
+    const float* qrow = p.qkv + (size_t)b * (3 * kD) + h * kDH + sub * 8;
+    float q[8];
+    {
+      const float4 a = __ldcg(reinterpret_cast<const float4*>(qrow)), c = __ldcg(reinterpret_cast<const float4*>(qrow) + 1);
+      q[0] = a.x * 0.125f; q[1] = a.y * 0.125f; q[2] = a.z * 0.125f; q[3] = a.w * 0.125f;
+      q[4] = c.x * 0.125f; q[5] = c.y * 0.125f; q[6] = c.z * 0.125f; q[7] = c.w * 0.125f;
+    }
+    bf16* kb = reinterpret_cast<bf16*>(p.kc) + (size_t)layer * p.kv_layer_elems + ((size_t)b * kH + h) * p.ctx_cap * kDH;
+    bf16* vb = reinterpret_cast<bf16*>(p.vc) + (size_t)layer * p.kv_layer_elems + ((size_t)b * kH + h) * p.ctx_cap * kDH;
+    uint4 knew = make_uint4(0, 0, 0, 0), vnew = make_uint4(0, 0, 0, 0);   // the new row, bf16-rounded like the cached ones
+    if (jb == n) {
+      const float4 k0 = __ldcg(reinterpret_cast<const float4*>(qrow + kD)), k1 = __ldcg(reinterpret_cast<const float4*>(qrow + kD) + 1);
+      const float4 v0 = __ldcg(reinterpret_cast<const float4*>(qrow + 2 * kD)), v1 = __ldcg(reinterpret_cast<const float4*>(qrow + 2 * kD) + 1);
+      knew = make_uint4(pack_bf16x2(k0.x, k0.y), pack_bf16x2(k0.z, k0.w), pack_bf16x2(k1.x, k1.y), pack_bf16x2(k1.z, k1.w));
+      vnew = make_uint4(pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
+      if (g == 0) {   // KV append (modules/activation.py:148-152 re-allocates the whole cache instead)
+        *reinterpret_cast<uint4*>(kb + (size_t)pos * kDH + sub * 8) = knew;
+        *reinterpret_cast<uint4*>(vb + (size_t)pos * kDH + sub * 8) = vnew;
+      }
+    }
+    const bf16* kp = kb + (size_t)g * kDH + sub * 8;
+    const bf16* vp = vb + (size_t)g * kDH + sub * 8;
+    uint4 kr[8], vr[8];
+    auto load8 = [&](uint4 (&dst)[8], const bf16* base, const uint4& fresh, int j0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int j = j0 + 4 * i + g;
+        dst[i] = (j < jb && j != pos) ? __ldcg(reinterpret_cast<const uint4*>(base + (size_t)(j0 + 4 * i) * kDH)) : fresh;
+      }
+    };
+    float m = -INFINITY, l = 0.f;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    load8(kr, kp, knew, ja);
+    for (int j0 = ja; j0 < jb; j0 += 32) {
+      load8(vr, vp, vnew, j0);
+      float sc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float w[8];
+        unpack8(kr[i], w);
+        float d = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d = fmaf(q[e], w[e], d);
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        d += __shfl_xor_sync(0xffffffffu, d, 4);
+        sc[i] = (j0 + 4 * i + g < jb) ? d : -INFINITY;
+      }
+      if (j0 + 32 < jb) load8(kr, kp, knew, j0 + 32);
+      float bm = sc[0];
+#pragma unroll
+      for (int i = 1; i < 8; ++i) bm = fmaxf(bm, sc[i]);
+      bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 8));
+      bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 16));
+      const float mn = fmaxf(m, bm);              // finite: every block holds at least one key
+      const float scale = expf(m - mn);           // 0 on the first block (m = -inf)
+      l *= scale;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] *= scale;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float pr = expf(sc[i] - mn);        // 0 for masked keys
+        l += pr;
+        float w[8];
+        unpack8(vr[i], w);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(pr, w[e], acc[e]);
+      }
+      m = mn;
+    }
+    // fold the 4 key groups of the warp (fixed order)
+    l += __shfl_xor_sync(0xffffffffu, l, 8);
+    l += __shfl_xor_sync(0xffffffffu, l, 16);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
+      acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+    }
+    float* att = p.att + (size_t)b * kD + h * kDH;
+    if (npieces == 1) {   // the whole head in one segment
+      if (g == 0) {
+        const float inv = 1.0f / l;
+        *reinterpret_cast<float4*>(att + sub * 8) = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
+        *reinterpret_cast<float4*>(att + sub * 8 + 4) = make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
+      }
+      continue;
+    }
+    float* rec0 = p.part + ((size_t)b * kH + h) * p.att_maxp * kRec;
+    float* rec = rec0 + (size_t)piece * kRec;
+    if (g == 0) {
+      *reinterpret_cast<float4*>(rec + 4 + sub * 8) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(rec + 4 + sub * 8 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      if (sub == 0) *reinterpret_cast<float2*>(rec) = make_float2(m, l);
+    }
+    __syncwarp();
+    int last = 0;
+    if (lane == 0) {
+      __threadfence();       // the record is visible device-wide before the ticket is taken
+      last = (atomicAdd(p.tickets + b * kH + h, 1) == npieces - 1);
+      if (last) __threadfence();
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {
+      // fold the pieces in piece order: lane owns output dims 2*lane, 2*lane+1
+      float M = -INFINITY;
+      for (int s = lane; s < npieces; s += 32) M = fmaxf(M, __ldcg(rec0 + (size_t)s * kRec));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+      float L = 0.f, O0 = 0.f, O1 = 0.f;
+      for (int s0 = 0; s0 < npieces; s0 += 4) {
+        float2 ml[4], ov[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool ok = s0 + u < npieces;
+          const float* rs = rec0 + (size_t)(s0 + u) * kRec;
+          ml[u] = ok ? __ldcg(reinterpret_cast<const float2*>(rs)) : make_float2(-INFINITY, 0.f);
+          ov[u] = ok ? __ldcg(reinterpret_cast<const float2*>(rs + 4) + lane) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float w = expf(ml[u].x - M);
+          L = fmaf(w, ml[u].y, L);
+          O0 = fmaf(w, ov[u].x, O0);
+          O1 = fmaf(w, ov[u].y, O1);
+        }
+      }
+      const float inv = 1.0f / L;
+      *reinterpret_cast<float2*>(att + 2 * lane) = make_float2(O0 * inv, O1 * inv);
+      if (lane == 0) p.tickets[b * kH + h] = 0;   // next use is behind two grid barriers
+    }
+  }
+}
+
 template <int MR, bool PIPE>
 __global__ void __launch_bounds__(PNT, 1) ar_decode_mma_kernel(const PParams p) {
   using WT = bf16;
@@ -311,6 +509,8 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_mma_kernel(const PParams p) 
     ++steps;
     if (!p.ignore_eos && ld_cg(bt.n_active) <= 0) break;
     if (step == p.max_steps - 1) break;
+    AttnPlan plan{};
+    if (p.att_maxp > 0) plan = attn_plan(bt);   // contexts are fixed for the 12 layers of this step
 
     for (int l = 0; l < kL; ++l) {
       const PLayer& L = p.layer[l];
@@ -321,7 +521,7 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_mma_kernel(const PParams p) 
       const WT* W2 = reinterpret_cast<const WT*>(L.ff2_w) + (size_t)kc * kD;
       (void)Wq;
       // ---- P1: LN1 + QKV rows ----------------------------------------------------------------------------------------
-      for (int u = blockIdx.x; u < B * kH * p.nsplit; u += gridDim.x) {
+      for (int u = blockIdx.x; p.att_maxp == 0 && u < B * kH * p.nsplit; u += gridDim.x) {
         if (tid == 0) {
           const int split = u % p.nsplit, bh = u / p.nsplit, b = bh / kH, h = bh % kH;
           const int n = bt.S[b] + bt.P[b] + ld_cg(bt.T + b) + 1;
@@ -341,17 +541,23 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_mma_kernel(const PParams p) 
       gemv_finish_mma<MR>(pre, fh, fl, q0, q1, B, L.qkv_b, nullptr, red, zero,
                           [&](int n, int m, float v) { p.qkv[(size_t)m * 3 * kD + n] = v; });
       PSTAMP(4);
-      gemv_issue_mma(pre, Wo, kD, o0, o1);
+      if (p.att_maxp == 0) gemv_issue_mma(pre, Wo, kD, o0, o1);
       PSTAMP(5);
       grid_barrier(p.bar, epoch, prof);
       // ---- P2: attention (ticket fold) -----------------------------------------------------------------------------------
-      for (int u = blockIdx.x; u < B * kH * p.nsplit; u += gridDim.x) {
-        const int split = u % p.nsplit, bh = u / p.nsplit;
-        const int b = bh / kH, h = bh % kH;
-        if (ld_cg(bt.finished + b)) continue;
-        if constexpr (PIPE) attn_unit_pipe(p, l, b, h, split, scratch);
-        else attn_unit<bf16>(p, l, b, h, split, scratch);
+      if (p.att_maxp > 0) {
+        attn_phase_balanced(p, l, plan);       // no weight registers are held across this (long) phase
+        gemv_issue_mma(pre, Wo, kD, o0, o1);
+      } else {
+        for (int u = blockIdx.x; u < B * kH * p.nsplit; u += gridDim.x) {
+          const int split = u % p.nsplit, bh = u / p.nsplit;
+          const int b = bh / kH, h = bh % kH;
+          if (ld_cg(bt.finished + b)) continue;
+          if constexpr (PIPE) attn_unit_pipe(p, l, b, h, split, scratch);
+          else attn_unit<bf16>(p, l, b, h, split, scratch);
+        }
       }
+      PSTAMP(6);
       grid_barrier(p.bar, epoch, prof);
       // ---- P3: out-proj + residual -> xa ---------------------------------------------------------------------------------
       stage_plain_frag<MR>(fh, fl, B, [&](int m, int c) {

@@ -36,7 +36,8 @@ struct PParams {
   unsigned long long* part_ll;// [B][16][nsplit][66] two-barrier variant: attention partials, same packing
   int trim;                   // VX_DECODE_TRIM bit mask (fused == 4)
   int fused;                  // 0: 5-barrier kernel, 1: 3-barrier kernel (default for B <= 2), 2: two-barrier kernel (VX_DECODE_V4=1), 3: cluster/DSMEM two-barrier kernel (VX_DECODE_CLUSTER=1, B = 1), 4: trimmed 3-barrier kernel (VX_DECODE_TRIM=<bits>), 5: 3-barrier kernel with TMA-staged weights (VX_DECODE_TMA=1)
-  float* part;                // [B][16][nsplit][66]
+  float* part;                // [B][16][nsplit][66]  (balanced batched attention: [B][16][att_maxp][68])
+  int att_maxp;               // balanced batched attention (decode_mma.cu): max pieces per (utterance, head); 0 = CTA-per-head units
   int32_t* tickets;           // [B*16]
   unsigned int* bar;          // grid barrier counter (zeroed by the host)
   int nsplit;

@@ -898,6 +898,14 @@ int vx_ar_decode(vx_engine* e, int max_new, int top_k, float top_p, float temper
         pp.fused = 2;
       }
     }
+    {   // batched tensor-core kernel (B >= 5, bf16): balanced warp-level attention phase unless VX_DECODE_ATTN=0
+      const char* ab = getenv("VX_DECODE_ATTN");
+      const char* mm = getenv("VX_DECODE_MMA");
+      if (e->mode == VX_BF16 && B > 4 && !pp.fused && !(ab && ab[0] == '0') && !(mm && mm[0] == '0')) {
+        pp.att_maxp = e->num_sms + 2;   // pieces of one (utterance, head): <= warps/16 + 2
+        ENS(e->part, (size_t)B * kH * pp.att_maxp * (kDH + 4) * 4);
+      }
+    }
     pp.norm_g = e->ar_norm_g; pp.norm_b = e->ar_norm_b; pp.predict_w = e->ar_predict;
     pp.audio_emb = vec(e, "ar_audio_embedding.word_embeddings.weight"); pp.alpha = vec(e, "ar_audio_position.alpha"); pp.pe = e->pe;
     pp.kc = e->kc.p; pp.vc = e->vc.p; pp.kv_layer_elems = e->kv_layer_elems; pp.ctx_cap = e->ctx_cap;
