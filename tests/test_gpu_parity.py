@@ -146,24 +146,6 @@ def test_best_of_greedy_beams_agree():
     m.engine.close()
 
 
-def test_ring_decode_variant(monkeypatch):
-    """VX_DECODE_RING=1 selects the experimental decode variant that stages every weight slice in shared memory with
-    the TMA engine (cp.async.bulk ring, two phases ahead).  Same arithmetic up to summation order: teacher-forced
-    agreement with the reference's bf16-weight tokens like the default kernel."""
-    g = load_golden("tiny_en")
-    monkeypatch.setenv("VX_DECODE_RING", "1")
-    m = _valle(state_dict_for(g["seed"]), "bf16", max_ctx=256)
-    want = g["codes_bf16w"].astype(np.int64)
-    eng = m.engine
-    lang = m._lang_ids(len(g["x"]), int(g["Lp"]), g["prompt_language_arg"], g["text_language_arg"])
-    eng.set_batch([g["x"].astype(np.int32)], [lang], [g["prompt"].astype(np.int32)])
-    eng.ar_prefill()
-    toks, lens, _ = eng.ar_decode(top_k=1, forced=want[None, :, 0].astype(np.int32), ignore_eos=True)
-    assert int(lens[0]) == want.shape[0]
-    assert (toks[0, :want.shape[0]] == want[:, 0]).mean() > 0.97
-    eng.close()
-
-
 @pytest.mark.parametrize("names", [["tiny_en"], ["mid_ja"], ["tiny_en", "noprompt_en"]])
 def test_fused_decode_variant(monkeypatch, names):
     """VX_DECODE_FUSED=1 selects the 3-barrier persistent decode kernel (attention + out-proj and FFN1 + FFN2 fused,

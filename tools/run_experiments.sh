@@ -10,17 +10,16 @@ say() { echo "== $*" | tee -a "$out"; }
 
 say "parity of the variants that have not run on a GPU yet (VX_TEST_EXPERIMENTAL=1)"
 VX_TEST_EXPERIMENTAL=1 timeout 240 python -m pytest tests/test_gpu_decode_variants.py tests/test_gpu_kernels.py -m gpu -q \
-  -k "tma or cluster or trimmed or pipelined or two_barrier or t5max or tcgen05_attention" 2>&1 | tail -15 >> "$out"
+  -k "t5max or tcgen05_attention" 2>&1 | tail -15 >> "$out"
 
 say "batch-1 decode, us/step (default = 3-barrier fused kernel)"
-for v in "" "VX_DECODE_FUSED=0" "VX_DECODE_TMA=1" "VX_DECODE_CLUSTER=1" "VX_DECODE_V4=1" \
-         "VX_DECODE_TRIM=1" "VX_DECODE_TRIM=2" "VX_DECODE_TRIM=4" "VX_DECODE_TRIM=8" "VX_DECODE_TRIM=15"; do
+for v in "" "VX_DECODE_FUSED=0"; do
   echo "-- ${v:-default}" >> "$out"
   env $v VX_TIMELINE_ALL=0 timeout 60 python tools/decode_timeline.py 1 2>&1 | grep -E "us/step|us per phase|Error|error" | head -8 >> "$out"
 done
 
-say "batched decode (config 3), tensor-core GEMV phases; =2 adds pipelined P.V loads"
-for v in "" "VX_DECODE_MMA=2" "VX_DECODE_MMA=0"; do
+say "batched decode (config 3): default (balanced warp attention) / CTA-per-head attention units / CUDA-core GEMV kernel"
+for v in "" "VX_DECODE_ATTN=0" "VX_DECODE_MMA=0"; do
   for b in 8 32; do
     echo "-- ${v:-default} B=$b" >> "$out"
     env $v timeout 90 python tools/bench_configs.py --config 3 --batch $b --steps 300 --reps 1 2>&1 | tail -1 | cut -c1-260 >> "$out"

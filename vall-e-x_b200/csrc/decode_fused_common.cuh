@@ -1,6 +1,5 @@
-// Shared by the fused decode kernels (decode_fused.cu, decode_exchange.cu): fixed-point accumulators, staging with
-// residual write-back, the out-proj share prefetch, the attention unit with head rendezvous, the FFN2 share, and the
-// flag-carrying 8-byte exchange.
+// Device code of the fused decode kernel (decode_fused.cu): fixed-point accumulators, staging with residual
+// write-back, the out-proj share prefetch, the attention unit with head rendezvous, the FFN2 share.
 #pragma once
 #include "decode_common.cuh"
 
@@ -261,27 +260,6 @@ __device__ __forceinline__ void ffn2_share(const bf16* __restrict__ W2T, int f0,
   }
 }
 
-
-// ---- flag-carrying 8-byte exchange (value + epoch in one store; readers poll the data itself) ----------------------
-__device__ __forceinline__ void ll_store(unsigned long long* p, float v, uint32_t epoch) {
-  const unsigned long long w = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(v);
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
-}
-__device__ __forceinline__ unsigned long long ll_load(const unsigned long long* p) {
-  unsigned long long w;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
-  return w;
-}
-// poll one element until its flag carries `epoch`
-__device__ __forceinline__ float ll_wait(const unsigned long long* p, uint32_t epoch) {
-  unsigned long long w;
-  unsigned int spins = 0;
-  do {
-    w = ll_load(p);
-    if (++spins > (1u << 24)) __trap();
-  } while ((uint32_t)(w >> 32) != epoch);
-  return __uint_as_float((uint32_t)w);
-}
 
 
 }  // namespace

@@ -32,10 +32,7 @@ struct PParams {
   float* xb;                  // [B][1024] fused variant: residual stream after the attention block (xa holds the layer input)
   long long* acc_out;         // [2][B][1024] fused variant: out-proj sums, 2^-30 fixed point, by layer parity
   long long* acc_ffn;         // [2][B][1024] fused variant: FFN2 sums
-  unsigned long long* qkv_ll; // [B][16][192] two-barrier variant: q|k|v of a head, (epoch << 32 | float bits) per element
-  unsigned long long* part_ll;// [B][16][nsplit][66] two-barrier variant: attention partials, same packing
-  int trim;                   // VX_DECODE_TRIM bit mask (fused == 4)
-  int fused;                  // 0: 5-barrier kernel, 1: 3-barrier kernel (default for B <= 2), 2: two-barrier kernel (VX_DECODE_V4=1), 3: cluster/DSMEM two-barrier kernel (VX_DECODE_CLUSTER=1, B = 1), 4: trimmed 3-barrier kernel (VX_DECODE_TRIM=<bits>), 5: 3-barrier kernel with TMA-staged weights (VX_DECODE_TMA=1)
+  int fused;                  // 0: 5-barrier kernel, 1: 3-barrier kernel (default for B <= 2)
   float* part;                // [B][16][nsplit][66]  (balanced batched attention: [B][16][att_maxp][68])
   int att_maxp;               // balanced batched attention (decode_mma.cu): max pieces per (utterance, head); 0 = CTA-per-head units
   int32_t* tickets;           // [B*16]
@@ -57,12 +54,7 @@ int launch_decode_persistent(const void* params, int wt, int B, int grid, cudaSt
 
 // launchers of the kernel variants (one translation unit each); mr = padded batch rows
 cudaError_t launch_decode_fused(const PParams& p, int mr, int grid, cudaStream_t st);     // decode_fused.cu
-cudaError_t launch_decode_fused2(const PParams& p, int mr, int grid, cudaStream_t st);    // decode_fused.cu
-cudaError_t launch_decode_v4(const PParams& p, int mr, int grid, cudaStream_t st);        // decode_exchange.cu
-cudaError_t launch_decode_cluster(const PParams& p, cudaStream_t st);                     // decode_exchange.cu
 cudaError_t launch_decode_mma(const PParams& p, int mr, int grid, cudaStream_t st);       // decode_mma.cu
-cudaError_t launch_decode_tma(const PParams& p, int mr, int grid, cudaStream_t st);       // decode_tma.cu
 constexpr int kDecodeHS = 64;   // max hidden units per CTA of the fused kernels (kHS in decode_fused_common.cuh)
-constexpr int kDecodeCS = 8;    // cluster size of the cluster variant (kCS in decode_exchange.cu)
 
 }  // namespace vx

@@ -130,7 +130,7 @@ struct vx_engine {
   bool attn_t5_fuse = false;                         // VX_ATTN_T5=3: QKV GEMM epilogue writes the per-head operand images (NAR layers)                              // VX_ATTN_T5=1: tcgen05/TMEM attention instead of mma.sync
   int64_t full_rows = 0;                             // packed rows of the current full-sequence pass (128-aligned starts)
   Buf xs, xsn, qkvs, atts, ffs, logits, part, tick;  // decode-step scratch
-  Buf p_xb, p_acc, p_ll;                                 // fused decode variant: mid-layer residual, fixed-point accumulators
+  Buf p_xb, p_acc;                                 // fused decode variant: mid-layer residual, fixed-point accumulators
   Buf p_pf, p_bar, p_prof;                                   // persistent decode: FFN2 partials, barrier counter + steps
   int num_sms = 148;
   bool decode_graph = false;                         // VX_DECODE_GRAPH=1: per-step CUDA-graph path instead of the persistent kernel
@@ -429,7 +429,7 @@ void vx_destroy(vx_engine* e) {
   }
   Buf* bufs[] = {&e->d_flag, &e->d_text, &e->d_lang, &e->d_prompt, &e->d_S, &e->d_P, &e->d_ar_row0, &e->d_nar_row0, &e->d_T,
                  &e->d_ctx, &e->d_y, &e->d_budget, &e->d_fin, &e->d_slp, &e->d_nact, &e->x, &e->xn, &e->qkv, &e->att,
-                 &e->ffh, &e->kc, &e->vc, &e->a_img, &e->qkv16, &e->att_img, &e->h_img, &e->t_img, &e->q_img, &e->k_img, &e->vt_img, &e->xs, &e->xsn, &e->qkvs, &e->atts, &e->ffs, &e->logits, &e->part, &e->tick, &e->p_xb, &e->p_acc, &e->p_ll, &e->p_pf, &e->p_bar, &e->p_prof,
+                 &e->ffh, &e->kc, &e->vc, &e->a_img, &e->qkv16, &e->att_img, &e->h_img, &e->t_img, &e->q_img, &e->k_img, &e->vt_img, &e->xs, &e->xsn, &e->qkvs, &e->atts, &e->ffs, &e->logits, &e->part, &e->tick, &e->p_xb, &e->p_acc, &e->p_pf, &e->p_bar, &e->p_prof,
                  &e->lastmap, &e->out_tok, &e->forced, &e->yemb, &e->yrow0, &e->trow0, &e->tgtmap, &e->nlog, &e->codes,
                  &e->tl_dev, &e->cb0_dev, &e->v_codes, &e->v_feat, &e->v_col, &e->v_x, &e->v_h, &e->v_ff, &e->v_head,
                  &e->v_spec, &e->v_frames, &e->v_wave};
@@ -864,7 +864,7 @@ int vx_ar_decode(vx_engine* e, int max_new, int top_k, float top_p, float temper
     }
     // 3-barrier variant: one attention unit per CTA, bf16 weights, B <= 8; anything else takes the 5-barrier kernel
     pp.fused = (e->decode_fused && e->mode == VX_BF16 && B <= e->decode_fused_maxb && B * kH * ns <= e->num_sms &&
-                (kFF + e->num_sms - 1) / e->num_sms <= 64 && e->ar[0].ff2_t && !getenv("VX_DECODE_RING")) ? 1 : 0;
+                (kFF + e->num_sms - 1) / e->num_sms <= 64 && e->ar[0].ff2_t) ? 1 : 0;
     if (pp.fused) {
       ENS(e->p_xb, (size_t)B * kD * 4);
       ENS(e->p_acc, (size_t)4 * B * kD * 8);
@@ -873,30 +873,6 @@ int vx_ar_decode(vx_engine* e, int max_new, int top_k, float top_p, float temper
       pp.xb = (float*)e->p_xb.p;
       pp.acc_out = (long long*)e->p_acc.p;
       pp.acc_ffn = (long long*)e->p_acc.p + (size_t)2 * B * kD;
-      const char* tm = getenv("VX_DECODE_TMA");
-      if (tm && tm[0] == '1' && B <= 2) pp.fused = 5;   // experimental: weights staged by the TMA engine, one layer ahead
-      const char* tr = getenv("VX_DECODE_TRIM");
-      if (pp.fused == 1 && tr && atoi(tr) > 0 && ns <= 12) {   // experimental trimmed 3-barrier kernel (A/B switches)
-        const size_t np = (size_t)B * kH * ns * (kDH + 2);
-        ENS(e->p_ll, np * 8);
-        CK(cudaMemsetAsync(e->p_ll.p, 0, np * 8, st));
-        pp.part_ll = (unsigned long long*)e->p_ll.p;
-        pp.trim = atoi(tr);
-        pp.fused = 4;
-      }
-      const char* cl = getenv("VX_DECODE_CLUSTER");
-      if (pp.fused == 1 && cl && cl[0] == '1' && B == 1 && final_ctx <= 8 * 2048) {   // experimental cluster kernel: 8 key splits = one cluster per head
-        pp.fused = 3;
-      }
-      const char* v4 = getenv("VX_DECODE_V4");
-      if (pp.fused == 1 && v4 && v4[0] == '1' && ns <= 12) {   // experimental two-barrier kernel: flag-carrying exchange buffers, epochs restart per launch
-        const size_t nq = (size_t)B * kH * 3 * kDH, np = (size_t)B * kH * ns * (kDH + 2);
-        ENS(e->p_ll, (nq + np) * 8);
-        CK(cudaMemsetAsync(e->p_ll.p, 0, (nq + np) * 8, st));
-        pp.qkv_ll = (unsigned long long*)e->p_ll.p;
-        pp.part_ll = (unsigned long long*)e->p_ll.p + nq;
-        pp.fused = 2;
-      }
     }
     {   // batched tensor-core kernel (B >= 5, bf16): balanced warp-level attention phase unless VX_DECODE_ATTN=0
       const char* ab = getenv("VX_DECODE_ATTN");
@@ -911,7 +887,7 @@ int vx_ar_decode(vx_engine* e, int max_new, int top_k, float top_p, float temper
     pp.kc = e->kc.p; pp.vc = e->vc.p; pp.kv_layer_elems = e->kv_layer_elems; pp.ctx_cap = e->ctx_cap;
     pp.xa = (float*)e->xs.p; pp.pf = (float*)e->p_pf.p; pp.qkv = (float*)e->qkvs.p; pp.att = (float*)e->atts.p;
     pp.hid = (float*)e->ffs.p; pp.logits = (float*)e->logits.p; pp.part = (float*)e->part.p; pp.tickets = (int32_t*)e->tick.p;
-    pp.bar = (unsigned int*)e->p_bar.p; pp.nsplit = (pp.fused == 3) ? 8 : ns;
+    pp.bar = (unsigned int*)e->p_bar.p; pp.nsplit = ns;
     pp.top_k = top_k; pp.top_p = top_p; pp.temperature = temperature; pp.seed = seed; pp.ignore_eos = ignore_eos;
     pp.forced = forced_dev; pp.forced_stride = max_steps; pp.out_tokens = (int32_t*)e->out_tok.p; pp.out_stride = max_steps;
     pp.max_steps = max_steps; pp.steps_done = (int32_t*)((char*)e->p_bar.p + 32);
