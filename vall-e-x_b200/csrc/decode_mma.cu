@@ -1,4 +1,5 @@
-// Tensor-core batched decode kernel (8 <= B <= 32): the five GEMV phases of the 62-barrier loop on mma.sync.
+// Tensor-core batched decode kernel (5 <= B <= 32, bf16): the five GEMV phases of the 62-barrier loop on mma.sync, row-per-warp
+// activation staging, FFN2 split-K fold by ticket, balanced warp-level attention over the flattened key space.
 #include "decode_common.cuh"
 
 namespace vx {
@@ -34,56 +35,69 @@ __device__ __forceinline__ void frag_store(uint16_t* fh, uint16_t* fl, int m, in
   fl[idx] = __bfloat16_as_ushort(l);
 }
 
-template <int MR, typename Val>
-__device__ __forceinline__ void stage_ln_frag(uint16_t* fh, uint16_t* fl, int B, Val value, const LnPre& lp, float* red) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr int R = 8;
-  for (int mb = 0; mb < B; mb += R) {
-    const int nb = min(R, B - mb);
-    float v0[R], v1[R];
+// Row-per-warp staging: warp w stages batch rows w, w + 16 (MR = 32); a lane holds columns it*128 + lane*4 .. +3 of a row
+// (8 coalesced 16-byte loads, all rows' loads in flight at once), LayerNorm statistics are warp shuffles (no block-wide
+// reduction), and the normalised row goes straight into the hi/lo fragment images.  src(m) -> row pointer or nullptr (zeros).
+template <int MR, bool LN, typename Src>
+__device__ __forceinline__ void stage_rows_frag(uint16_t* fh, uint16_t* fl, int B, Src src, const float* __restrict__ gamma,
+                                                const float* __restrict__ beta) {
+  constexpr int NT = MR / 8;
+  constexpr int RPW = (MR + PNW - 1) / PNW;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 v[RPW][8];
 #pragma unroll
-    for (int m = 0; m < R; ++m) {
-      v0[m] = (m < nb) ? value(mb + m, tid) + lp.f0 : 0.f;
-      v1[m] = (m < nb) ? value(mb + m, tid + PNT) + lp.f1 : 0.f;
-    }
+  for (int r = 0; r < RPW; ++r) {
+    const int m = warp + r * PNW;
+    const float* row = (m < B) ? src(m) : nullptr;
 #pragma unroll
-    for (int m = 0; m < R; ++m) {
-      const float s = warp_sum(v0[m] + v1[m]);
-      if (lane == 0) red[warp * 8 + m] = s;
-    }
-    __syncthreads();
-    float mean[R];
+    for (int it = 0; it < 8; ++it)
+      v[r][it] = row ? __ldcg(reinterpret_cast<const float4*>(row + it * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
 #pragma unroll
-    for (int m = 0; m < R; ++m) {
-      float s = 0.f;
-#pragma unroll
-      for (int w = 0; w < PNW; ++w) s += red[w * 8 + m];
-      mean[m] = s / (float)kD;
-    }
-#pragma unroll
-    for (int m = 0; m < R; ++m) {
-      const float d0 = v0[m] - mean[m], d1 = v1[m] - mean[m];
-      const float s = warp_sum(d0 * d0 + d1 * d1);
-      if (lane == 0) red[PNW * 8 + warp * 8 + m] = s;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int m = 0; m < R; ++m) {
-      if (m < nb) {
+  for (int r = 0; r < RPW; ++r) {
+    const int m = warp + r * PNW;
+    if (m < MR) {   // warp-uniform (MR = 8: warps 8..15 have no row)
+      float mean = 0.f, rstd = 1.f;
+      if constexpr (LN) {
         float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < PNW; ++w) s += red[PNW * 8 + w * 8 + m];
-        const float rstd = 1.0f / sqrtf(s / (float)kD + 1e-5f);
-        frag_store<MR>(fh, fl, mb + m, tid, __fadd_rn(__fmul_rn((v0[m] - mean[m]) * rstd, lp.g0), lp.b0));
-        frag_store<MR>(fh, fl, mb + m, tid + PNT, __fadd_rn(__fmul_rn((v1[m] - mean[m]) * rstd, lp.g1), lp.b1));
+        for (int it = 0; it < 8; ++it) s += (v[r][it].x + v[r][it].y) + (v[r][it].z + v[r][it].w);
+        mean = warp_sum(s) / (float)kD;
+        float q = 0.f;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const float d0 = v[r][it].x - mean, d1 = v[r][it].y - mean, d2 = v[r][it].z - mean, d3 = v[r][it].w - mean;
+          q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+        }
+        rstd = 1.0f / sqrtf(warp_sum(q) / (float)kD + 1e-5f);
+      }
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        float x[4] = {v[r][it].x, v[r][it].y, v[r][it].z, v[r][it].w};
+        if constexpr (LN) {
+          const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + it * 128 + lane * 4));
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(beta + it * 128 + lane * 4));
+          x[0] = __fadd_rn(__fmul_rn((x[0] - mean) * rstd, g.x), bb.x);
+          x[1] = __fadd_rn(__fmul_rn((x[1] - mean) * rstd, g.y), bb.y);
+          x[2] = __fadd_rn(__fmul_rn((x[2] - mean) * rstd, g.z), bb.z);
+          x[3] = __fadd_rn(__fmul_rn((x[3] - mean) * rstd, g.w), bb.w);
+        }
+        // fragment image slot of (m, c = it*128 + lane*4 .. +3): kg = it, ch = lane >> 3, q = (lane >> 1) & 3, e = (lane & 1) * 4
+        const size_t idx = (((((size_t)it * 4 + (lane >> 3)) * NT + (m >> 3)) * 32) + (m & 7) * 4 + ((lane >> 1) & 3)) * 8 + (lane & 1) * 4;
+        uint32_t hw[2], lw[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * e]), h1 = __float2bfloat16_rn(x[2 * e + 1]);
+          const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * e] - __bfloat162float(h0));
+          const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * e + 1] - __bfloat162float(h1));
+          hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+          lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        }
+        *reinterpret_cast<uint2*>(fh + idx) = make_uint2(hw[0], hw[1]);
+        *reinterpret_cast<uint2*>(fl + idx) = make_uint2(lw[0], lw[1]);
       }
     }
-    __syncthreads();
   }
-}
-template <int MR, typename Val>
-__device__ __forceinline__ void stage_plain_frag(uint16_t* fh, uint16_t* fl, int B, Val value) {
-  for (int i = threadIdx.x; i < B * kD; i += PNT) frag_store<MR>(fh, fl, i / kD, i % kD, value(i / kD, i % kD));
   __syncthreads();
 }
 
@@ -101,14 +115,24 @@ __device__ __forceinline__ void gemv_issue_mma(MPre& pre, const bf16* __restrict
 }
 
 // rows [r0,r1) x batch: tensor-core partial tiles, fixed-order reduction over the 8 k-groups, then
-// emit(n, m, dot + addend(n, m) + bias[n] + bias2[n]).  red: [8][32][MR] floats.
+// emit(n, m, dot + addend(n, m) + bias[n] + bias2[n]).  red: [8][32][MR + 1] floats (odd stride: the transposed read is
+// conflict-free).  The addends are requested BEFORE the tensor-core loop (they do not depend on it), and consecutive threads
+// emit consecutive rows n of one batch entry, so the global stores are 128-byte runs.
 template <int MR, typename Add, typename Emit>
 __device__ __forceinline__ void gemv_finish_mma(const MPre& pre, const uint16_t* fh, const uint16_t* fl, int r0, int r1, int B,
                                                 const float* __restrict__ bias, const float* __restrict__ bias2, float* red,
                                                 Add addend, Emit emit) {
   constexpr int NT = MR / 8;
+  constexpr int RS = MR + 1;
+  constexpr int NOUT = (32 * MR + PNT - 1) / PNT;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int mt = warp & 1, kg = warp >> 1, g = lane >> 2, q = lane & 3;
+  float ad[NOUT];
+#pragma unroll
+  for (int i = 0; i < NOUT; ++i) {
+    const int t = tid + i * PNT, row = t & 31, m = t >> 5, n = r0 + row;
+    ad[i] = (m < B && n < r1) ? (addend(n, m) + (bias ? bias[n] : 0.f) + (bias2 ? bias2[n] : 0.f)) : 0.f;
+  }
   float c[NT][4];
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) { c[nt][0] = 0.f; c[nt][1] = 0.f; c[nt][2] = 0.f; c[nt][3] = 0.f; }
@@ -129,139 +153,24 @@ __device__ __forceinline__ void gemv_finish_mma(const MPre& pre, const uint16_t*
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) {
     const int row = mt * 16 + g, n = nt * 8 + q * 2;
-    float* d0 = red + ((size_t)kg * 32 + row) * MR + n;
-    float* d1 = red + ((size_t)kg * 32 + row + 8) * MR + n;
+    float* d0 = red + ((size_t)kg * 32 + row) * RS + n;
+    float* d1 = red + ((size_t)kg * 32 + row + 8) * RS + n;
     d0[0] = c[nt][0]; d0[1] = c[nt][1];
     d1[0] = c[nt][2]; d1[1] = c[nt][3];
   }
   __syncthreads();
-  for (int t = tid; t < 32 * MR; t += PNT) {
-    const int row = t / MR, m = t % MR, n = r0 + row;
-    if (n < r1 && m < B) {
+#pragma unroll
+  for (int i = 0; i < NOUT; ++i) {
+    const int t = tid + i * PNT, row = t & 31, m = t >> 5, n = r0 + row;
+    if (m < B && n < r1) {
       float s = 0.f;
 #pragma unroll
-      for (int k8 = 0; k8 < 8; ++k8) s += red[((size_t)k8 * 32 + row) * MR + m];
-      emit(n, m, s + (addend(n, m) + (bias ? bias[n] : 0.f) + (bias2 ? bias2[n] : 0.f)));
+      for (int k8 = 0; k8 < 8; ++k8) s += red[((size_t)k8 * 32 + row) * RS + m];
+      emit(n, m, s + ad[i]);
     }
   }
   __syncthreads();
 }
-
-// attention unit of the batched kernel with a pipelined P.V loop (PIPE = true; VX_DECODE_MMA=2).  Same arithmetic and
-// summation order as attn_unit<bf16>: a lane still walks its keys in increasing order, only the loads are issued ahead.
-__device__ void attn_unit_pipe(const PParams& p, int layer, int b, int h, int split, float* smem) {
-  float* sq = smem;                  // [64]
-  float* sknew = smem + 64;          // [64]
-  float* svnew = smem + 128;         // [64]
-  float* red = smem + 192;           // [32]
-  int* s_last = reinterpret_cast<int*>(smem + 224);
-  float* sp = smem + 256;            // [PCHUNK]
-  float* sacc = sp + PCHUNK;         // [PNT/8][64]
-  const Batch& bt = p.bt;
-  const int tid = threadIdx.x;
-  const int pos = bt.S[b] + bt.P[b] + ld_cg(bt.T + b);
-  const int n = pos + 1;
-  int chunk = (n + p.nsplit - 1) / p.nsplit;
-  chunk = (chunk + 31) & ~31;
-  const int j0 = split * chunk, j1 = min(n, j0 + chunk);
-  const float* row = p.qkv + (size_t)b * (3 * kD) + h * kDH;
-  __syncthreads();  // smem reuse across units
-  if (tid < kDH) {
-    sq[tid] = __ldcg(row + tid) * 0.125f;
-    sknew[tid] = __ldcg(row + kD + tid);
-    svnew[tid] = __ldcg(row + 2 * kD + tid);
-  }
-  __syncthreads();
-  bf16* kb = reinterpret_cast<bf16*>(p.kc) + (size_t)layer * p.kv_layer_elems + ((size_t)b * kH + h) * p.ctx_cap * kDH;
-  bf16* vb = reinterpret_cast<bf16*>(p.vc) + (size_t)layer * p.kv_layer_elems + ((size_t)b * kH + h) * p.ctx_cap * kDH;
-  if (split == 0 && tid < kDH) {
-    store_as(kb + (size_t)pos * kDH + tid, sknew[tid]);
-    store_as(vb + (size_t)pos * kDH + tid, svnew[tid]);
-  }
-  float mloc = -INFINITY;
-  for (int j = j0 + tid; j < j1; j += PNT) {
-    float s = 0.f;
-    if (j == pos) {
-#pragma unroll
-      for (int d = 0; d < kDH; ++d) s = fmaf(sq[d], kv_round<bf16>(sknew[d]), s);
-    } else {
-      const bf16* kr = kb + (size_t)j * kDH;
-#pragma unroll
-      for (int d = 0; d < kDH; d += 8) {
-        float w[8];
-        ldkv8(kr + d, w);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) s = fmaf(sq[d + i], w[i], s);
-      }
-    }
-    sp[j - j0] = s;
-    mloc = fmaxf(mloc, s);
-  }
-  const float m = block_max(mloc, red);
-  float lloc = 0.f;
-  for (int j = j0 + tid; j < j1; j += PNT) {
-    const float pr = expf(sp[j - j0] - m);
-    sp[j - j0] = pr;
-    lloc += pr;
-  }
-  const float l = block_sum(lloc, red);
-  constexpr int NG = PNT / 8;
-  const int g = tid >> 3, dc = (tid & 7) * 8;
-  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  // P.V with 8 value chunks in flight per lane (a batched unit holds ALL keys of its head: ~20 keys per lane group; one
-  // load per loop trip would put 20 dependent memory round trips on the critical path)
-  constexpr int UV = 8;
-  for (int jb = j0 + g; jb < j1; jb += NG * UV) {
-    uint4 raw[UV];
-    float prs[UV];
-#pragma unroll
-    for (int u = 0; u < UV; ++u) {
-      const int j = jb + u * NG;
-      const bool ok = j < j1;
-      raw[u] = (ok && j != pos) ? __ldcg(reinterpret_cast<const uint4*>(vb + (size_t)j * kDH + dc)) : make_uint4(0, 0, 0, 0);
-      prs[u] = ok ? sp[j - j0] : 0.f;
-    }
-#pragma unroll
-    for (int u = 0; u < UV; ++u) {
-      const int j = jb + u * NG;
-      float w[8];
-      if (j == pos) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) w[i] = kv_round<bf16>(svnew[dc + i]);
-      } else {
-        raw_to_f32<bf16>(&raw[u], 0, w);
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = fmaf(prs[u], w[i], acc[i]);
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) sacc[g * kDH + dc + i] = acc[i];
-  __syncthreads();
-  float od = 0.f;
-  if (tid < kDH) {
-    for (int q = 0; q < NG; ++q) od += sacc[q * kDH + tid];
-  }
-  // partial (m, l, o[64]) of this split.  The LAST split of (b, h) to arrive (ticket) folds all of them in fixed split
-  // order -- deterministic whoever is last -- into att[b][h*64 ..], so the out-proj phase stages 4 KB per utterance
-  // instead of every CTA gathering all partials.
-  float* pp = p.part + (((size_t)b * kH + h) * p.nsplit + split) * (kDH + 2);
-  if (tid < kDH) pp[2 + tid] = od;
-  if (tid == 0) { pp[0] = m; pp[1] = l; }
-  if (p.dbg & 2) return;   // bisecting aid: the out-proj phase folds the splits itself
-  __syncthreads();
-  if (tid == 0) {
-    __threadfence();       // the CTA's partial is visible device-wide before the ticket is taken
-    *s_last = (atomicAdd(p.tickets + b * kH + h, 1) == p.nsplit - 1);
-  }
-  __syncthreads();
-  if (*s_last) {
-    __threadfence();
-    if (tid < kDH) p.att[(size_t)b * kD + h * kDH + tid] = att_combined(p, b, h * kDH + tid);
-    if (tid == 0) p.tickets[b * kH + h] = 0;   // next use is behind a grid barrier
-  }
-}
-
 
 // =================================================================================================================
 // Balanced warp-level attention phase of the batched kernel (modules/activation.py:142-167 for one new query row).
@@ -461,31 +370,63 @@ __device__ void attn_phase_balanced(const PParams& p, int layer, const AttnPlan&
   }
 }
 
-template <int MR, bool PIPE>
+// ---- L2 prefetch of the NEXT layer's keys / values (issued when the attention phase of this layer is over) --------------------
+// The GEMV phases leave HBM idle for ~40 us per layer while the attention phase is bandwidth-bound, so a share of the next
+// attention phase's KV rows (frac16/16 of the 32-key blocks, interleaved so L2 hits and HBM reads overlap) is pulled into
+// the 126 MB L2 by the TMA engine's prefetch path.  Same walk over the flattened key space as attn_phase_balanced: the warp
+// that will read a block asks for it.
+__device__ void kv_prefetch_balanced(const PParams& p, int layer, const AttnPlan& pl, int frac16) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gw = blockIdx.x * PNW + warp;
+  if (frac16 <= 0 || (long long)gw * pl.per >= pl.tb) return;
+  int gb = gw * pl.per;
+  const int gb1 = min(pl.tb, gb + pl.per);
+  while (gb < gb1) {
+    const unsigned cand = __ballot_sync(0xffffffffu, pl.nblk > 0 && pl.pb <= gb);
+    const int b = 31 - __clz(cand);
+    const int nb = __shfl_sync(0xffffffffu, pl.nblk, b), pbb = __shfl_sync(0xffffffffu, pl.pb, b), n = __shfl_sync(0xffffffffu, pl.n, b);
+    const int r = gb - pbb, h = r / nb, blk0 = r - h * nb;
+    const int cnt = min(gb1 - gb, nb - blk0);
+    const size_t base = (size_t)layer * p.kv_layer_elems + ((size_t)b * kH + h) * p.ctx_cap * kDH;
+    for (int i = lane; i < cnt; i += 32) {
+      const int gbi = gb + i;
+      if ((((gbi + 1) * frac16) >> 4) == ((gbi * frac16) >> 4)) continue;
+      const int j0 = (blk0 + i) * 32, nk = min(32, n - 1 - j0);   // row n-1 is written by that layer's attention phase
+      if (nk <= 0) continue;
+      const char* kp = reinterpret_cast<const char*>(p.kc) + (base + (size_t)j0 * kDH) * sizeof(bf16);
+      const char* vp = reinterpret_cast<const char*>(p.vc) + (base + (size_t)j0 * kDH) * sizeof(bf16);
+      const unsigned int bytes = (unsigned int)nk * kDH * (unsigned int)sizeof(bf16);
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(kp), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(vp), "r"(bytes) : "memory");
+    }
+    gb += cnt;
+  }
+}
+
+template <int MR>
 __global__ void __launch_bounds__(PNT, 1) ar_decode_mma_kernel(const PParams p) {
   using WT = bf16;
   extern __shared__ __align__(16) float dsm[];
   uint16_t* fh = reinterpret_cast<uint16_t*>(dsm);        // [MR*1024] hi halves, fragment order
   uint16_t* fl = fh + MR * kD;                             // [MR*1024] lo halves
-  float* scratch = dsm + MR * kD;                          // attention / sampling / LN scratch
-  float* red = scratch;                                    // [8][32][MR] partial tiles (GEMV phases only)
+  float* scratch = dsm + MR * kD;                          // sampling scratch / partial tiles
+  float* red = scratch;                                    // [8][32][MR + 1] partial tiles (GEMV phases only)
+  __shared__ int s_fold;
   const Batch& bt = p.bt;
   const int B = bt.B;
   const int tid = threadIdx.x;
   unsigned int epoch = 0;
-  const size_t wsz = sizeof(WT);
 
   int q0, q1, o0, o1, f0, f1, pr0, pr1;
   slice(3 * kD, q0, q1);
   slice(kD, o0, o1);
   slice(kFF, f0, f1);
   slice(kARLogits, pr0, pr1);
+  // FFN2 is split 4 ways over K: CTA (kc, i) multiplies rows [g0,g1) by hidden units [kc*1024, +1024)  (grid % 4 == 0)
   const int per = gridDim.x / 4;
-  const int kc = min((int)blockIdx.x / per, 3);
-  const int kc_first = kc * per;
-  const int kc_n = (kc == 3) ? (int)gridDim.x - kc_first : per;
-  const int g0 = (int)(((long long)(blockIdx.x - kc_first) * kD) / kc_n);
-  const int g1 = (int)(((long long)(blockIdx.x - kc_first + 1) * kD) / kc_n);
+  const int kc = (int)blockIdx.x / per, gi = (int)blockIdx.x - kc * per;
+  const int g0 = (int)(((long long)gi * kD) / per), g1 = (int)(((long long)(gi + 1) * kD) / per);
+  int32_t* fold_ticket = p.tickets + B * kH + gi;
 
   MPre pre;
   LnPre lp;
@@ -496,6 +437,7 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_mma_kernel(const PParams p) 
   long long* prof = nullptr;
   const int prof_slot = (blockIdx.x == 0) ? 0 : (blockIdx.x == gridDim.x / 2) ? 1 : (blockIdx.x == gridDim.x - 1) ? 2 : -1;
   auto zero = [](int, int) { return 0.f; };
+  auto xa_row = [&](int m) -> const float* { return p.xa + (size_t)m * kD; };
 
   int steps = 0;
   for (int step = 0; step < p.max_steps; ++step) {
@@ -503,78 +445,49 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_mma_kernel(const PParams p) 
       if (step == p.prof_step0) prof = p.prof + (size_t)prof_slot * 4096;
       if (step == p.prof_step0 + 4) prof = nullptr;
     }
+    // ---- S0: sample, append, embed the new token -> xa (models/vallex.py:529-531,568-598) -------------------------------
     for (int b = blockIdx.x; b < B; b += gridDim.x)
       if (!ld_cg(bt.finished + b)) sample_utterance(p, b, scratch);
     grid_barrier(p.bar, epoch, prof);
     ++steps;
     if (!p.ignore_eos && ld_cg(bt.n_active) <= 0) break;
     if (step == p.max_steps - 1) break;
-    AttnPlan plan{};
-    if (p.att_maxp > 0) plan = attn_plan(bt);   // contexts are fixed for the 12 layers of this step
+    const AttnPlan plan = attn_plan(bt);   // contexts are fixed for the 12 layers of this step
+    // share of a layer's KV blocks to pull into L2 ahead of its attention phase: all of them while one layer's keys and values
+    // (8 KB per block) fit the budget (p.kv_l2_mb, default 80 of the 126 MB), else that fraction
+    const int pf16 = (p.kv_l2_mb <= 0) ? 0 : (int)min(16ll, (16ll * p.kv_l2_mb * 128) / max(plan.tb, 1));
 
     for (int l = 0; l < kL; ++l) {
       const PLayer& L = p.layer[l];
-      const float* fb_prev = (l > 0) ? p.layer[l - 1].ff2_b : nullptr;
-      const WT* Wq = reinterpret_cast<const WT*>(L.qkv_w);
       const WT* Wo = reinterpret_cast<const WT*>(L.out_w);
       const WT* W1 = reinterpret_cast<const WT*>(L.ff1_w);
       const WT* W2 = reinterpret_cast<const WT*>(L.ff2_w) + (size_t)kc * kD;
-      (void)Wq;
-      // ---- P1: LN1 + QKV rows ----------------------------------------------------------------------------------------
-      for (int u = blockIdx.x; p.att_maxp == 0 && u < B * kH * p.nsplit; u += gridDim.x) {
-        if (tid == 0) {
-          const int split = u % p.nsplit, bh = u / p.nsplit, b = bh / kH, h = bh % kH;
-          const int n = bt.S[b] + bt.P[b] + ld_cg(bt.T + b) + 1;
-          int chunk = (n + p.nsplit - 1) / p.nsplit;
-          chunk = (chunk + 31) & ~31;
-          const int j0 = split * chunk, j1 = min(n - 1, j0 + chunk);
-          if (j1 > j0) {
-            const size_t off = ((size_t)l * p.kv_layer_elems + ((size_t)b * kH + h) * p.ctx_cap * kDH + (size_t)j0 * kDH) * wsz;
-            l2_prefetch(reinterpret_cast<const char*>(p.kc) + off, (size_t)(j1 - j0) * kDH * wsz);
-            l2_prefetch(reinterpret_cast<const char*>(p.vc) + off, (size_t)(j1 - j0) * kDH * wsz);
-          }
-        }
-      }
-      ln_load(lp, L.n1_g, L.n1_b, fb_prev);
-      stage_ln_frag<MR>(fh, fl, B, [&](int m, int c) { return stream_dyn(p, l, m, c, B); }, lp, scratch);
+      // ---- P1: LN1(x_l) + QKV rows (x_l is complete in xa: the FFN2 fold of layer l-1 wrote it) ---------------------------
+      stage_rows_frag<MR, true>(fh, fl, B, xa_row, L.n1_g, L.n1_b);
       PSTAMP(3);
       gemv_finish_mma<MR>(pre, fh, fl, q0, q1, B, L.qkv_b, nullptr, red, zero,
                           [&](int n, int m, float v) { p.qkv[(size_t)m * 3 * kD + n] = v; });
       PSTAMP(4);
-      if (p.att_maxp == 0) gemv_issue_mma(pre, Wo, kD, o0, o1);
-      PSTAMP(5);
       grid_barrier(p.bar, epoch, prof);
-      // ---- P2: attention (ticket fold) -----------------------------------------------------------------------------------
-      if (p.att_maxp > 0) {
-        attn_phase_balanced(p, l, plan);       // no weight registers are held across this (long) phase
-        gemv_issue_mma(pre, Wo, kD, o0, o1);
-      } else {
-        for (int u = blockIdx.x; u < B * kH * p.nsplit; u += gridDim.x) {
-          const int split = u % p.nsplit, bh = u / p.nsplit;
-          const int b = bh / kH, h = bh % kH;
-          if (ld_cg(bt.finished + b)) continue;
-          if constexpr (PIPE) attn_unit_pipe(p, l, b, h, split, scratch);
-          else attn_unit<bf16>(p, l, b, h, split, scratch);
-        }
-      }
+      // ---- P2: attention over the flattened key space; no weight registers are held across this (long) phase ------------
+      attn_phase_balanced(p, l, plan);
+      gemv_issue_mma(pre, Wo, kD, o0, o1);
       PSTAMP(6);
       grid_barrier(p.bar, epoch, prof);
-      // ---- P3: out-proj + residual -> xa ---------------------------------------------------------------------------------
-      stage_plain_frag<MR>(fh, fl, B, [&](int m, int c) {
-        if (ld_cg(bt.finished + m)) return 0.f;
-        return (p.dbg & 2) ? att_combined(p, m, c) : __ldcg(p.att + (size_t)m * kD + c);
-      });
+      // ---- P3: out-proj + residual -> xa -------------------------------------------------------------------------------
+      kv_prefetch_balanced(p, (l + 1 < kL) ? l + 1 : 0, plan, pf16);   // next layer (or layer 0 of the next step)
+      stage_rows_frag<MR, false>(fh, fl, B, [&](int m) -> const float* { return ld_cg(bt.finished + m) ? nullptr : p.att + (size_t)m * kD; },
+                                 nullptr, nullptr);
       PSTAMP(3);
-      gemv_finish_mma<MR>(pre, fh, fl, o0, o1, B, L.out_b, fb_prev, red, [&](int n, int m) { return stream_dyn(p, l, m, n, B); },
+      gemv_finish_mma<MR>(pre, fh, fl, o0, o1, B, L.out_b, nullptr, red, [&](int n, int m) { return __ldcg(p.xa + (size_t)m * kD + n); },
                           [&](int n, int m, float v) { p.xa[(size_t)m * kD + n] = v; });
       PSTAMP(4);
       gemv_issue_mma(pre, W1, kD, f0, f1);
       ln_issue(lp, L.n2_g, L.n2_b, nullptr);
       PSTAMP(5);
       grid_barrier(p.bar, epoch, prof);
-      // ---- P4: LN2 + FFN1 + ReLU -----------------------------------------------------------------------------------------
-      ln_load(lp, L.n2_g, L.n2_b, nullptr);
-      stage_ln_frag<MR>(fh, fl, B, [&](int m, int c) { return __ldcg(p.xa + (size_t)m * kD + c); }, lp, scratch);
+      // ---- P4: LN2 + FFN1 + ReLU ---------------------------------------------------------------------------------------
+      stage_rows_frag<MR, true>(fh, fl, B, xa_row, L.n2_g, L.n2_b);
       PSTAMP(3);
       gemv_finish_mma<MR>(pre, fh, fl, f0, f1, B, L.ff1_b, nullptr, red, zero,
                           [&](int n, int m, float v) { p.hid[(size_t)m * kFF + n] = fmaxf(v, 0.f); });
@@ -582,24 +495,42 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_mma_kernel(const PParams p) 
       gemv_issue_mma(pre, W2, kFF, g0, g1);
       PSTAMP(5);
       grid_barrier(p.bar, epoch, prof);
-      // ---- P5: FFN2, split-K -----------------------------------------------------------------------------------------------
-      stage_plain_frag<MR>(fh, fl, B, [&](int m, int c) { return __ldcg(p.hid + (size_t)m * kFF + kc * kD + c); });
+      // ---- P5: FFN2 split-K x4; the last of the four k-quarter CTAs of a row group folds the partials (fixed order), the
+      //          bias and the residual into xa, so every consumer reads ONE value per element ------------------------------
+      stage_rows_frag<MR, false>(fh, fl, B, [&](int m) -> const float* { return p.hid + (size_t)m * kFF + kc * kD; }, nullptr, nullptr);
       PSTAMP(3);
       gemv_finish_mma<MR>(pre, fh, fl, g0, g1, B, nullptr, nullptr, red, zero,
                           [&](int n, int m, float v) { p.pf[((size_t)kc * B + m) * kD + n] = v; });
       PSTAMP(4);
       if (l + 1 < kL) {
         gemv_issue_mma(pre, reinterpret_cast<const WT*>(p.layer[l + 1].qkv_w), kD, q0, q1);
-        ln_issue(lp, p.layer[l + 1].n1_g, p.layer[l + 1].n1_b, L.ff2_b);
+        ln_issue(lp, p.layer[l + 1].n1_g, p.layer[l + 1].n1_b, nullptr);
       } else {
         gemv_issue_mma(pre, reinterpret_cast<const WT*>(p.predict_w), kD, pr0, pr1);
-        ln_issue(lp, p.norm_g, p.norm_b, L.ff2_b);
+        ln_issue(lp, p.norm_g, p.norm_b, nullptr);
       }
+      if (tid == 0) {
+        __threadfence();       // this CTA's partial tile is visible device-wide before the ticket is taken
+        s_fold = (atomicAdd(fold_ticket, 1) == 3);
+        if (s_fold) __threadfence();
+      }
+      __syncthreads();
+      if (s_fold) {
+        const int nr = g1 - g0;
+        for (int t = tid; t < nr * B; t += PNT) {
+          const int m = t / nr, n = g0 + t - m * nr;
+          float s4 = 0.f;
+#pragma unroll
+          for (int sp = 0; sp < 4; ++sp) s4 += __ldcg(p.pf + ((size_t)sp * B + m) * kD + n);
+          p.xa[(size_t)m * kD + n] = (__ldcg(p.xa + (size_t)m * kD + n) + s4) + L.ff2_b[n];
+        }
+        if (tid == 0) *fold_ticket = 0;   // next use is behind four grid barriers
+      }
+      PSTAMP(5);
       grid_barrier(p.bar, epoch, prof);
     }
-    // ---- PF ------------------------------------------------------------------------------------------------------------------
-    ln_load(lp, p.norm_g, p.norm_b, p.layer[kL - 1].ff2_b);
-    stage_ln_frag<MR>(fh, fl, B, [&](int m, int c) { return stream_dyn(p, kL, m, c, B); }, lp, scratch);
+    // ---- PF: final LayerNorm + predict rows -> logits ----------------------------------------------------------------------
+    stage_rows_frag<MR, true>(fh, fl, B, xa_row, p.norm_g, p.norm_b);
     gemv_finish_mma<MR>(pre, fh, fl, pr0, pr1, B, nullptr, nullptr, red, zero,
                         [&](int n, int m, float v) { p.logits[(size_t)m * kARLogits + n] = v; });
     gemv_issue_mma(pre, Wqkv0, kD, q0, q1);
@@ -609,38 +540,30 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_mma_kernel(const PParams p) 
   if (blockIdx.x == 0 && tid == 0) *p.steps_done = steps;
 }
 
-template <int MR, bool PIPE>
+template <int MR>
 static cudaError_t mma_launch(const PParams& p, int grid, cudaStream_t st) {
-  const size_t scratch_floats = 256 + PCHUNK + (PNT / 8) * kDH;
+  if (grid % 4 != 0 || p.att_maxp <= 0) return cudaErrorInvalidConfiguration;   // FFN2 k-quarters; balanced attention buffers
   const size_t sample_floats = 1032 + PSORT + PSORT / 2 + PNT + 32 + 8;
-  const size_t red_floats = (size_t)8 * 32 * MR;
-  const size_t smem = ((size_t)MR * kD + std::max(std::max(scratch_floats, sample_floats), red_floats)) * sizeof(float);
-  cudaError_t e = cudaFuncSetAttribute(ar_decode_mma_kernel<MR, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t red_floats = (size_t)8 * 32 * (MR + 1);
+  const size_t smem = ((size_t)MR * kD + std::max(sample_floats, red_floats)) * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(ar_decode_mma_kernel<MR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ar_decode_mma_kernel<MR, PIPE>, PNT, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ar_decode_mma_kernel<MR>, PNT, smem);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) return cudaErrorLaunchOutOfResources;
   void* args[] = {(void*)&p};
-  return cudaLaunchCooperativeKernel((void*)ar_decode_mma_kernel<MR, PIPE>, dim3(grid), dim3(PNT), args, smem, st);
+  return cudaLaunchCooperativeKernel((void*)ar_decode_mma_kernel<MR>, dim3(grid), dim3(PNT), args, smem, st);
 }
 
 
 }  // namespace
 
 cudaError_t launch_decode_mma(const PParams& p, int mr, int grid, cudaStream_t st) {
-  const char* env = getenv("VX_DECODE_MMA");
-  if (env && env[0] == '2') {   // experimental: pipelined P.V loads in the attention phase
-    switch (mr) {
-      case 8: return mma_launch<8, true>(p, grid, st);
-      case 16: return mma_launch<16, true>(p, grid, st);
-      default: return mma_launch<32, true>(p, grid, st);
-    }
-  }
   switch (mr) {
-    case 8: return mma_launch<8, false>(p, grid, st);
-    case 16: return mma_launch<16, false>(p, grid, st);
-    default: return mma_launch<32, false>(p, grid, st);
+    case 8: return mma_launch<8>(p, grid, st);
+    case 16: return mma_launch<16>(p, grid, st);
+    default: return mma_launch<32>(p, grid, st);
   }
 }
 

@@ -187,9 +187,8 @@ static cudaError_t persist_launch(const PParams& p, int grid, cudaStream_t st) {
 int launch_decode_persistent(const void* params, int wt, int B, int grid, cudaStream_t st) {
   const PParams& p = *reinterpret_cast<const PParams*>(params);
   const int mr = B <= 1 ? 1 : B <= 2 ? 2 : B <= 4 ? 4 : B <= 8 ? 8 : B <= 16 ? 16 : 32;
-  const char* mma_env = getenv("VX_DECODE_MMA");   // tensor-core batched variant (<= 32 rows per CTA slice); VX_DECODE_MMA=0 -> CUDA-core GEMV
-  if (wt == 1 && mr >= 8 && grid >= 128 && !(mma_env && mma_env[0] == '0')) {
-    return (int)launch_decode_mma(p, mr, grid, st);
+  if (wt == 1 && p.att_maxp > 0) {   // tensor-core batched kernel (engine.cu decides: bf16, 5 <= B <= 32)
+    return (int)launch_decode_mma(p, mr < 8 ? 8 : mr, grid, st);
   }
   if (wt == 1 && p.fused) {  // 3-barrier variant: requires one attention unit per CTA and <= kDecodeHS hidden units per CTA
     if (mr > 8 || B * kH * p.nsplit > grid || (kFF + grid - 1) / grid > kDecodeHS) return (int)cudaErrorInvalidConfiguration;

@@ -34,6 +34,7 @@ struct PParams {
   long long* acc_ffn;         // [2][B][1024] fused variant: FFN2 sums
   int fused;                  // 0: 5-barrier kernel, 1: 3-barrier kernel (default for B <= 2)
   float* part;                // [B][16][nsplit][66]  (balanced batched attention: [B][16][att_maxp][68])
+  int kv_l2_mb;               // batched kernel: MB of the next layer's KV rows prefetched into L2 during the GEMV phases (0: off)
   int att_maxp;               // balanced batched attention (decode_mma.cu): max pieces per (utterance, head); 0 = CTA-per-head units
   int32_t* tickets;           // [B*16]
   unsigned int* bar;          // grid barrier counter (zeroed by the host)

@@ -829,7 +829,7 @@ int vx_ar_decode(vx_engine* e, int max_new, int top_k, float top_p, float temper
   nsplit = std::max(nsplit, (final_ctx + 2047) / 2048);
   nsplit = std::min(nsplit, 64);
   ENS(e->qkvs, (size_t)B * 3 * kD * 4); ENS(e->atts, (size_t)B * kD * 4); ENS(e->ffs, (size_t)B * kFF * 4);
-  ENS(e->part, (size_t)B * kH * nsplit * (kDH + 2) * 4); ENS(e->tick, (size_t)B * kH * 4);
+  ENS(e->part, (size_t)B * kH * nsplit * (kDH + 2) * 4); ENS(e->tick, ((size_t)B * kH + 64) * 4);   // + FFN2 fold tickets of the batched kernel
   ENS(e->out_tok, (size_t)B * max_steps * 4);
   if (forced_tokens) {
     ENS(e->forced, (size_t)B * max_steps * 4);
@@ -840,7 +840,7 @@ int vx_ar_decode(vx_engine* e, int max_new, int top_k, float top_p, float temper
   e->h_pinned[B] = B;
   CK(cudaMemcpyAsync(e->d_budget.p, e->h_pinned, B * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(e->d_nact.p, e->h_pinned + B, 4, cudaMemcpyHostToDevice, st));
-  CK(cudaMemsetAsync(e->tick.p, 0, (size_t)B * kH * 4, st));
+  CK(cudaMemsetAsync(e->tick.p, 0, ((size_t)B * kH + 64) * 4, st));
   CK(cudaMemsetAsync(e->out_tok.p, 0, (size_t)B * max_steps * 4, st));
   CK(cudaStreamSynchronize(st));  // h_pinned reused below
   const int32_t* forced_dev = forced_tokens ? (const int32_t*)e->forced.p : nullptr;
@@ -863,7 +863,9 @@ int vx_ar_decode(vx_engine* e, int max_new, int top_k, float top_p, float temper
       pp.layer[l] = PLayer{L.qkv_w, L.out_w, L.ff1_w, L.ff2_w, L.ff2_t, L.qkv_b, L.out_b, L.ff1_b, L.ff2_b, L.n1_g, L.n1_b, L.n2_g, L.n2_b};
     }
     // 3-barrier variant: one attention unit per CTA, bf16 weights, B <= 8; anything else takes the 5-barrier kernel
-    pp.fused = (e->decode_fused && e->mode == VX_BF16 && B <= e->decode_fused_maxb && B * kH * ns <= e->num_sms &&
+    const char* mm_env = getenv("VX_DECODE_MMA");   // VX_DECODE_MMA=0: CUDA-core GEMV kernel instead of the tensor-core batched one
+    const bool batched = e->mode == VX_BF16 && B > 4 && e->num_sms >= 128 && e->num_sms % 4 == 0 && !(mm_env && mm_env[0] == '0');
+    pp.fused = (!batched && e->decode_fused && e->mode == VX_BF16 && B <= e->decode_fused_maxb && B * kH * ns <= e->num_sms &&
                 (kFF + e->num_sms - 1) / e->num_sms <= 64 && e->ar[0].ff2_t) ? 1 : 0;
     if (pp.fused) {
       ENS(e->p_xb, (size_t)B * kD * 4);
@@ -874,13 +876,10 @@ int vx_ar_decode(vx_engine* e, int max_new, int top_k, float top_p, float temper
       pp.acc_out = (long long*)e->p_acc.p;
       pp.acc_ffn = (long long*)e->p_acc.p + (size_t)2 * B * kD;
     }
-    {   // batched tensor-core kernel (B >= 5, bf16): balanced warp-level attention phase unless VX_DECODE_ATTN=0
-      const char* ab = getenv("VX_DECODE_ATTN");
-      const char* mm = getenv("VX_DECODE_MMA");
-      if (e->mode == VX_BF16 && B > 4 && !pp.fused && !(ab && ab[0] == '0') && !(mm && mm[0] == '0')) {
-        pp.att_maxp = e->num_sms + 2;   // pieces of one (utterance, head): <= warps/16 + 2
-        ENS(e->part, (size_t)B * kH * pp.att_maxp * (kDH + 4) * 4);
-      }
+    if (batched) {   // batched tensor-core kernel: balanced warp-level attention phase
+      pp.att_maxp = e->num_sms + 2;   // pieces of one (utterance, head): <= warps/16 + 2
+      pp.kv_l2_mb = getenv("VX_KV_L2_MB") ? atoi(getenv("VX_KV_L2_MB")) : 80;
+      ENS(e->part, (size_t)B * kH * pp.att_maxp * (kDH + 4) * 4);
     }
     pp.norm_g = e->ar_norm_g; pp.norm_b = e->ar_norm_b; pp.predict_w = e->ar_predict;
     pp.audio_emb = vec(e, "ar_audio_embedding.word_embeddings.weight"); pp.alpha = vec(e, "ar_audio_position.alpha"); pp.pe = e->pe;
