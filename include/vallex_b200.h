@@ -113,6 +113,10 @@ VX_API int vx_vocos_decode(vx_engine* e, const int32_t* codes, int B, int T, int
 VX_API int vx_last_timing(vx_engine* e, float* ms_prefill, float* ms_decode, float* ms_nar, float* ms_vocos,
                    int64_t* decode_steps, int64_t* kernel_launches);
 VX_API int vx_debug_read(vx_engine* e, const char* what, float* dst, int64_t max_elems, int64_t* out_elems);
+/* Name of the kernel the last vx_ar_decode actually launched (e.g. "ar_decode_fused_kernel<1>", "ar_decode_mma_kernel<32>"):
+ * the engine picks the decode kernel from dtype mode, batch size and context, so bench.py reports this string instead of
+ * guessing from the environment.  Valid until the next vx_ar_decode / vx_destroy. */
+VX_API const char* vx_last_decode_kernel(vx_engine* e);
 
 /* Isolated kernel checks (tests/test_gpu_kernels.py); host fp32 buffers, current CUDA device.
  * vx_debug_gemm_tc: C[M,N] = A[M,K] W[N,K]^T (+bias) through the tcgen05 GEMM (epi 0: bf16 row-major, 1: fp32 += into

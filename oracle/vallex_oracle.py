@@ -18,6 +18,7 @@ only the last y row re-embedded per step) -- the arithmetic per element is the s
 from __future__ import annotations
 
 import math
+import time
 from typing import Dict, List, Optional, Sequence, Union
 
 import torch
@@ -170,6 +171,8 @@ class OracleVALLE:
         alpha = sd["ar_audio_position.alpha"]
         kvs = None
         while True:
+            if debug is not None and "times" in debug:   # bench.py's CPU baseline: wall clock at the start of every iteration
+                debug["times"].append(time.perf_counter())
             Ly = y.shape[1]
             mask = self.ar_mask(S, Ly)
             if kvs is None:

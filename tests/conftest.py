@@ -10,7 +10,7 @@ for p in (ROOT, os.path.join(ROOT, "vall-e-x_b200")):
         sys.path.insert(0, p)
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
-GOLDEN_CASES = ["tiny_en", "noprompt_en", "mixlang", "mid_ja", "cfg1_librispeech"]
+GOLDEN_CASES = ["tiny_en", "noprompt_en", "mixlang", "mid_ja", "cfg1_librispeech", "longctx_en"]
 
 
 def pytest_configure(config):

@@ -39,6 +39,9 @@ CASES = {
     "mixlang": (1, 3, 5, 12, "zh", ["en", "en", "zh", "ja", "ja"], None),
     "mid_ja": (2, 6, 10, 40, "ja", "ja", None),
     "cfg1_librispeech": (0, None, 64, None, "en", "en", "librispeech_1"),
+    # context > 2048 keys and audio PE positions > 4000 (modules/embedding.py:68-91 auto-extension): a 3900-frame prompt,
+    # 10 phonemes -> the reference's own 16*S cap ends the run at T = 160 (context 4071)
+    "longctx_en": (0, 4, 6, 3900, "en", "en", None),
 }
 
 
@@ -77,7 +80,7 @@ def run_reference(model, x, Lp, prompt, pl, tl):
 
 
 def main(names):
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(int(os.environ.get("GOLDEN_THREADS", os.cpu_count())))
     by_seed = {}
     for name in names:
         seed, x, Lp, prompt, pl, tl = build_inputs(name)
@@ -145,8 +148,90 @@ def make_eos_cases():
             raise SystemExit(f"no EOS candidate worked for {name}")
 
 
+def make_cfg2_case(T_stop=1275):
+    """BASELINE config 2 / the bench.py workload (S = 58 + 256, librispeech_1 prompt P = 225, T = 1275 so P + T = 1500).
+    With random weights the unmodified reference would run to its 16*S = 5024 cap, so -- as in make_eos_cases -- row 1024
+    of ar_predict_layer.weight is crafted from the reference's own hidden states so that EOS wins exactly at step 1275:
+    pass 1 runs the reference and is cut short by a forward hook once the hidden state of step 1275 has been seen (the
+    reference code is untouched); the row is the weighted least-squares solution that gives EOS the winning logit at that
+    step and a low one at every earlier step; pass 2 is a COMPLETE run of the unmodified reference (AR stops by itself at T = 1275, then the 7 NAR stages) and
+    is kept only if T == 1275.  Stored for fp32 weights and for bf16-rounded matrix weights (each with its own EOS row).
+    Inputs are exactly bench.py's workload_inputs()."""
+    torch.set_num_threads(int(os.environ.get("GOLDEN_THREADS", os.cpu_count())))
+    d = np.load(os.path.join(ref_shim.REF_ROOT, "presets", "librispeech_1.npz"))
+    prompt = d["audio_tokens"][0].astype(np.int64)
+    xp = d["text_tokens"][0].astype(np.int64)
+    xn = np.random.default_rng(2024).integers(5, 70, size=(256,), dtype=np.int64)
+    x, Lp = np.concatenate([xp, xn]), len(xp)
+    pl = tl = "en"
+    sd = synthetic_state_dict(0)
+    out = dict(x=x, Lp=np.int64(Lp), prompt=prompt, prompt_language=np.array(pl), text_language=np.array([tl]),
+               text_language_is_list=np.bool_(False), seed=np.int64(0), T=np.int64(T_stop))
+
+    class _Stop(Exception):
+        pass
+
+    for tag, sdr in (("", sd), ("_bf16w", round_state_dict_bf16(sd))):
+        t0 = time.time()
+        model = ref_shim.load_reference_valle(sdr)
+        hs, lg = [], []
+
+        def on_norm(m, i, o):
+            hs.append(o.detach()[0, -1].clone())
+
+        def on_pred(m, i, o):
+            lg.append(o.detach()[0].clone())
+            if len(lg) == T_stop + 1:
+                raise _Stop()
+        h1 = model.ar_decoder.norm.register_forward_hook(on_norm)
+        h2 = model.ar_predict_layer.register_forward_hook(on_pred)
+        try:
+            with torch.no_grad():
+                model.inference(torch.from_numpy(x)[None], torch.tensor([len(x)]), torch.from_numpy(prompt)[None],
+                                enroll_x_lens=Lp, top_k=1, temperature=1.0, prompt_language=pl, text_language=tl)
+        except _Stop:
+            pass
+        h1.remove(); h2.remove()
+        print(f"cfg2{tag}: pass 1 ({len(lg)} steps) in {time.time() - t0:.0f}s", flush=True)
+        H = torch.stack(hs)                                   # [T_stop + 1, 1024]
+        hstar = H[T_stop]
+        c = float(lg[T_stop].max()) + 1.0
+        # EOS row: weighted least squares over the hidden states the reference itself produced -- logit c at step T_stop
+        # (exact after the final rescale), about -2 at every earlier step (1276 equations, 1024 unknowns: small residuals)
+        wts = torch.ones(T_stop + 1, dtype=torch.float64)
+        wts[T_stop] = 1e3
+        tgt = torch.full((T_stop + 1,), -2.0, dtype=torch.float64)
+        tgt[T_stop] = c
+        A = H.double() * wts[:, None]
+        row = torch.linalg.lstsq(A, (tgt * wts)[:, None]).solution[:, 0].float()
+        row = row * (c / float((row * hstar).sum()))
+        if tag:   # the bf16 engine mode stores this matrix in bf16: the reference sees exactly that value
+            row = row.to(torch.bfloat16).to(torch.float32)
+        eos_all = H @ row
+        top = torch.stack([l[:1024].max() for l in lg])
+        assert bool((eos_all[:T_stop] < top[:T_stop]).all()), "crafted EOS row fires early"
+        sd2 = dict(sdr)
+        wmat = sdr["ar_predict_layer.weight"].clone()
+        wmat[1024] = row
+        sd2["ar_predict_layer.weight"] = wmat
+        m2 = ref_shim.load_reference_valle(sd2)
+        codes, ar_top2, nar_top2, head = run_reference(m2, x, Lp, prompt, pl, tl)
+        print(f"cfg2{tag}: complete reference run T={codes.shape[0]} in {time.time() - t0:.0f}s", flush=True)
+        assert codes.shape[0] == T_stop, codes.shape
+        out["eos_row" + tag] = row.numpy().astype(np.float32)
+        out["codes" + tag] = codes.astype(np.int16)
+        # margins over the 1024 audio logits + EOS as the reference saw them (top-2 of the full 1025 row)
+        out["ar_top2" + tag] = ar_top2.astype(np.float32)
+        out["nar_top2" + tag] = nar_top2.astype(np.float32)
+        del model, m2
+    np.savez_compressed(os.path.join(OUT, "cfg2_librispeech.npz"), **out)
+
+
 if __name__ == "__main__":
     if sys.argv[1:] == ["eos"]:
         make_eos_cases()
+        sys.exit(0)
+    if sys.argv[1:] == ["cfg2"]:
+        make_cfg2_case()
         sys.exit(0)
     main(sys.argv[1:] or [n for n in CASES if n != "cfg1_librispeech"])

@@ -8,6 +8,8 @@ bf16 mode  : weights are the bf16-rounded values; compared with the reference ru
              top-1/top-2 logit margin exceeds MARGIN must match; overall agreement is also bounded.
 Vocos      : waveform RMS delta < 1e-4 against oracle/vocos_oracle.py (parity unpinned: see its header).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -47,8 +49,14 @@ def _infer(m, g, **kw):
                        prompt_language=g["prompt_language_arg"], text_language=g["text_language_arg"], quiet=True, **kw)
 
 
-def T_small_enough(bad):
-    return bad.shape[0] >= 1000 and bad.mean() < 5e-4   # only the 13,664-token case may carry near-tie flips
+def flips_allowed(bad, margin):
+    """The only NAR mismatches fp32 mode may show: at most 4 ROOT flips (the earliest stage with any mismatch has no upstream
+    cause), each on a reference top-1/top-2 margin < 2e-3, in a case of >= 1000 frames; stage i+1 attends over every frame's
+    stage-i token, so later stages may carry a bounded number (<= 32) of consequences."""
+    first_stage = int(np.argmax(bad.any(axis=0)))
+    root = bad[:, first_stage]
+    return (bad.shape[0] >= 1000 and int(root.sum()) <= 4 and bool((margin[:, first_stage][root] < 2e-3).all())
+            and int(bad.sum()) <= 32)
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
@@ -70,11 +78,10 @@ def test_fp32_greedy_tokens_bit_exact(name):
     margin = (g["nar_top2"][..., 0] - g["nar_top2"][..., 1]).T  # [T,7]
     first_stage = int(np.argmax(bad.any(axis=0)))
     print(f"{name}: NAR mismatches {int(bad.sum())}/{bad.size}, first at stage {first_stage}, margins {margin[:, first_stage][bad[:, first_stage]]}")
-    assert T_small_enough(bad), f"NAR mismatch rate {bad.mean():.5f}"
-    assert (margin[:, first_stage][bad[:, first_stage]] < 2e-3).all()
+    assert flips_allowed(bad, margin), f"NAR mismatches {int(bad.sum())}, root margins {margin[:, first_stage][bad[:, first_stage]]}"
 
 
-@pytest.mark.parametrize("name", ["tiny_en", "mixlang", "mid_ja", "cfg1_librispeech"])
+@pytest.mark.parametrize("name", ["tiny_en", "mixlang", "mid_ja", "cfg1_librispeech", "longctx_en"])
 def test_bf16_teacher_forced_tokens(name):
     g = load_golden(name)
     m = model_for(g["seed"], "bf16")
@@ -171,6 +178,100 @@ def test_fused_decode_variant(monkeypatch, names):
         assert match[margin > MARGIN].all(), (names[b], margin[~match & (margin > MARGIN)][:5])
         assert match.mean() > 0.97, (names[b], match.mean())
     eng.close()
+
+
+def _cfg2_state_dict(g, tag):
+    """synthetic checkpoint 0 with the fixture's crafted EOS row (make_golden.py cfg2): the reference stops at T = 1275 by itself"""
+    sd = dict(state_dict_for(0, rounded=bool(tag)))
+    w = sd["ar_predict_layer.weight"].clone()
+    w[1024] = torch.from_numpy(g["eos_row" + tag])
+    sd["ar_predict_layer.weight"] = w
+    return sd
+
+
+@pytest.mark.skipif(not os.path.isfile(os.path.join(os.path.dirname(__file__), "golden", "cfg2_librispeech.npz")),
+                    reason="cfg2 fixture not generated")
+def test_bench_shape_fixture_fp32_and_bf16():
+    """The bench.py workload itself (BASELINE config 2: S = 314, librispeech_1 prompt P = 225, T = 1275): fp32 mode reproduces
+    the unmodified reference's complete run (true EOS at step 1275, then 7 NAR stages) token for token up to named near-tie
+    flips; bf16 mode teacher-forced against the reference run on bf16-rounded weights."""
+    g = load_golden("cfg2_librispeech")
+    T = int(g["T"])
+    m = _valle(_cfg2_state_dict(g, ""), "fp32", max_ctx=2048)
+    got = _infer(m, g)[0].numpy()
+    want = g["codes"].astype(np.int64)
+    assert got.shape == want.shape == (T, 8)
+    assert np.array_equal(got[:, 0], want[:, 0])
+    bad = got[:, 1:] != want[:, 1:]
+    if bad.any():
+        margin = (g["nar_top2"][..., 0] - g["nar_top2"][..., 1]).T
+        print(f"cfg2 fp32: NAR mismatches {int(bad.sum())}/{bad.size}")
+        assert flips_allowed(bad, margin)
+    m.engine.close()
+    m = _valle(_cfg2_state_dict(g, "_bf16w"), "bf16", max_ctx=2048)
+    want = g["codes_bf16w"].astype(np.int64)
+    eng = m.engine
+    lang = m._lang_ids(len(g["x"]), int(g["Lp"]), "en", "en")
+    eng.set_batch([g["x"].astype(np.int32)], [lang], [g["prompt"].astype(np.int32)])
+    eng.ar_prefill()
+    toks, lens, _ = eng.ar_decode(top_k=1, forced=want[None, :, 0].astype(np.int32), max_new=T, ignore_eos=True)
+    margin = g["ar_top2_bf16w"][:T, 0] - g["ar_top2_bf16w"][:T, 1]
+    match = toks[0, :T] == want[:, 0]
+    print(f"cfg2 bf16: AR teacher-forced match {match.mean():.4f}")
+    assert match[margin > MARGIN].all() and match.mean() > 0.97
+    eng.close()
+
+
+def test_top_p_filter_restricts_support():
+    """top_p < 1 (models/vallex.py:811-832): the nucleus is the smallest prefix of the sorted distribution whose mass exceeds
+    top_p (the token that crosses the threshold is kept); every draw must come from the oracle's kept set."""
+    from oracle.vallex_oracle import top_k_top_p_filtering
+    g = load_golden("tiny_en")
+    m = _valle(state_dict_for(g["seed"]), "fp32", max_ctx=256, max_batch=64)
+    eng = m.engine
+    lang = m._lang_ids(len(g["x"]), int(g["Lp"]), "en", "en")
+    nb = 64
+    eng.set_batch([g["x"].astype(np.int32)] * nb, [lang] * nb, [g["prompt"].astype(np.int32)] * nb)
+    eng.ar_prefill()
+    logits = torch.from_numpy(g["ar_logits_head"][0])[None]
+    for top_p, temp in ((0.9, 1.0), (0.5, 0.8), (0.05, 1.0)):
+        kept = torch.isfinite(top_k_top_p_filtering(logits / temp, top_k=0, top_p=min(top_p + 1e-4, 1.0)))[0].numpy()
+        eng.ar_prefill()
+        toks, _, slp = eng.ar_decode(max_new=1, top_k=-100, top_p=top_p, temperature=temp, seed=5)
+        first = toks[:, 0]
+        assert kept[first].all(), (top_p, sorted(set(first.tolist()) - set(np.nonzero(kept)[0].tolist())))
+        if kept.sum() > 4:
+            assert len(set(first.tolist())) > 1
+        # logprob bookkeeping over the FILTERED distribution (models/vallex.py:849-852)
+        lp = torch.log_softmax(top_k_top_p_filtering(logits / temp, top_k=0, top_p=top_p), -1)[0].numpy()
+        np.testing.assert_allclose(slp, lp[first], atol=2e-3)
+    eng.close()
+
+
+def test_large_ragged_mixed_language_batch_equals_sequential():
+    """X1: a ragged mixed-language batch (13 utterances: four golden cases with different S / P / languages / per-token language
+    lists, repeated) through inference_batch in fp32 == each utterance alone == the reference's tokens."""
+    names = ["tiny_en", "noprompt_en", "cfg1_short", "tiny_en", "noprompt_en"] * 3
+    names = names[:13]
+    base = {n: load_golden(n) for n in ("tiny_en", "noprompt_en")}
+    g1 = load_golden("cfg1_librispeech")
+    m = _valle(state_dict_for(0), "fp32", max_ctx=1024, max_batch=13)
+    items, wants = [], []
+    for n in names:
+        g = g1 if n == "cfg1_short" else base[n]
+        items.append((torch.from_numpy(g["x"].astype(np.int64))[None], torch.from_numpy(g["prompt"].astype(np.int64))[None],
+                      int(g["Lp"]), g["prompt_language_arg"], g["text_language_arg"]))
+        wants.append(g["codes"].astype(np.int64))
+    outs = m.inference_batch(items, top_k=1, temperature=1.0, quiet=True, max_new_tokens=96)
+    for out, want, n in zip(outs, wants, names):
+        T = min(96, want.shape[0])
+        assert out.shape == (1, T, 8), (n, out.shape)
+        assert np.array_equal(out[0, :, 0].numpy(), want[:T, 0]), n      # AR codebook 0: the reference's tokens
+    # the tiny cases run to their own caps (T = 96 / 80) inside the batch: complete codes equal the reference's
+    for out, want, n in zip(outs, wants, names):
+        if n != "cfg1_short":
+            assert np.array_equal(out[0].numpy(), want), n
+    m.engine.close()
 
 
 def test_max_new_tokens_is_a_prefix():

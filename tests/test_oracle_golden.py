@@ -48,6 +48,21 @@ def test_oracle_prefix_of_full_size_case():
     assert np.array_equal(yy[0, 1 + y.shape[1]:].numpy(), g["codes"][:24, 0].astype(np.int64))
 
 
+def test_oracle_prefix_of_long_context_case():
+    """longctx_en (3900-frame prompt, context 4071 > 2048, audio PE positions > 4000 = past the reference's initial table,
+    modules/embedding.py:68-72): the oracle's first tokens equal the unmodified reference's."""
+    g = load_golden("longctx_en")
+    o = OracleVALLE(state_dict_for(g["seed"]))
+    x = torch.from_numpy(g["x"].astype(np.int64))[None]
+    y = torch.from_numpy(g["prompt"].astype(np.int64))[None]
+    dbg = {}
+    yy = o.ar_decode(x, y[..., 0], int(g["Lp"]), "en", "en", top_k=1, max_new_tokens=2, debug=dbg)
+    assert g["codes"].shape == (160, 8) and g["prompt"].shape == (3900, 8)
+    assert np.array_equal(yy[0, 1 + y.shape[1]:].numpy(), g["codes"][:2, 0].astype(np.int64))
+    top2 = torch.stack([torch.topk(l[0], 2)[0] for l in dbg["logits"]]).numpy()
+    np.testing.assert_allclose(top2, g["ar_top2"][:3], rtol=0, atol=0)
+
+
 @pytest.mark.parametrize("name,T", [("eos_mid", 37), ("eos_first", 0)])
 def test_oracle_true_eos_termination(name, T):
     """EOS sampled by the model (models/vallex.py:574): row 1024 of the predict layer is crafted in the fixture so the

@@ -50,38 +50,8 @@ def main():
     rng = np.random.default_rng(7)
     hbm, tfl, how = peaks()
     if a.config == 3:
-        B = a.batch or 32
-        Lp = rng.integers(18, 161, size=B)
-        P = rng.integers(161, 759, size=B)
-        S = Lp + 512
-        max_ctx = int((S + P).max()) + a.steps + 8
-        eng = Engine(0, B, max_ctx, a.dtype)
-        eng.load_valle_state_dict(synthetic_state_dict(0))
-        eng.finalize()
-        text = [rng.integers(5, 70, size=int(s)).astype(np.int32) for s in S]
-        lang = [np.concatenate([np.full(int(lp), l % 3, np.int32), np.full(512, (l + 1) % 3, np.int32)]) for l, lp in enumerate(Lp)]
-        prm = [rng.integers(0, 1024, size=(int(p), 8)).astype(np.int32) for p in P]
-        res = []
-        for _ in range(a.reps + 1):
-            eng.set_batch(text, lang, prm)
-            eng.ar_prefill()
-            toks, lens, _ = eng.ar_decode(max_new=a.steps, top_k=1, ignore_eos=True)
-            t = eng.timing()
-            res.append(t)
-        t = res[-1]
-        fw = t["decode_steps"] - 1
-        t_step = t["ms_decode"] / 1e3 / fw
-        L0 = (S + P + 1).astype(np.float64)
-        Lmean = L0 + fw / 2.0
-        kvb = 49152 if a.dtype == "bf16" else 98304
-        wb = 304412672 if a.dtype == "bf16" else 608825344
-        bytes_step = wb + kvb * float((Lmean + 1).sum())
-        ach = bytes_step / t_step / 1e9
-        print(json.dumps({"config": 3, "B": B, "dtype": a.dtype, "decode_steps": t["decode_steps"], "ms_decode": t["ms_decode"],
-                          "ms_prefill": t["ms_prefill"], "us_per_step": t_step * 1e6, "ar_tokens_per_s": B / t_step,
-                          "mean_ctx": float(Lmean.mean()), "bytes_per_step": bytes_step,
-                          "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "peak_source": how},
-                          "lens_ok": bool((lens == np.minimum(a.steps, 16 * S)).all())}))
+        import bench
+        print(json.dumps(dict(bench.cfg3_result(a.batch or 32, a.steps, a.dtype, reps=a.reps), config=3)))
     elif a.config == 5:
         from vallex_b200 import generation as g
         from vallex_b200.vallex import VALLE
@@ -115,31 +85,8 @@ def main():
                           "api": "generation.generate_audio_from_long_text(mode='fixed-prompt')", **out,
                           "speedup_batched": out["sequential"]["s_per_request"] / out["batched"]["s_per_request"]}))
     else:
-        B = a.batch or 8
-        S, P, T = 314, 225, 1275
-        eng = Engine(0, B, S + P + T + 8, a.dtype)
-        eng.load_valle_state_dict(synthetic_state_dict(0))
-        eng.load_vocos_state_dict(synthetic_vocos_state_dict(0))
-        eng.finalize()
-        text = [rng.integers(5, 70, size=S).astype(np.int32) for _ in range(B)]
-        lang = [np.zeros(S, np.int32) for _ in range(B)]
-        prm = [rng.integers(0, 1024, size=(P, 8)).astype(np.int32) for _ in range(B)]
-        cb0 = rng.integers(0, 1024, size=(B, T)).astype(np.int32)
-        tl = np.full((B,), T, np.int32)
-        for _ in range(a.reps + 1):
-            eng.set_batch(text, lang, prm)
-            codes = eng.nar(cb0=cb0, t_lens=tl)
-            t_nar = eng.timing()["ms_nar"]
-            wave = eng.vocos_decode(np.ascontiguousarray(codes.transpose(2, 0, 1)))
-            t_voc = eng.timing()["ms_vocos"]
-        L = S + P + T
-        flops = 7 * (2 * L * 150994944 + 49152 * L * L + 2 * T * 1048576) * B
-        ach = flops / (t_nar / 1e3) / 1e12
-        print(json.dumps({"config": 4, "B": B, "dtype": a.dtype, "ms_nar": t_nar, "ms_vocos": t_voc,
-                          "frames_per_s": B * T / ((t_nar + t_voc) / 1e3), "nar_tflops": ach,
-                          "roofline": {"bound": "tensor", "achieved": ach, "peak": tfl, "unit": "TFLOP/s", "frac": ach / tfl,
-                                       "peak_source": how + " (bf16_tflops_sustained)"},
-                          "vocos_frames_per_s": B * T / (t_voc / 1e3)}))
+        import bench
+        print(json.dumps(dict(bench.cfg4_result(a.batch or 8, a.dtype, reps=a.reps), config=4)))
 
 
 if __name__ == "__main__":

@@ -38,9 +38,21 @@ __device__ __forceinline__ void frag_store(uint16_t* fh, uint16_t* fl, int m, in
 // Row-per-warp staging: warp w stages batch rows w, w + 16 (MR = 32); a lane holds columns it*128 + lane*4 .. +3 of a row
 // (8 coalesced 16-byte loads, all rows' loads in flight at once), LayerNorm statistics are warp shuffles (no block-wide
 // reduction), and the normalised row goes straight into the hi/lo fragment images.  src(m) -> row pointer or nullptr (zeros).
+// LayerNorm vectors of the NEXT LN phase: 8 KB copied into shared memory with cp.async BEFORE the grid barrier that precedes
+// the phase (they are evicted from L2 by the 3 GB a step streams, so a plain load would put an HBM round trip behind the
+// row statistics); stage_rows_frag<LN> waits for the copy.
+__device__ __forceinline__ void ln_copy_async(float* lnp, const float* __restrict__ gamma, const float* __restrict__ beta) {
+  const int t = threadIdx.x;   // 512 threads x 16 B = gamma[1024] | beta[1024]
+  const float* srcp = (t < PNT / 2) ? gamma + t * 4 : beta + (t - PNT / 2) * 4;
+  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(lnp + t * 4);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(srcp) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 template <int MR, bool LN, typename Src>
-__device__ __forceinline__ void stage_rows_frag(uint16_t* fh, uint16_t* fl, int B, Src src, const float* __restrict__ gamma,
-                                                const float* __restrict__ beta) {
+__device__ __forceinline__ void stage_rows_frag(uint16_t* fh, uint16_t* fl, int B, Src src, const float* lnp) {
+  const float* gamma = lnp;
+  const float* beta = lnp + kD;
   constexpr int NT = MR / 8;
   constexpr int RPW = (MR + PNW - 1) / PNW;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -52,6 +64,10 @@ __device__ __forceinline__ void stage_rows_frag(uint16_t* fh, uint16_t* fl, int 
 #pragma unroll
     for (int it = 0; it < 8; ++it)
       v[r][it] = row ? __ldcg(reinterpret_cast<const float4*>(row + it * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if constexpr (LN) {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();   // every thread's 16 bytes of gamma | beta have landed
   }
 #pragma unroll
   for (int r = 0; r < RPW; ++r) {
@@ -75,8 +91,8 @@ __device__ __forceinline__ void stage_rows_frag(uint16_t* fh, uint16_t* fl, int 
       for (int it = 0; it < 8; ++it) {
         float x[4] = {v[r][it].x, v[r][it].y, v[r][it].z, v[r][it].w};
         if constexpr (LN) {
-          const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + it * 128 + lane * 4));
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(beta + it * 128 + lane * 4));
+          const float4 g = *reinterpret_cast<const float4*>(gamma + it * 128 + lane * 4);
+          const float4 bb = *reinterpret_cast<const float4*>(beta + it * 128 + lane * 4);
           x[0] = __fadd_rn(__fmul_rn((x[0] - mean) * rstd, g.x), bb.x);
           x[1] = __fadd_rn(__fmul_rn((x[1] - mean) * rstd, g.y), bb.y);
           x[2] = __fadd_rn(__fmul_rn((x[2] - mean) * rstd, g.z), bb.z);
@@ -412,6 +428,7 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_mma_kernel(const PParams p) 
   float* scratch = dsm + MR * kD;                          // sampling scratch / partial tiles
   float* red = scratch;                                    // [8][32][MR + 1] partial tiles (GEMV phases only)
   __shared__ int s_fold;
+  __shared__ __align__(16) float lnp[2 * kD];              // gamma | beta of the next LayerNorm phase
   const Batch& bt = p.bt;
   const int B = bt.B;
   const int tid = threadIdx.x;
@@ -429,10 +446,9 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_mma_kernel(const PParams p) 
   int32_t* fold_ticket = p.tickets + B * kH + gi;
 
   MPre pre;
-  LnPre lp;
   const WT* Wqkv0 = reinterpret_cast<const WT*>(p.layer[0].qkv_w);
   gemv_issue_mma(pre, Wqkv0, kD, q0, q1);
-  ln_issue(lp, p.layer[0].n1_g, p.layer[0].n1_b, nullptr);
+  ln_copy_async(lnp, p.layer[0].n1_g, p.layer[0].n1_b);
 
   long long* prof = nullptr;
   const int prof_slot = (blockIdx.x == 0) ? 0 : (blockIdx.x == gridDim.x / 2) ? 1 : (blockIdx.x == gridDim.x - 1) ? 2 : -1;
@@ -453,6 +469,7 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_mma_kernel(const PParams p) 
     if (!p.ignore_eos && ld_cg(bt.n_active) <= 0) break;
     if (step == p.max_steps - 1) break;
     const AttnPlan plan = attn_plan(bt);   // contexts are fixed for the 12 layers of this step
+    const unsigned live = __ballot_sync(0xffffffffu, plan.n > 0);   // utterances still decoding (bit b)
     // share of a layer's KV blocks to pull into L2 ahead of its attention phase: all of them while one layer's keys and values
     // (8 KB per block) fit the budget (p.kv_l2_mb, default 80 of the 126 MB), else that fraction
     const int pf16 = (p.kv_l2_mb <= 0) ? 0 : (int)min(16ll, (16ll * p.kv_l2_mb * 128) / max(plan.tb, 1));
@@ -463,7 +480,7 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_mma_kernel(const PParams p) 
       const WT* W1 = reinterpret_cast<const WT*>(L.ff1_w);
       const WT* W2 = reinterpret_cast<const WT*>(L.ff2_w) + (size_t)kc * kD;
       // ---- P1: LN1(x_l) + QKV rows (x_l is complete in xa: the FFN2 fold of layer l-1 wrote it) ---------------------------
-      stage_rows_frag<MR, true>(fh, fl, B, xa_row, L.n1_g, L.n1_b);
+      stage_rows_frag<MR, true>(fh, fl, B, xa_row, lnp);
       PSTAMP(3);
       gemv_finish_mma<MR>(pre, fh, fl, q0, q1, B, L.qkv_b, nullptr, red, zero,
                           [&](int n, int m, float v) { p.qkv[(size_t)m * 3 * kD + n] = v; });
@@ -476,18 +493,17 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_mma_kernel(const PParams p) 
       grid_barrier(p.bar, epoch, prof);
       // ---- P3: out-proj + residual -> xa -------------------------------------------------------------------------------
       kv_prefetch_balanced(p, (l + 1 < kL) ? l + 1 : 0, plan, pf16);   // next layer (or layer 0 of the next step)
-      stage_rows_frag<MR, false>(fh, fl, B, [&](int m) -> const float* { return ld_cg(bt.finished + m) ? nullptr : p.att + (size_t)m * kD; },
-                                 nullptr, nullptr);
+      stage_rows_frag<MR, false>(fh, fl, B, [&](int m) -> const float* { return ((live >> m) & 1u) ? p.att + (size_t)m * kD : nullptr; }, nullptr);
       PSTAMP(3);
       gemv_finish_mma<MR>(pre, fh, fl, o0, o1, B, L.out_b, nullptr, red, [&](int n, int m) { return __ldcg(p.xa + (size_t)m * kD + n); },
                           [&](int n, int m, float v) { p.xa[(size_t)m * kD + n] = v; });
       PSTAMP(4);
       gemv_issue_mma(pre, W1, kD, f0, f1);
-      ln_issue(lp, L.n2_g, L.n2_b, nullptr);
+      ln_copy_async(lnp, L.n2_g, L.n2_b);
       PSTAMP(5);
       grid_barrier(p.bar, epoch, prof);
       // ---- P4: LN2 + FFN1 + ReLU ---------------------------------------------------------------------------------------
-      stage_rows_frag<MR, true>(fh, fl, B, xa_row, L.n2_g, L.n2_b);
+      stage_rows_frag<MR, true>(fh, fl, B, xa_row, lnp);
       PSTAMP(3);
       gemv_finish_mma<MR>(pre, fh, fl, f0, f1, B, L.ff1_b, nullptr, red, zero,
                           [&](int n, int m, float v) { p.hid[(size_t)m * kFF + n] = fmaxf(v, 0.f); });
@@ -497,17 +513,17 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_mma_kernel(const PParams p) 
       grid_barrier(p.bar, epoch, prof);
       // ---- P5: FFN2 split-K x4; the last of the four k-quarter CTAs of a row group folds the partials (fixed order), the
       //          bias and the residual into xa, so every consumer reads ONE value per element ------------------------------
-      stage_rows_frag<MR, false>(fh, fl, B, [&](int m) -> const float* { return p.hid + (size_t)m * kFF + kc * kD; }, nullptr, nullptr);
+      stage_rows_frag<MR, false>(fh, fl, B, [&](int m) -> const float* { return p.hid + (size_t)m * kFF + kc * kD; }, nullptr);
       PSTAMP(3);
       gemv_finish_mma<MR>(pre, fh, fl, g0, g1, B, nullptr, nullptr, red, zero,
                           [&](int n, int m, float v) { p.pf[((size_t)kc * B + m) * kD + n] = v; });
       PSTAMP(4);
       if (l + 1 < kL) {
         gemv_issue_mma(pre, reinterpret_cast<const WT*>(p.layer[l + 1].qkv_w), kD, q0, q1);
-        ln_issue(lp, p.layer[l + 1].n1_g, p.layer[l + 1].n1_b, nullptr);
+        ln_copy_async(lnp, p.layer[l + 1].n1_g, p.layer[l + 1].n1_b);
       } else {
         gemv_issue_mma(pre, reinterpret_cast<const WT*>(p.predict_w), kD, pr0, pr1);
-        ln_issue(lp, p.norm_g, p.norm_b, nullptr);
+        ln_copy_async(lnp, p.norm_g, p.norm_b);
       }
       if (tid == 0) {
         __threadfence();       // this CTA's partial tile is visible device-wide before the ticket is taken
@@ -530,11 +546,11 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_mma_kernel(const PParams p) 
       grid_barrier(p.bar, epoch, prof);
     }
     // ---- PF: final LayerNorm + predict rows -> logits ----------------------------------------------------------------------
-    stage_rows_frag<MR, true>(fh, fl, B, xa_row, p.norm_g, p.norm_b);
+    stage_rows_frag<MR, true>(fh, fl, B, xa_row, lnp);
     gemv_finish_mma<MR>(pre, fh, fl, pr0, pr1, B, nullptr, nullptr, red, zero,
                         [&](int n, int m, float v) { p.logits[(size_t)m * kARLogits + n] = v; });
     gemv_issue_mma(pre, Wqkv0, kD, q0, q1);
-    ln_issue(lp, p.layer[0].n1_g, p.layer[0].n1_b, nullptr);
+    ln_copy_async(lnp, p.layer[0].n1_g, p.layer[0].n1_b);
     grid_barrier(p.bar, epoch, prof);
   }
   if (blockIdx.x == 0 && tid == 0) *p.steps_done = steps;

@@ -140,6 +140,7 @@ struct vx_engine {
   int ctx_cap = 0;
   size_t kv_layer_elems = 0;
 
+  std::string decode_kernel;                         // name of the kernel the last vx_ar_decode launched
   float ms_prefill = 0, ms_decode = 0, ms_nar = 0, ms_vocos = 0;
   int64_t decode_steps = 0, launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -878,7 +879,7 @@ int vx_ar_decode(vx_engine* e, int max_new, int top_k, float top_p, float temper
     }
     if (batched) {   // batched tensor-core kernel: balanced warp-level attention phase
       pp.att_maxp = e->num_sms + 2;   // pieces of one (utterance, head): <= warps/16 + 2
-      pp.kv_l2_mb = getenv("VX_KV_L2_MB") ? atoi(getenv("VX_KV_L2_MB")) : 80;
+      pp.kv_l2_mb = getenv("VX_KV_L2_MB") ? atoi(getenv("VX_KV_L2_MB")) : 0;   // measured: no gain (the 3 GB a step streams do not stay in L2), off by default
       ENS(e->part, (size_t)B * kH * pp.att_maxp * (kDH + 4) * 4);
     }
     pp.norm_g = e->ar_norm_g; pp.norm_b = e->ar_norm_b; pp.predict_w = e->ar_predict;
@@ -896,6 +897,12 @@ int vx_ar_decode(vx_engine* e, int max_new, int top_k, float top_p, float temper
       CK(cudaMemsetAsync(e->p_prof.p, 0, 3 * 4096 * 8, st));
       pp.prof = (long long*)e->p_prof.p;
       pp.prof_step0 = std::max(0, std::min(max_steps - 6, atoi(getenv("VX_DECODE_PROF"))));
+    }
+    {
+      const int mr = B <= 1 ? 1 : B <= 2 ? 2 : B <= 4 ? 4 : B <= 8 ? 8 : B <= 16 ? 16 : 32;
+      if (pp.att_maxp > 0) e->decode_kernel = "ar_decode_mma_kernel<" + std::to_string(mr < 8 ? 8 : mr) + ">";
+      else if (pp.fused) e->decode_kernel = "ar_decode_fused_kernel<" + std::to_string(mr) + ">";
+      else e->decode_kernel = std::string("ar_decode_persistent_kernel<") + (e->mode == VX_BF16 ? "bf16," : "float,") + std::to_string(mr) + ">";
     }
     CK(cudaEventRecord(e->ev0, st));
     const int rc = launch_decode_persistent(&pp, e->mode, B, e->num_sms, st);
@@ -924,6 +931,7 @@ int vx_ar_decode(vx_engine* e, int max_new, int top_k, float top_p, float temper
   }
 
   // capture one iteration [sample -> forward] into a CUDA graph; kernels read all step state from the device
+  e->decode_kernel = "cuda-graph step (sample_kernel + gemv/attn_decode kernels)";
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
   const int64_t launches_before = e->launches;
@@ -1141,6 +1149,8 @@ int vx_last_timing(vx_engine* e, float* ms_prefill, float* ms_decode, float* ms_
   if (kernel_launches) *kernel_launches = e->launches;
   return VX_OK;
 }
+
+const char* vx_last_decode_kernel(vx_engine* e) { return e ? e->decode_kernel.c_str() : ""; }
 
 int vx_debug_read(vx_engine* e, const char* what, float* dst, int64_t max_elems, int64_t* out_elems) {
   if (!e || !what || !dst) return fail(VX_ERR_ARG, "vx_debug_read: bad arguments");

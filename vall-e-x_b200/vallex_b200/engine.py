@@ -153,6 +153,11 @@ class Engine:
         return dict(ms_prefill=a.value, ms_decode=b.value, ms_nar=c.value, ms_vocos=d.value, decode_steps=s.value,
                     kernel_launches=k.value)
 
+    def last_decode_kernel(self) -> str:
+        """Engine-reported name of the kernel the last ar_decode launched."""
+        v = self._lib.vx_last_decode_kernel(self._h)
+        return v.decode() if v else ""
+
     def debug_read(self, what: str, max_elems: int) -> np.ndarray:
         buf = np.zeros((max_elems,), np.float32)
         n = C.c_int64()
