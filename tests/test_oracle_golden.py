@@ -63,6 +63,26 @@ def test_oracle_prefix_of_long_context_case():
     np.testing.assert_allclose(top2, g["ar_top2"][:3], rtol=0, atol=0)
 
 
+def test_oracle_prefix_of_bench_shape_case():
+    """cfg2_librispeech = the bench.py workload (S = 314, P = 225; the unmodified reference stops by itself at T = 1275 thanks to
+    the fixture's crafted EOS row): the oracle's AR prefix and logit margins equal the reference's, for fp32 weights and for
+    bf16-rounded matrix weights."""
+    g = load_golden("cfg2_librispeech")
+    assert g["codes"].shape == g["codes_bf16w"].shape == (1275, 8) and len(g["x"]) == 314 and g["prompt"].shape == (225, 8)
+    x = torch.from_numpy(g["x"].astype(np.int64))[None]
+    y = torch.from_numpy(g["prompt"].astype(np.int64))[None]
+    for tag in ("", "_bf16w"):
+        sd = dict(state_dict_for(0, rounded=bool(tag)))
+        w = sd["ar_predict_layer.weight"].clone()
+        w[1024] = torch.from_numpy(g["eos_row" + tag])
+        sd["ar_predict_layer.weight"] = w
+        dbg = {}
+        yy = OracleVALLE(sd).ar_decode(x, y[..., 0], int(g["Lp"]), "en", "en", top_k=1, max_new_tokens=6, debug=dbg)
+        assert np.array_equal(yy[0, 1 + y.shape[1]:].numpy(), g["codes" + tag][:6, 0].astype(np.int64))
+        top2 = torch.stack([torch.topk(l[0], 2)[0] for l in dbg["logits"]]).numpy()
+        np.testing.assert_allclose(top2, g["ar_top2" + tag][:7], rtol=0, atol=0)
+
+
 @pytest.mark.parametrize("name,T", [("eos_mid", 37), ("eos_first", 0)])
 def test_oracle_true_eos_termination(name, T):
     """EOS sampled by the model (models/vallex.py:574): row 1024 of the predict layer is crafted in the fixture so the

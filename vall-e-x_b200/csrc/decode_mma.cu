@@ -56,62 +56,59 @@ __device__ __forceinline__ void stage_rows_frag(uint16_t* fh, uint16_t* fl, int 
   constexpr int NT = MR / 8;
   constexpr int RPW = (MR + PNW - 1) / PNW;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4 v[RPW][8];
-#pragma unroll
-  for (int r = 0; r < RPW; ++r) {
-    const int m = warp + r * PNW;
-    const float* row = (m < B) ? src(m) : nullptr;
-#pragma unroll
-    for (int it = 0; it < 8; ++it)
-      v[r][it] = row ? __ldcg(reinterpret_cast<const float4*>(row + it * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
   if constexpr (LN) {
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();   // every thread's 16 bytes of gamma | beta have landed
   }
-#pragma unroll
+  // one row at a time (a row = 32 registers per lane: with the prefetched weight registers live, two rows in flight spill,
+  // and a spilled load serialises every following one behind it)
+#pragma unroll 1
   for (int r = 0; r < RPW; ++r) {
     const int m = warp + r * PNW;
-    if (m < MR) {   // warp-uniform (MR = 8: warps 8..15 have no row)
-      float mean = 0.f, rstd = 1.f;
-      if constexpr (LN) {
-        float s = 0.f;
+    if (m >= MR) break;   // warp-uniform (MR = 8: warps 8..15 have no row)
+    const float* row = (m < B) ? src(m) : nullptr;
+    float4 v[8];
 #pragma unroll
-        for (int it = 0; it < 8; ++it) s += (v[r][it].x + v[r][it].y) + (v[r][it].z + v[r][it].w);
-        mean = warp_sum(s) / (float)kD;
-        float q = 0.f;
+    for (int it = 0; it < 8; ++it)
+      v[it] = row ? __ldcg(reinterpret_cast<const float4*>(row + it * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float mean = 0.f, rstd = 1.f;
+    if constexpr (LN) {
+      float s = 0.f;
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const float d0 = v[r][it].x - mean, d1 = v[r][it].y - mean, d2 = v[r][it].z - mean, d3 = v[r][it].w - mean;
-          q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
-        }
-        rstd = 1.0f / sqrtf(warp_sum(q) / (float)kD + 1e-5f);
-      }
+      for (int it = 0; it < 8; ++it) s += (v[it].x + v[it].y) + (v[it].z + v[it].w);
+      mean = warp_sum(s) / (float)kD;
+      float q = 0.f;
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
-        float x[4] = {v[r][it].x, v[r][it].y, v[r][it].z, v[r][it].w};
-        if constexpr (LN) {
-          const float4 g = *reinterpret_cast<const float4*>(gamma + it * 128 + lane * 4);
-          const float4 bb = *reinterpret_cast<const float4*>(beta + it * 128 + lane * 4);
-          x[0] = __fadd_rn(__fmul_rn((x[0] - mean) * rstd, g.x), bb.x);
-          x[1] = __fadd_rn(__fmul_rn((x[1] - mean) * rstd, g.y), bb.y);
-          x[2] = __fadd_rn(__fmul_rn((x[2] - mean) * rstd, g.z), bb.z);
-          x[3] = __fadd_rn(__fmul_rn((x[3] - mean) * rstd, g.w), bb.w);
-        }
-        // fragment image slot of (m, c = it*128 + lane*4 .. +3): kg = it, ch = lane >> 3, q = (lane >> 1) & 3, e = (lane & 1) * 4
-        const size_t idx = (((((size_t)it * 4 + (lane >> 3)) * NT + (m >> 3)) * 32) + (m & 7) * 4 + ((lane >> 1) & 3)) * 8 + (lane & 1) * 4;
-        uint32_t hw[2], lw[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * e]), h1 = __float2bfloat16_rn(x[2 * e + 1]);
-          const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * e] - __bfloat162float(h0));
-          const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * e + 1] - __bfloat162float(h1));
-          hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-          lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-        }
-        *reinterpret_cast<uint2*>(fh + idx) = make_uint2(hw[0], hw[1]);
-        *reinterpret_cast<uint2*>(fl + idx) = make_uint2(lw[0], lw[1]);
+        const float d0 = v[it].x - mean, d1 = v[it].y - mean, d2 = v[it].z - mean, d3 = v[it].w - mean;
+        q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
       }
+      rstd = 1.0f / sqrtf(warp_sum(q) / (float)kD + 1e-5f);
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      float x[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+      if constexpr (LN) {
+        const float4 g = *reinterpret_cast<const float4*>(gamma + it * 128 + lane * 4);
+        const float4 bb = *reinterpret_cast<const float4*>(beta + it * 128 + lane * 4);
+        x[0] = __fadd_rn(__fmul_rn((x[0] - mean) * rstd, g.x), bb.x);
+        x[1] = __fadd_rn(__fmul_rn((x[1] - mean) * rstd, g.y), bb.y);
+        x[2] = __fadd_rn(__fmul_rn((x[2] - mean) * rstd, g.z), bb.z);
+        x[3] = __fadd_rn(__fmul_rn((x[3] - mean) * rstd, g.w), bb.w);
+      }
+      // fragment image slot of (m, c = it*128 + lane*4 .. +3): kg = it, ch = lane >> 3, q = (lane >> 1) & 3, e = (lane & 1) * 4
+      const size_t idx = (((((size_t)it * 4 + (lane >> 3)) * NT + (m >> 3)) * 32) + (m & 7) * 4 + ((lane >> 1) & 3)) * 8 + (lane & 1) * 4;
+      uint32_t hw[2], lw[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * e]), h1 = __float2bfloat16_rn(x[2 * e + 1]);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * e] - __bfloat162float(h0));
+        const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * e + 1] - __bfloat162float(h1));
+        hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+      }
+      *reinterpret_cast<uint2*>(fh + idx) = make_uint2(hw[0], hw[1]);
+      *reinterpret_cast<uint2*>(fl + idx) = make_uint2(lw[0], lw[1]);
     }
   }
   __syncthreads();
