@@ -91,6 +91,16 @@ VX_API int vx_ar_prefill(vx_engine* e, void* stream);
  * out_tokens [B,max_steps] (max_steps = the largest per-utterance budget, returned in *out_max_steps
  * by vx_ar_budget), out_lens [B] = T_b, out_sum_logprobs [B] nullable (models/vallex.py:572). */
 VX_API int vx_ar_budget(vx_engine* e, int max_new, int* out_max_steps);
+
+/* Replaces: `x.repeat(best_of, 1, 1); y.repeat(best_of, 1)` (models/vallex.py:525-527), where the reference pushes best_of
+ * copies of the utterance through the first (full-sequence) iteration.  Here the utterance is prefilled ONCE
+ * (vx_set_batch with B = 1, vx_ar_prefill) and vx_ar_fork replicates its decode state -- KV rows of every layer, token buffer,
+ * first-step logits -- on the device for beams 1..n_beams-1 (n_beams <= max_batch); vx_ar_decode then runs the beams as a
+ * batch, each with its own Philox stream.  vx_ar_select_beam replaces models/vallex.py:583-594: avg = sum_logprobs /
+ * len ** length_penalty (len = BOS + prompt + generated non-EOS tokens), first argmax (return_worst: first argmin), computed on the
+ * device; the chosen beam becomes the batch's only utterance so vx_nar(cb0 = NULL) continues with it.  *out_pick = beam index. */
+VX_API int vx_ar_fork(vx_engine* e, int n_beams, void* stream);
+VX_API int vx_ar_select_beam(vx_engine* e, float length_penalty, int return_worst, int* out_pick, void* stream);
 VX_API int vx_ar_decode(vx_engine* e, int max_new, int top_k, float top_p, float temperature, uint64_t seed,
                  int ignore_eos, const int32_t* forced_tokens, int32_t* out_tokens, int32_t* out_lens,
                  float* out_sum_logprobs, int mem, void* stream);

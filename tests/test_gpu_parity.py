@@ -180,6 +180,62 @@ def test_fused_decode_variant(monkeypatch, names):
     eng.close()
 
 
+def test_best_of_shares_one_prefill_and_ranks_on_device():
+    """SURVEY 8(f2) / models/vallex.py:525-527,572-594: best_of beams come from ONE prefill (vx_ar_fork replicates the decode
+    state on the device) and must be indistinguishable from best_of replicated prefills: same sampled tokens, lengths and
+    sum_logprobs per beam under the same Philox seed.  The per-beam sum_logprobs are checked against the ORACLE's logits along
+    each beam's own token sequence, and the device-side best / worst choice against the reference's formula."""
+    from oracle.vallex_oracle import OracleVALLE
+    g = load_golden("tiny_en")
+    sd = state_dict_for(g["seed"])
+    nb, steps = 5, 10
+    m = _valle(sd, "fp32", max_ctx=256, max_batch=nb)
+    eng = m.engine
+    x, prompt = g["x"].astype(np.int32), g["prompt"].astype(np.int32)
+    lang = m._lang_ids(len(x), int(g["Lp"]), "en", "en")
+    kw = dict(max_new=steps, top_k=-100, temperature=1.0, seed=77)
+    eng.set_batch([x] * nb, [lang] * nb, [prompt] * nb)
+    eng.ar_prefill()
+    toks_a, lens_a, slp_a = eng.ar_decode(**kw)
+    eng.set_batch([x], [lang], [prompt])
+    eng.ar_prefill()
+    eng.ar_fork(nb)
+    toks_b, lens_b, slp_b = eng.ar_decode(**kw)
+    assert np.array_equal(toks_a, toks_b) and np.array_equal(lens_a, lens_b)
+    np.testing.assert_allclose(slp_a, slp_b, rtol=0, atol=0)
+    assert len({tuple(t) for t in toks_b.tolist()}) > 1                      # the beams really differ (own Philox streams)
+    # oracle: log-softmax of the reference arithmetic's logits along each beam's sequence
+    o = OracleVALLE(sd)
+    xt = torch.from_numpy(x.astype(np.int64))[None]
+    want = np.zeros(nb, np.float64)
+    for b in range(nb):
+        for t in range(int(lens_b[b])):
+            yb = torch.from_numpy(np.concatenate([prompt[:, 0], toks_b[b, :t]]).astype(np.int64))[None]
+            dbg = {}
+            o.ar_decode(xt, yb, int(g["Lp"]), "en", "en", top_k=1, max_new_tokens=0, debug=dbg)
+            want[b] += float(torch.log_softmax(dbg["logits"][0][0], -1)[int(toks_b[b, t])])
+    np.testing.assert_allclose(slp_b, want, atol=5e-3)
+    P = prompt.shape[0]
+    for lp, worst in ((1.0, False), (1.0, True), (0.3, False), (2.0, True)):
+        avg = torch.from_numpy(slp_b) / (torch.from_numpy(lens_b.astype(np.int64)) + 1 + P) ** lp    # models/vallex.py:583-584
+        ref_pick = int(torch.argmin(avg) if worst else torch.argmax(avg))
+        eng.set_batch([x], [lang], [prompt])
+        eng.ar_prefill()
+        eng.ar_fork(nb)
+        eng.ar_decode(**kw)
+        pick = eng.ar_select_beam(lp, worst)
+        assert pick == ref_pick, (lp, worst, pick, ref_pick, avg)
+        codes = eng.nar(Tmax=int(lens_b[pick]))
+        assert np.array_equal(codes[0, :, 0], toks_b[pick, :int(lens_b[pick])])   # the NAR continues with the chosen beam
+    # through the public API
+    xt3 = torch.from_numpy(x.astype(np.int64))[None]
+    out = m.inference(xt3, torch.tensor([len(x)]), torch.from_numpy(prompt.astype(np.int64))[None], int(g["Lp"]), top_k=-100,
+                      temperature=1.0, prompt_language="en", text_language="en", best_of=nb, max_new_tokens=steps, seed=77, quiet=True)
+    avg = torch.from_numpy(slp_b) / (torch.from_numpy(lens_b.astype(np.int64)) + 1 + P) ** 1.0
+    assert np.array_equal(out[0, :, 0].numpy(), toks_b[int(torch.argmax(avg)), :out.shape[1]])
+    eng.close()
+
+
 def _cfg2_state_dict(g, tag):
     """synthetic checkpoint 0 with the fixture's crafted EOS row (make_golden.py cfg2): the reference stops at T = 1275 by itself"""
     sd = dict(state_dict_for(0, rounded=bool(tag)))

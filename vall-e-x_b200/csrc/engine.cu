@@ -72,6 +72,56 @@ __global__ void check_range_kernel(const int32_t* __restrict__ a, int64_t stride
   if (bad) atomicOr(flag, bit);
 }
 
+// best_of beams (models/vallex.py:525-527): after ONE prefill of the utterance, beam b > 0 gets a copy of beam 0's decode state:
+// KV rows [0, n) of every layer and head, the token buffer, the first-step logits.  grid (layers * heads, beams - 1).
+template <typename KVT>
+__global__ void fork_kv_kernel(KVT* __restrict__ kc, KVT* __restrict__ vc, size_t kv_layer_elems, int ctx_cap, int n) {
+  const int layer = blockIdx.x / kH, h = blockIdx.x % kH, b = blockIdx.y + 1;
+  const size_t src = (size_t)layer * kv_layer_elems + (size_t)h * ctx_cap * kDH;
+  const size_t dst = (size_t)layer * kv_layer_elems + ((size_t)b * kH + h) * ctx_cap * kDH;
+  const size_t cnt = (size_t)n * kDH * sizeof(KVT) / 16;   // rows are 128 B (bf16) / 256 B (fp32): whole uint4s
+  const uint4* ks = reinterpret_cast<const uint4*>(kc + src);
+  const uint4* vs = reinterpret_cast<const uint4*>(vc + src);
+  uint4* kd = reinterpret_cast<uint4*>(kc + dst);
+  uint4* vd = reinterpret_cast<uint4*>(vc + dst);
+  for (size_t i = threadIdx.x; i < cnt; i += blockDim.x) { kd[i] = ks[i]; vd[i] = vs[i]; }
+}
+__global__ void fork_state_kernel(Batch bt, int nb, int ylen, float* __restrict__ logits, float* __restrict__ xs, int32_t* S, int32_t* P, int32_t* row0) {
+  const int b = blockIdx.x + 1;
+  for (int i = threadIdx.x; i < ylen; i += blockDim.x) bt.y[(size_t)b * bt.ymax + i] = bt.y[i];
+  for (int i = threadIdx.x; i < kARLogits; i += blockDim.x) logits[(size_t)b * kARLogits + i] = logits[i];
+  for (int i = threadIdx.x; i < kD; i += blockDim.x) xs[(size_t)b * kD + i] = xs[i];
+  if (threadIdx.x == 0) {
+    S[b] = S[0]; P[b] = P[0]; row0[b] = row0[0];
+    bt.T[b] = 0; bt.finished[b] = 0; bt.sum_logprobs[b] = 0.f;
+  }
+}
+// models/vallex.py:583-594: avg = sum_logprobs / len ** length_penalty with len = BOS + prompt + generated non-EOS tokens;
+// best = first argmax, worst = first argmin; the chosen beam becomes utterance 0 (tokens, length) for the NAR stages.
+__global__ void select_beam_kernel(Batch bt, int nb, float length_penalty, int return_worst, int32_t* __restrict__ out_pick) {
+  __shared__ int s_pick;
+  if (threadIdx.x == 0) {
+    int pick = 0;
+    float best = 0.f;
+    for (int b = 0; b < nb; ++b) {
+      const float len = (float)(1 + bt.P[b] + bt.T[b]);
+      const float avg = bt.sum_logprobs[b] / powf(len, length_penalty);
+      if (b == 0 || (return_worst ? avg < best : avg > best)) { best = avg; pick = b; }
+    }
+    s_pick = pick;
+    out_pick[0] = pick;
+    out_pick[1] = bt.T[pick];
+  }
+  __syncthreads();
+  const int pick = s_pick;
+  if (pick != 0) {
+    const int n = 1 + bt.P[pick] + bt.T[pick];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) bt.y[i] = bt.y[(size_t)pick * bt.ymax + i];
+    __syncthreads();
+    if (threadIdx.x == 0) { bt.T[0] = bt.T[pick]; bt.sum_logprobs[0] = bt.sum_logprobs[pick]; }
+  }
+}
+
 struct Weight {
   std::vector<int64_t> shape;
   float* f32 = nullptr;  // device fp32 (always present until finalize may drop it for bf16 matrices)
@@ -113,7 +163,7 @@ struct vx_engine {
   float* dft_basis = nullptr;  // [1280][1296]
 
   // batch state
-  bool batch_set = false, prefilled = false, decoded = false;
+  bool batch_set = false, prefilled = false, decoded = false, forked = false;
   int B = 0, Smax = 0, Pmax = 0, ymax = 0;
   std::vector<int> hS, hP, hT, h_ar_row0;
   int ar_rows = 0, ar_maxlen = 0;
@@ -667,10 +717,11 @@ int vx_set_batch(vx_engine* e, int B, const int32_t* text_ids, const int32_t* te
   ENS(e->d_text, (size_t)B * Smax * 4);
   ENS(e->d_lang, (size_t)B * Smax * 4);
   ENS(e->d_prompt, (size_t)B * std::max(Pmax, 1) * kNQ * 4);
-  ENS(e->d_S, B * 4); ENS(e->d_P, B * 4); ENS(e->d_ar_row0, B * 4); ENS(e->d_nar_row0, B * 4);
-  ENS(e->d_T, B * 4); ENS(e->d_ctx, B * 4); ENS(e->d_budget, B * 4); ENS(e->d_fin, B * 4);
-  ENS(e->d_slp, B * 4); ENS(e->d_nact, 4);
-  ENS(e->d_y, (size_t)B * e->ymax * 4);
+  const int MB = e->max_batch;   // per-utterance state is sized for max_batch: vx_ar_fork grows the batch in place
+  ENS(e->d_S, MB * 4); ENS(e->d_P, MB * 4); ENS(e->d_ar_row0, MB * 4); ENS(e->d_nar_row0, MB * 4);
+  ENS(e->d_T, MB * 4); ENS(e->d_ctx, MB * 4); ENS(e->d_budget, MB * 4); ENS(e->d_fin, MB * 4);
+  ENS(e->d_slp, MB * 4); ENS(e->d_nact, 4);
+  ENS(e->d_y, (size_t)MB * e->ymax * 4);
   int r;
   if ((r = copy_in(e->d_text.p, text_ids, (size_t)B * Smax * 4, mem, st))) return r;
   if ((r = copy_in(e->d_lang.p, lang_ids, (size_t)B * Smax * 4, mem, st))) return r;
@@ -702,7 +753,7 @@ int vx_set_batch(vx_engine* e, int B, const int32_t* text_ids, const int32_t* te
   bt.budget = (int32_t*)e->d_budget.p; bt.finished = (int32_t*)e->d_fin.p;
   bt.sum_logprobs = (float*)e->d_slp.p; bt.n_active = (int32_t*)e->d_nact.p;
   e->Pmax = Pmax;
-  e->batch_set = true; e->prefilled = false; e->decoded = false;
+  e->batch_set = true; e->prefilled = false; e->decoded = false; e->forked = false;
   return VX_OK;
 }
 
@@ -716,8 +767,8 @@ int vx_ar_prefill(vx_engine* e, void* stream) {
   e->kv_layer_elems = (size_t)e->max_batch * kH * e->ctx_cap * kDH;
   { int _r = ensure_full_buffers(e, R); if (_r) return _r; }
   ENS(e->kc, e->kv_layer_elems * kL * kvb); ENS(e->vc, e->kv_layer_elems * kL * kvb);
-  ENS(e->xs, (size_t)B * kD * 4); ENS(e->xsn, (size_t)B * kD * 4); ENS(e->logits, (size_t)B * kARLogits * 4);
-  ENS(e->lastmap, B * 4);
+  ENS(e->xs, (size_t)e->max_batch * kD * 4); ENS(e->xsn, (size_t)e->max_batch * kD * 4); ENS(e->logits, (size_t)e->max_batch * kARLogits * 4);
+  ENS(e->lastmap, e->max_batch * 4);
   CK(cudaEventRecord(e->ev0, st));
   const Batch& bt = e->bt;
   float* x = (float*)e->x.p;
@@ -743,6 +794,52 @@ int vx_ar_prefill(vx_engine* e, void* stream) {
   CK(cudaEventElapsedTime(&e->ms_prefill, e->ev0, e->ev1));
   CK(cudaGetLastError());
   e->prefilled = true; e->decoded = false;
+  return VX_OK;
+}
+
+int vx_ar_fork(vx_engine* e, int n_beams, void* stream) {
+  if (!e || !e->prefilled || e->decoded) return fail(VX_ERR_STATE, "vx_ar_fork: call right after vx_ar_prefill");
+  if (e->B != 1) return fail(VX_ERR_STATE, "vx_ar_fork: the batch must hold exactly one utterance");
+  if (n_beams < 1 || n_beams > e->max_batch) return fail(VX_ERR_CAPACITY, "vx_ar_fork: n_beams exceeds max_batch");
+  if (n_beams == 1) return VX_OK;
+  CK(cudaSetDevice(e->device));
+  cudaStream_t st = pick(e, stream);
+  const int n = e->hS[0] + e->hP[0] + 1;   // keys in the cache after the prefill
+  if (e->mode == VX_BF16)
+    fork_kv_kernel<bf16><<<dim3(kL * kH, n_beams - 1), 256, 0, st>>>((bf16*)e->kc.p, (bf16*)e->vc.p, e->kv_layer_elems, e->ctx_cap, n);
+  else
+    fork_kv_kernel<float><<<dim3(kL * kH, n_beams - 1), 256, 0, st>>>((float*)e->kc.p, (float*)e->vc.p, e->kv_layer_elems, e->ctx_cap, n);
+  fork_state_kernel<<<n_beams - 1, 256, 0, st>>>(e->bt, n_beams, e->hP[0] + 1, (float*)e->logits.p, (float*)e->xs.p, (int32_t*)e->d_S.p,
+                                                (int32_t*)e->d_P.p, (int32_t*)e->d_ar_row0.p);
+  e->launches += 2;
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  e->hS.assign(n_beams, e->hS[0]);
+  e->hP.assign(n_beams, e->hP[0]);
+  e->h_ar_row0.assign(n_beams, e->h_ar_row0[0]);
+  e->B = n_beams;
+  e->bt.B = n_beams;
+  e->forked = true;
+  return VX_OK;
+}
+
+int vx_ar_select_beam(vx_engine* e, float length_penalty, int return_worst, int* out_pick, void* stream) {
+  if (!e || !e->decoded) return fail(VX_ERR_STATE, "vx_ar_select_beam: call after vx_ar_decode");
+  if (!e->forked && e->B != 1) return fail(VX_ERR_STATE, "vx_ar_select_beam: the batch does not hold the beams of one utterance (vx_ar_fork)");
+  CK(cudaSetDevice(e->device));
+  cudaStream_t st = pick(e, stream);
+  ENS(e->d_flag, 16);
+  select_beam_kernel<<<1, 256, 0, st>>>(e->bt, e->B, length_penalty, return_worst, (int32_t*)e->d_flag.p);
+  e->launches++;
+  CK(cudaMemcpyAsync(e->h_pinned, e->d_flag.p, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  if (out_pick) *out_pick = e->h_pinned[0];
+  e->hS.resize(1); e->hP.resize(1); e->h_ar_row0.resize(1);
+  e->hT.assign(1, e->h_pinned[1]);
+  e->B = 1;
+  e->bt.B = 1;
+  e->forked = false;
   return VX_OK;
 }
 

@@ -25,6 +25,8 @@ SIGNATURES = {
     "vx_set_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "vx_ar_prefill": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vx_ar_fork": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "vx_ar_select_beam": (C.c_int, [C.c_void_p, C.c_float, C.c_int, C.POINTER(C.c_int), C.c_void_p]),
     "vx_ar_budget": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "vx_ar_decode": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_uint64, C.c_int, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),

@@ -98,6 +98,22 @@ class Engine:
     def ar_prefill(self):
         check(self._lib.vx_ar_prefill(self._h, None), "vx_ar_prefill")
 
+    def ar_fork(self, n_beams: int):
+        """best_of beams from ONE prefill (models/vallex.py:525-527): replicate utterance 0's decode state on the device."""
+        check(self._lib.vx_ar_fork(self._h, int(n_beams), None), "vx_ar_fork")
+        self.B = int(n_beams)
+        self.S = self.S[:1] * self.B
+        self.P = self.P[:1] * self.B
+
+    def ar_select_beam(self, length_penalty: float = 1.0, return_worst: bool = False) -> int:
+        """models/vallex.py:583-594 on the device; the chosen beam becomes the batch's only utterance."""
+        pick = C.c_int()
+        check(self._lib.vx_ar_select_beam(self._h, float(length_penalty), int(bool(return_worst)), C.byref(pick), None),
+              "vx_ar_select_beam")
+        self.B = 1
+        self.S, self.P = self.S[:1], self.P[:1]
+        return pick.value
+
     def ar_budget(self, max_new: int = 0) -> int:
         n = C.c_int()
         check(self._lib.vx_ar_budget(self._h, int(max_new), C.byref(n)), "vx_ar_budget")

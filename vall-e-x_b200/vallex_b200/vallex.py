@@ -171,26 +171,26 @@ class VALLE:
         eng = self.engine
         seed = _resolve_seed(seed)
         nb = int(best_of)
-        eng.set_batch([text] * nb, [lang] * nb, [prompt] * nb)
-        eng.ar_prefill()
+        if nb > self._max_batch:
+            raise ValueError(f"best_of={nb} exceeds the engine's max_batch={self._max_batch}")
+        eng.set_batch([text], [lang], [prompt])
+        eng.ar_prefill()                      # ONE prefill; the reference recomputes it best_of times (models/vallex.py:525-527)
         t_pre = eng.timing()["ms_prefill"]
+        if nb > 1:
+            eng.ar_fork(nb)                   # KV rows / token buffer / first logits replicated on the device
         toks, lens, slp = eng.ar_decode(max_new=max_new_tokens, top_k=top_k, top_p=1.0, temperature=temperature, seed=seed)
         if int(lens.max()) == 0 and P + 1 == P:  # unreachable with prepend_bos (models/vallex.py:579-582)
             raise SyntaxError("well trained model shouldn't reach here.")
-        # choose the best / worst beam by sum_logprobs / len**length_penalty (models/vallex.py:583-594);
-        # len counts BOS + prompt + generated non-EOS tokens
-        length = (1 + P + lens).astype(np.float64)
-        avg = slp.astype(np.float64) / length ** length_penalty
-        pick = int(np.argmin(avg) if return_worst else np.argmax(avg))
+        # best / worst beam by sum_logprobs / len**length_penalty (models/vallex.py:583-594), chosen on the device; the
+        # NAR stages run on the chosen beam only (batch 1), like the reference.  (At the 16*S cap the reference draws one
+        # more sample whose logprob enters the ranking before it breaks, models/vallex.py:569-578; the engine stops at the
+        # cap without that extra forward pass -- only the ranking of beams that ALL hit the cap can differ.)
+        pick = eng.ar_select_beam(length_penalty, return_worst) if nb > 1 else 0
+        self.last_beam = dict(pick=pick, lens=lens.copy(), sum_logprobs=slp.copy())
         T = int(lens[pick])
         if not quiet:
             print(f"VALL-E EOS [{P} -> {P + 1 + T}]")
-        if nb > 1:  # NAR runs on the chosen beam only (batch 1), like the reference
-            eng.set_batch([text], [lang], [prompt])
-            codes = eng.nar(cb0=toks[pick:pick + 1, :max(T, 1)][:, :T] if T else np.zeros((1, 0), np.int32),
-                            t_lens=np.asarray([T], np.int32))
-        else:
-            codes = eng.nar(Tmax=T)
+        codes = eng.nar(Tmax=T)
         self.last_timing = dict(eng.timing(), ms_prefill=t_pre)
         out = torch.from_numpy(codes[:1, :T].astype(np.int64))
         return out.to(x.device) if x.is_cuda else out
