@@ -161,6 +161,9 @@ struct vx_engine {
   const float* pe = nullptr;
   int pe_rows = 0;
   float* dft_basis = nullptr;  // [1280][1296]
+  // tensor-core Vocos path (bf16 mode): split-3 weight images [hi | lo | hi] of every contraction, tap-major depthwise weights
+  struct { bool ready = false; void *embed = nullptr, *pw1[8] = {}, *pw2[8] = {}, *head = nullptr, *dft = nullptr; float* dwT[8] = {}; float* head_bias = nullptr; } vtc;
+  Buf v_imgA, v_imgB;
 
   // batch state
   bool batch_set = false, prefilled = false, decoded = false, forked = false;
@@ -483,12 +486,14 @@ void vx_destroy(vx_engine* e) {
                  &e->ffh, &e->kc, &e->vc, &e->a_img, &e->qkv16, &e->att_img, &e->h_img, &e->t_img, &e->q_img, &e->k_img, &e->vt_img, &e->xs, &e->xsn, &e->qkvs, &e->atts, &e->ffs, &e->logits, &e->part, &e->tick, &e->p_xb, &e->p_acc, &e->p_pf, &e->p_bar, &e->p_prof,
                  &e->lastmap, &e->out_tok, &e->forced, &e->yemb, &e->yrow0, &e->trow0, &e->tgtmap, &e->nlog, &e->codes,
                  &e->tl_dev, &e->cb0_dev, &e->v_codes, &e->v_feat, &e->v_col, &e->v_x, &e->v_h, &e->v_ff, &e->v_head,
-                 &e->v_spec, &e->v_frames, &e->v_wave};
+                 &e->v_spec, &e->v_frames, &e->v_wave, &e->v_imgA, &e->v_imgB};
   for (Buf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (e->ada_all) cudaFree(e->ada_all);
   if (e->ff2_t_blob) cudaFree(e->ff2_t_blob);
   if (e->dft_basis) cudaFree(e->dft_basis);
+  for (void* q : {e->vtc.embed, e->vtc.head, e->vtc.dft, (void*)e->vtc.head_bias}) if (q) cudaFree(q);
+  for (int i = 0; i < 8; ++i) { if (e->vtc.pw1[i]) cudaFree(e->vtc.pw1[i]); if (e->vtc.pw2[i]) cudaFree(e->vtc.pw2[i]); if (e->vtc.dwT[i]) cudaFree(e->vtc.dwT[i]); }
   if (e->h_pinned) cudaFreeHost(e->h_pinned);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
@@ -678,6 +683,37 @@ int vx_finalize_weights(vx_engine* e) {
     CK(cudaMalloc(&packed.f32, packed.numel * sizeof(float)));
     CK(cudaMemcpy(packed.f32, dst.data(), packed.numel * sizeof(float), cudaMemcpyHostToDevice));
     e->w["vocos.__embed_im2col"] = packed;
+  }
+  if (e->has_vocos && e->mode == VX_BF16 && !e->force_simt && !e->vtc.ready) {
+    // tensor-core Vocos path: split-3 weight images (bf16 x 3; vocos.cu) of the im2col'ed embed conv, the 16 point-wise
+    // linears, the head (1282 rows padded to 1408) and the inverse-DFT basis (K 1282 -> 1344)
+    auto img3 = [&](const float* w, int64_t rows, int K_src, int64_t ld, int K, void** out) -> int {
+      const int64_t rows_pad = (rows + 127) / 128 * 128;
+      CK(cudaMalloc(out, (size_t)rows_pad * 3 * K * sizeof(bf16)));
+      launch_pack_split3_weight(w, rows, K_src, ld, K, *out, st);
+      return VX_OK;
+    };
+    int r;
+    if ((r = img3(vec(e, "vocos.__embed_im2col"), 384, 896, 896, 896, &e->vtc.embed))) return r;
+    for (int i = 0; i < 8; ++i) {
+      const std::string p = "vocos.backbone.convnext." + std::to_string(i);
+      if ((r = img3(vec(e, p + ".pwconv1.weight"), 1152, 384, 384, 384, &e->vtc.pw1[i]))) return r;
+      if ((r = img3(vec(e, p + ".pwconv2.weight"), 384, 1152, 1152, 1152, &e->vtc.pw2[i]))) return r;
+      std::vector<float> w(384 * 7), wt(7 * 384);
+      CK(cudaMemcpy(w.data(), vec(e, p + ".dwconv.weight"), w.size() * 4, cudaMemcpyDeviceToHost));
+      for (int c = 0; c < 384; ++c)
+        for (int j = 0; j < 7; ++j) wt[j * 384 + c] = w[c * 7 + j];
+      CK(cudaMalloc(&e->vtc.dwT[i], wt.size() * 4));
+      CK(cudaMemcpy(e->vtc.dwT[i], wt.data(), wt.size() * 4, cudaMemcpyHostToDevice));
+    }
+    if ((r = img3(vec(e, "vocos.head.out.weight"), 1282, 384, 384, 384, &e->vtc.head))) return r;
+    CK(cudaMalloc(&e->vtc.head_bias, 1408 * 4));
+    CK(cudaMemset(e->vtc.head_bias, 0, 1408 * 4));
+    CK(cudaMemcpy(e->vtc.head_bias, vec(e, "vocos.head.out.bias"), 1282 * 4, cudaMemcpyDeviceToDevice));
+    if ((r = img3(e->dft_basis, 1280, 1282, 1296, 1344, &e->vtc.dft))) return r;
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    e->vtc.ready = true;
   }
   e->finalized = true;
   return VX_OK;
@@ -1203,6 +1239,41 @@ int vx_vocos_decode(vx_engine* e, const int32_t* codes, int B, int T, int bandwi
   float* h = (float*)e->v_h.p; float* ff = (float*)e->v_ff.p; float* head = (float*)e->v_head.p;
   float* spec = (float*)e->v_spec.p; float* frames = (float*)e->v_frames.p; float* wv = (float*)e->v_wave.p;
   launch_vocos_features((const int32_t*)e->v_codes.p, B, T, V("feature_extractor.codebook_weights"), feat, st);
+  if (e->vtc.ready) {
+    // ---- tensor-core path: every contraction on the tcgen05 GEMM with bf16 x 3 split operands (vocos.cu) ------------------
+    const int64_t Rp = (R + 127) / 128 * 128;
+    ENS(e->v_imgA, (size_t)Rp * 4032 * 2); ENS(e->v_imgB, (size_t)Rp * 3456 * 2);
+    ENS(e->v_head, (size_t)R * 1408 * 4);
+    head = (float*)e->v_head.p;
+    void *ia = e->v_imgA.p, *ib = e->v_imgB.p;
+    launch_vocos_im2col_split3(feat, B, T, ia, st);
+    launch_gemm_tc(ia, e->vtc.embed, V("backbone.embed.bias"), x, 384, R, 384, 3 * 896, TC_EPI_F32, st);
+    launch_layernorm(x, nullptr, R, 384, nullptr, nullptr, V("backbone.norm.scale.weight") + bandwidth_id * 384,
+                     V("backbone.norm.shift.weight") + bandwidth_id * 384, 1e-6f, x, st);
+    e->launches += 4;
+    for (int i = 0; i < 8; ++i) {
+      const std::string p = "backbone.convnext." + std::to_string(i);
+      launch_vocos_dwconv_ln_split3(x, B, T, e->vtc.dwT[i], V(p + ".dwconv.bias"), V(p + ".norm.scale.weight") + bandwidth_id * 384,
+                                    V(p + ".norm.shift.weight") + bandwidth_id * 384, ia, st);
+      launch_gemm_tc(ia, e->vtc.pw1[i], V(p + ".pwconv1.bias"), ib, 0, R, 1152, 3 * 384, TC_EPI_GELU_SPLIT3, st);
+      launch_gemm_tc(ib, e->vtc.pw2[i], V(p + ".pwconv2.bias"), x, 384, R, 384, 3 * 1152, TC_EPI_F32_SCALE_RESIDUAL, st, V(p + ".gamma"));
+      e->launches += 3;
+    }
+    launch_vocos_ln_split3(x, R, V("backbone.final_layer_norm.weight"), V("backbone.final_layer_norm.bias"), ia, st);
+    launch_gemm_tc(ia, e->vtc.head, e->vtc.head_bias, head, 1408, R, 1408, 3 * 384, TC_EPI_F32, st);
+    launch_vocos_spectrum_split3(head, 1408, R, ia, st);
+    launch_gemm_tc(ia, e->vtc.dft, nullptr, frames, 1280, R, 1280, 3 * 1344, TC_EPI_F32, st);
+    launch_vocos_overlap_add(frames, B, T, V("head.istft.window"), wv, st);
+    e->launches += 5;
+    if ((r = copy_out(wave, wv, (size_t)R * 320 * 4, mem, st))) return r;
+    CK(cudaEventRecord(e->ev1, st));
+    CK(cudaMemcpyAsync(e->h_pinned, e->d_flag.p, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&e->ms_vocos, e->ev0, e->ev1));
+    CK(cudaGetLastError());
+    if (e->h_pinned[0] != 0) return fail(VX_ERR_ARG, "vx_vocos_decode: code out of range (0..1023)");
+    return VX_OK;
+  }
   launch_vocos_im2col7(feat, B, T, 128, col, st);
   launch_gemm(col, 896, V("__embed_im2col"), 0, V("backbone.embed.bias"), x, 384, R, 384, 896, EPI_NONE, nullptr, st);
   launch_layernorm(x, nullptr, R, 384, nullptr, nullptr, V("backbone.norm.scale.weight") + bandwidth_id * 384,

@@ -18,7 +18,9 @@
 namespace vx {
 using namespace tc;
 
-enum TcEpi { TC_BF16_ROW = 0, TC_F32_RESIDUAL = 1, TC_BF16_IMAGE_RELU = 2, TC_F32 = 3, TC_QKV_HEADS = 4 };
+enum TcEpi { TC_BF16_ROW = 0, TC_F32_RESIDUAL = 1, TC_BF16_IMAGE_RELU = 2, TC_F32 = 3, TC_QKV_HEADS = 4, TC_F32_SCALE_RESIDUAL = 5,
+             TC_GELU_SPLIT3 = 6 };
+__device__ __forceinline__ float tc_gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 template <int BN>
 struct TcCfg {
@@ -33,7 +35,7 @@ struct TcCfg {
 template <int BN, int EPI>
 __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const bf16* __restrict__ A, const bf16* __restrict__ W,
                                                          const float* __restrict__ bias, void* __restrict__ out,
-                                                         int64_t ldc, int64_t M, int N, int K) {
+                                                         int64_t ldc, int64_t M, int N, int K, const float* __restrict__ aux) {
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -180,6 +182,35 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const bf16* __restrict_
                 *reinterpret_cast<uint16_t*>(vb + d * 128 + ((kc ^ (d & 7)) << 4) + kl * 2) = __bfloat16_as_ushort(__float2bfloat16_rn(v[i]));
               }
             }
+          } else if constexpr (EPI == TC_GELU_SPLIT3) {
+            // Vocos pwconv1: GELU(acc + bias) as the NEXT contraction's split-3 operand image [rows, 3N] = [hi | hi | lo]
+            // (bf16 x 3: a*b ~ a_hi*b_hi + a_hi*b_lo + a_lo*b_hi against the weight image [hi | lo | hi])
+            uint8_t* img = reinterpret_cast<uint8_t*>(out);
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              uint32_t hw[4], lw[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float x0 = tc_gelu_exact(v[i + 2 * e]), x1 = tc_gelu_exact(v[i + 2 * e + 1]);
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+                hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+              }
+              const uint4 hp = make_uint4(hw[0], hw[1], hw[2], hw[3]), lp = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+              *reinterpret_cast<uint4*>(img + tile_image_offset(row, n0 + i, 3 * N)) = hp;
+              *reinterpret_cast<uint4*>(img + tile_image_offset(row, N + n0 + i, 3 * N)) = hp;
+              *reinterpret_cast<uint4*>(img + tile_image_offset(row, 2 * N + n0 + i, 3 * N)) = lp;
+            }
+          } else if constexpr (EPI == TC_F32_SCALE_RESIDUAL) {
+            float* o = reinterpret_cast<float*>(out) + row * ldc + n0;   // Vocos pwconv2: x += gamma[n] * (acc + bias[n])
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              float4 r = *reinterpret_cast<const float4*>(o + i);
+              const float4 g = __ldg(reinterpret_cast<const float4*>(aux + n0 + i));
+              r.x = fmaf(g.x, v[i], r.x); r.y = fmaf(g.y, v[i + 1], r.y); r.z = fmaf(g.z, v[i + 2], r.z); r.w = fmaf(g.w, v[i + 3], r.w);
+              *reinterpret_cast<float4*>(o + i) = r;
+            }
           } else if constexpr (EPI == TC_F32_RESIDUAL) {
             float* o = reinterpret_cast<float*>(out) + row * ldc + n0;
 #pragma unroll
@@ -207,7 +238,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const bf16* __restrict_
 
 template <int BN, int EPI>
 static void tc_launch(const bf16* A, const bf16* W, const float* bias, void* out, int64_t ldc, int64_t M, int N, int K,
-                      cudaStream_t st) {
+                      const float* aux, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
   static bool attr_done[64] = {};
   int dev = 0;
@@ -218,24 +249,26 @@ static void tc_launch(const bf16* A, const bf16* W, const float* bias, void* out
   }
   const int tiles = (int)((M + 127) / 128) * (N / BN);
   const int grid = tiles < kSMs ? tiles : kSMs;
-  gemm_tc_kernel<BN, EPI><<<grid, 192, Cfg::kSmemBytes, st>>>(A, W, bias, out, ldc, M, N, K);
+  gemm_tc_kernel<BN, EPI><<<grid, 192, Cfg::kSmemBytes, st>>>(A, W, bias, out, ldc, M, N, K, aux);
 }
 
 // epi: TcEpi.  N % 256 == 0 uses 128x256 tiles (shared-memory read rate of the A/B operands stays under
 // 128 B/clk/SM), otherwise 128x128.  K % 64 == 0.  A and W are tile images; M is padded to 128 by the caller's
 // allocation (rows >= M are never stored).
 void launch_gemm_tc(const void* A_img, const void* W_img, const float* bias, void* out, int64_t ldc, int64_t M, int N,
-                    int K, int epi, cudaStream_t st) {
+                    int K, int epi, cudaStream_t st, const float* aux) {
   if (M <= 0) return;
   const bf16* A = (const bf16*)A_img;
   const bf16* W = (const bf16*)W_img;
 #define VX_TC(BN_)                                                                                      \
   switch (epi) {                                                                                        \
-    case TC_BF16_ROW: tc_launch<BN_, TC_BF16_ROW>(A, W, bias, out, ldc, M, N, K, st); break;            \
-    case TC_F32_RESIDUAL: tc_launch<BN_, TC_F32_RESIDUAL>(A, W, bias, out, ldc, M, N, K, st); break;    \
-    case TC_BF16_IMAGE_RELU: tc_launch<BN_, TC_BF16_IMAGE_RELU>(A, W, bias, out, ldc, M, N, K, st); break; \
-    case TC_QKV_HEADS: tc_launch<BN_, TC_QKV_HEADS>(A, W, bias, out, ldc, M, N, K, st); break;          \
-    default: tc_launch<BN_, TC_F32>(A, W, bias, out, ldc, M, N, K, st); break;                         \
+    case TC_BF16_ROW: tc_launch<BN_, TC_BF16_ROW>(A, W, bias, out, ldc, M, N, K, aux, st); break;            \
+    case TC_F32_RESIDUAL: tc_launch<BN_, TC_F32_RESIDUAL>(A, W, bias, out, ldc, M, N, K, aux, st); break;    \
+    case TC_BF16_IMAGE_RELU: tc_launch<BN_, TC_BF16_IMAGE_RELU>(A, W, bias, out, ldc, M, N, K, aux, st); break; \
+    case TC_QKV_HEADS: tc_launch<BN_, TC_QKV_HEADS>(A, W, bias, out, ldc, M, N, K, aux, st); break;          \
+    case TC_F32_SCALE_RESIDUAL: tc_launch<BN_, TC_F32_SCALE_RESIDUAL>(A, W, bias, out, ldc, M, N, K, aux, st); break; \
+    case TC_GELU_SPLIT3: tc_launch<BN_, TC_GELU_SPLIT3>(A, W, bias, out, ldc, M, N, K, aux, st); break; \
+    default: tc_launch<BN_, TC_F32>(A, W, bias, out, ldc, M, N, K, aux, st); break;                         \
   }
   // 128x256 tiles keep the operand read rate under the shared-memory limit, but a small problem needs enough tiles to
   // cover the 148 SMs: fall back to 128x128 when the 256-wide tiling would leave most of the chip idle.
@@ -268,6 +301,38 @@ void launch_pack_tile_image(const float* src, int64_t rows, int K, void* img, cu
   const int64_t rows_pad = (rows + 127) / 128 * 128;
   const int64_t total = rows_pad * (K >> 3);
   pack_tile_image_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, rows, K, (uint8_t*)img, rows_pad);
+}
+
+// fp32 weight [rows, K] -> split-3 bf16 tile image [rows_pad, 3K] = [hi | lo | hi] (rows padded to 128 with zeros): the B
+// operand of the bf16 x 3 contractions (Vocos), against activation images [hi | hi | lo].  ld = row stride of src (>= K_src);
+// columns >= K_src up to K are zero padding.
+__global__ void pack_split3_weight_kernel(const float* __restrict__ src, int64_t rows, int K_src, int64_t ld, int K,
+                                          uint8_t* __restrict__ img, int64_t rows_pad) {
+  const int64_t chunk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte chunk (8 elements) of the [rows_pad, K] grid
+  const int64_t total = rows_pad * (K >> 3);
+  if (chunk >= total) return;
+  const int64_t r = chunk / (K >> 3);
+  const int k = (int)(chunk % (K >> 3)) * 8;
+  uint32_t hw[4] = {0, 0, 0, 0}, lw[4] = {0, 0, 0, 0};
+  if (r < rows) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float x0 = (k + 2 * e < K_src) ? src[r * ld + k + 2 * e] : 0.f, x1 = (k + 2 * e + 1 < K_src) ? src[r * ld + k + 2 * e + 1] : 0.f;
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+      const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+      hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+  }
+  const uint4 hp = make_uint4(hw[0], hw[1], hw[2], hw[3]), lp = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  *reinterpret_cast<uint4*>(img + tile_image_offset(r, k, 3 * K)) = hp;
+  *reinterpret_cast<uint4*>(img + tile_image_offset(r, K + k, 3 * K)) = lp;
+  *reinterpret_cast<uint4*>(img + tile_image_offset(r, 2 * K + k, 3 * K)) = hp;
+}
+void launch_pack_split3_weight(const float* src, int64_t rows, int K_src, int64_t ld, int K, void* img, cudaStream_t st) {
+  const int64_t rows_pad = (rows + 127) / 128 * 128;
+  const int64_t total = rows_pad * (K >> 3);
+  pack_split3_weight_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, rows, K_src, ld, K, (uint8_t*)img, rows_pad);
 }
 
 // LayerNorm / AdaLN rows -> bf16 tile image (the A operand of the next GEMM); same math as layernorm_kernel.

@@ -81,10 +81,13 @@ void launch_attn_decode(const Batch& bt, const float* qkv_step, void* kcache, vo
 
 // ---- bf16 tensor-core path (tcgen05 GEMM, mma.sync attention); operands are "tile images" (tc_common.cuh) ----
 enum TcEpilogue { TC_EPI_BF16_ROW = 0, TC_EPI_F32_RESIDUAL = 1, TC_EPI_BF16_IMAGE_RELU = 2, TC_EPI_F32 = 3,
-                  TC_EPI_QKV_HEADS = 4 };   // 4: N = 3072 QKV projection written as the per-head operand images of attention_t5.cu
+                  TC_EPI_QKV_HEADS = 4, TC_EPI_F32_SCALE_RESIDUAL = 5, TC_EPI_GELU_SPLIT3 = 6 };
+                  // 5: out[r][n] += aux[n] * (acc + bias[n]) (Vocos gamma residual); 6: GELU(acc + bias) -> split-3 image [rows, 3N]   // 4: N = 3072 QKV projection written as the per-head operand images of attention_t5.cu
                                             //    (out = [q_img | k_img | vt_img], ldc = padded row count R)
 void launch_gemm_tc(const void* A_img, const void* W_img, const float* bias, void* out, int64_t ldc, int64_t M, int N,
-                    int K, int epi, cudaStream_t st);
+                    int K, int epi, cudaStream_t st, const float* aux = nullptr);
+// fp32 weight [rows, K_src] (row stride ld) -> split-3 image [pad128(rows), 3K] = [hi | lo | hi]; K % 64 == 0, K >= K_src
+void launch_pack_split3_weight(const float* src, int64_t rows, int K_src, int64_t ld, int K, void* img, cudaStream_t st);
 void launch_pack_tile_image(const float* src, int64_t rows, int K, void* img, cudaStream_t st);
 void launch_layernorm_image(const float* x, const int32_t* row_map, int64_t rows, const float* gamma,
                             const float* beta, const float* ada_w, const float* ada_b, float eps, void* img,
@@ -110,6 +113,12 @@ void launch_vocos_im2col7(const float* in, int B, int T, int C, float* out, cuda
 void launch_vocos_dwconv7(const float* x, int B, int T, int C, const float* w, const float* bias, float* out,
                           cudaStream_t st);
 void launch_vocos_spectrum(const float* head_out, int64_t rows, float* spec, int ldspec, cudaStream_t st);
+// tensor-core Vocos path (bf16 x 3 split operands; activation images are [rows_pad, 3K] = [hi | hi | lo]):
+void launch_vocos_im2col_split3(const float* feats, int B, int T, void* img, cudaStream_t st);                 // K = 896
+void launch_vocos_dwconv_ln_split3(const float* x, int B, int T, const float* dw_wT, const float* dw_b, const float* scale,
+                                   const float* shift, void* img, cudaStream_t st);                              // K = 384
+void launch_vocos_ln_split3(const float* x, int64_t rows, const float* gamma, const float* beta, void* img, cudaStream_t st);  // K = 384
+void launch_vocos_spectrum_split3(const float* head_out, int ldh, int64_t rows, void* img, cudaStream_t st);     // K = 1344
 void launch_vocos_overlap_add(const float* frames, int B, int T, const float* window, float* wave, cudaStream_t st);
 
 }  // namespace vx
