@@ -366,6 +366,7 @@ def main():
         raise SystemExit("bench.py needs a B200: there is no CPU fallback for the product path")
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
+    t_start = time.perf_counter()
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
         sd = broadcast_state_dict(synthetic_state_dict(0) if rank == 0 else None, src=0, device=dev)
@@ -378,7 +379,13 @@ def main():
     m.load_state_dict(sd)
     m.to(dev).eval()
     voc = Vocos(vsd).to(dev).share_engine(m)
+    t_sd = time.perf_counter()
     eng = m.engine
+    torch.cuda.synchronize()
+    # start-up: checkpoint generation on rank 0 + NCCL broadcast (N > 1; the tensors stay in HBM and are ingested device-to-
+    # device, vx_load_weight_mem), then weight packing (tile images, transposes, AdaLN tables) on the device
+    startup = {"checkpoint_and_broadcast_s": t_sd - t_start, "ingest_and_pack_s": time.perf_counter() - t_sd,
+               "ingest": "device-to-device from the NCCL receive buffers" if world > 1 else "host fp32 -> device"}
     lib, h = eng.raw()
     x, Lp, prompt = workload_inputs()
     S, P = len(x), prompt.shape[0]
@@ -497,6 +504,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * e2e_elapsed / a.steps, "rtf": (e2e_elapsed / a.steps) / (T_NEW / 75.0)},
         "gpu_launches": int(launches),
+        "startup_s": startup,
         "clocks": clk,
         "parity": parity,
         "roofline": {"kernel": decode_kernel + " (engine-reported; one launch = all decode steps; per-step figures)", "bound": "hbm",

@@ -64,6 +64,10 @@ VX_API void vx_destroy(vx_engine* e);
  * vx_finalize_weights: strict check (every key present, shapes match), packs to the kernel layouts and
  * precomputes the 7x25 AdaLN (weight,bias) vectors (modules/transformer.py:93-108). */
 VX_API int vx_load_weight(vx_engine* e, const char* key, const float* data, const int64_t* shape, int ndim);
+/* Same with `mem` saying where `data` lives: VX_DEVICE takes a device pointer on the engine's GPU (e.g. the NCCL receive
+ * buffer of the multi-GPU start-up broadcast, vallex_b200/dist.py) -- the tensor is copied and packed on the device and
+ * never visits the host. */
+VX_API int vx_load_weight_mem(vx_engine* e, const char* key, const float* data, const int64_t* shape, int ndim, int mem);
 VX_API int vx_finalize_weights(vx_engine* e);
 
 /* Replaces: the argument marshalling of `VALLE.inference` (models/vallex.py:458-527): B independent

@@ -502,7 +502,12 @@ void vx_destroy(vx_engine* e) {
 }
 
 int vx_load_weight(vx_engine* e, const char* key, const float* data, const int64_t* shape, int ndim) {
-  if (!e || !key || !data || !shape || ndim < 1 || ndim > 4) return fail(VX_ERR_ARG, "vx_load_weight: bad arguments");
+  return vx_load_weight_mem(e, key, data, shape, ndim, VX_HOST);
+}
+
+int vx_load_weight_mem(vx_engine* e, const char* key, const float* data, const int64_t* shape, int ndim, int mem) {
+  if (!e || !key || !data || !shape || ndim < 1 || ndim > 4 || (mem != VX_HOST && mem != VX_DEVICE))
+    return fail(VX_ERR_ARG, "vx_load_weight: bad arguments");
   CK(cudaSetDevice(e->device));
   Weight wt;
   wt.numel = 1;
@@ -518,7 +523,7 @@ int vx_load_weight(vx_engine* e, const char* key, const float* data, const int64
     e->w.erase(it);
   }
   CK(cudaMalloc(&wt.f32, std::max<size_t>(wt.numel, 4) * sizeof(float)));
-  CK(cudaMemcpy(wt.f32, data, wt.numel * sizeof(float), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(wt.f32, data, wt.numel * sizeof(float), mem == VX_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice));
   e->w[key] = wt;
   e->finalized = false;
   return VX_OK;

@@ -21,6 +21,7 @@ SIGNATURES = {
     "vx_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "vx_destroy": (None, [C.c_void_p]),
     "vx_load_weight": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int]),
+    "vx_load_weight_mem": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int, C.c_int]),
     "vx_finalize_weights": (C.c_int, [C.c_void_p]),
     "vx_set_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                C.c_void_p, C.c_int, C.c_int, C.c_void_p]),

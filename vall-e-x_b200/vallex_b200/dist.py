@@ -26,7 +26,9 @@ def state_dict_manifest(sd: Dict[str, torch.Tensor]) -> List[Tuple[str, Tuple[in
 
 def broadcast_state_dict(sd: Optional[Dict[str, torch.Tensor]], src: int = 0, device: str = "cpu",
                          chunk_elems: int = 64 * 1024 * 1024) -> "OrderedDict[str, torch.Tensor]":
-    """Rank `src` passes the fp32 state dict, the others pass None; everybody returns the full dict (CPU fp32).
+    """Rank `src` passes the fp32 state dict, the others pass None; everybody returns the full dict as views of the
+    receive buffers ON `device` (cuda: the tensors stay in HBM and `Engine._load` ingests them device-to-device through
+    vx_load_weight_mem -- nothing bounces through the host; cpu: the gloo test path).
     The payload travels as a few large flat buffers (bucket size chosen for launch latency, not link count).
     Tied tensors (nar_predict_layers.j <-> nar_audio_embeddings.j+2) are sent once and re-tied."""
     rank = dist.get_rank()
@@ -59,11 +61,10 @@ def broadcast_state_dict(sd: Optional[Dict[str, torch.Tensor]], src: int = 0, de
                 flat[off:off + m].copy_(sd[k].reshape(-1))
                 off += m
         dist.broadcast(flat, src=src)
-        host = flat.to("cpu")
         off = 0
         for k, s in group:
             m = _numel(s)
-            out[k] = host[off:off + m].reshape(s).clone()
+            out[k] = flat[off:off + m].reshape(s)   # a view of the receive buffer, wherever it lives
             off += m
     ordered: "OrderedDict[str, torch.Tensor]" = OrderedDict()
     for k, s, a in manifest:

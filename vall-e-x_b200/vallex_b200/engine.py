@@ -50,6 +50,14 @@ class Engine:
 
     # ---- weights -------------------------------------------------------------------------
     def _load(self, key: str, value):
+        if getattr(value, "is_cuda", False) and value.device.index == self.device:
+            # already on this engine's GPU (e.g. the NCCL receive buffer of dist.broadcast_state_dict): device-to-device ingest
+            t = value.detach().float().contiguous()
+            if t.ndim == 0:
+                t = t.reshape(1)
+            shape = (C.c_int64 * t.ndim)(*t.shape)
+            check(self._lib.vx_load_weight_mem(self._h, key.encode(), ptr(t), shape, t.ndim, VX_DEVICE), f"vx_load_weight_mem({key})")
+            return
         a = _np_f32(value)
         if a.ndim == 0:
             a = a.reshape(1)
