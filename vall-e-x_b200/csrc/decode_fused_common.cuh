@@ -100,87 +100,141 @@ __device__ __forceinline__ void wo_issue(WoPre& wp, const bf16* __restrict__ Wo,
 }
 
 // attention unit + head rendezvous + out-proj share.  `att_epoch`: tickets this unit's head has seen so far.
+// The unit's keys [j0, j1) are spread over the 16 warps in runs of 16 (4 key rows per load instruction: 8 lanes x 16 B = one
+// 128-byte row, 512 contiguous bytes per instruction); a warp requests ALL of its K and V chunks of a 256-key round at once
+// (one memory round trip), keeps a running (max, sum, o[64]) over its rounds, and the 16 warp partials are folded through
+// shared memory in fixed order.  (The round-1 unit took one key per thread for Q.K, two block reductions, then 2-3 dependent
+// V loads per 8-lane group and a 64-deep serial fold: ~3 more dependent L2 round trips and 5 more block barriers per layer.)
 __device__ void attn_unit_fused(const PParams& p, int layer, int b, int h, int split, float* smem, int& att_epoch,
                                 const WoPre& wp, const bf16* __restrict__ Wo, int r0, int r1, long long* accO) {
-  float* sq = smem;                  // [64]   (reused for the folded head output)
-  float* sknew = smem + 64;
-  float* svnew = smem + 128;
-  float* red = smem + 192;
-  float* sp = smem + 256;            // [PCHUNK]
-  float* sacc = sp + PCHUNK;         // [PNT/8][64]
+  float* sq = smem;                  // [64]   folded head output
+  float* wm = smem + 64;             // [16]   warp partial max
+  float* wl = smem + 80;             // [16]   warp partial sum
+  float* wo = smem + 128;            // [16][64] warp partial outputs
   const Batch& bt = p.bt;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 3, sub = lane & 7;
   const int pos = bt.S[b] + bt.P[b] + ld_cg(bt.T + b);
   const int n = pos + 1;
   int chunk = (n + p.nsplit - 1) / p.nsplit;
   chunk = (chunk + 31) & ~31;
   const int j0 = split * chunk, j1 = min(n, j0 + chunk);
-  const float* row = p.qkv + (size_t)b * (3 * kD) + h * kDH;
-  __syncthreads();
-  if (tid < kDH) {
-    sq[tid] = __ldcg(row + tid) * 0.125f;
-    sknew[tid] = __ldcg(row + kD + tid);
-    svnew[tid] = __ldcg(row + 2 * kD + tid);
-  }
-  __syncthreads();
+  const float* row = p.qkv + (size_t)b * (3 * kD) + h * kDH + sub * 8;
   bf16* kb = reinterpret_cast<bf16*>(p.kc) + (size_t)layer * p.kv_layer_elems + ((size_t)b * kH + h) * p.ctx_cap * kDH;
   bf16* vb = reinterpret_cast<bf16*>(p.vc) + (size_t)layer * p.kv_layer_elems + ((size_t)b * kH + h) * p.ctx_cap * kDH;
-  if (split == 0 && tid < kDH) {
-    store_as(kb + (size_t)pos * kDH + tid, sknew[tid]);
-    store_as(vb + (size_t)pos * kDH + tid, svnew[tid]);
+  // ---- first round's K / V chunks: requested before anything else -------------------------------------------------------
+  uint4 kr[4], vr[4];
+  const int wbase = j0 + warp * 16 + g;     // this lane group's first key of round 0
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int j = wbase + 4 * i;
+    const bool ok = j < j1 && j != pos;
+    kr[i] = ok ? __ldcg(reinterpret_cast<const uint4*>(kb + (size_t)j * kDH + sub * 8)) : make_uint4(0, 0, 0, 0);
+    vr[i] = ok ? __ldcg(reinterpret_cast<const uint4*>(vb + (size_t)j * kDH + sub * 8)) : make_uint4(0, 0, 0, 0);
   }
-  float mloc = -INFINITY;
-  for (int j = j0 + tid; j < j1; j += PNT) {
-    float s = 0.f;
-    if (j == pos) {
+  float q[8];
+  {
+    const float4 a = __ldcg(reinterpret_cast<const float4*>(row)), c = __ldcg(reinterpret_cast<const float4*>(row) + 1);
+    q[0] = a.x * 0.125f; q[1] = a.y * 0.125f; q[2] = a.z * 0.125f; q[3] = a.w * 0.125f;
+    q[4] = c.x * 0.125f; q[5] = c.y * 0.125f; q[6] = c.z * 0.125f; q[7] = c.w * 0.125f;
+  }
+  uint4 knew = make_uint4(0, 0, 0, 0), vnew = make_uint4(0, 0, 0, 0);   // the new row, bf16-rounded like the cached ones
+  if (j1 == n) {   // the split that holds the new key (warp-uniform): it also appends the row to the cache
+    const float4 k0 = __ldcg(reinterpret_cast<const float4*>(row + kD)), k1 = __ldcg(reinterpret_cast<const float4*>(row + kD) + 1);
+    const float4 v0 = __ldcg(reinterpret_cast<const float4*>(row + 2 * kD)), v1 = __ldcg(reinterpret_cast<const float4*>(row + 2 * kD) + 1);
+    auto pk = [](float x, float y) {
+      return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(x)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(y)) << 16);
+    };
+    knew = make_uint4(pk(k0.x, k0.y), pk(k0.z, k0.w), pk(k1.x, k1.y), pk(k1.z, k1.w));
+    vnew = make_uint4(pk(v0.x, v0.y), pk(v0.z, v0.w), pk(v1.x, v1.y), pk(v1.z, v1.w));
+    if (warp == 0 && g == 0) {
+      *reinterpret_cast<uint4*>(kb + (size_t)pos * kDH + sub * 8) = knew;
+      *reinterpret_cast<uint4*>(vb + (size_t)pos * kDH + sub * 8) = vnew;
+    }
+  }
+  float m = -INFINITY, l = 0.f;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int base = wbase; base - g < j1; base += 256) {   // warp-uniform trip count (base - g is the warp's first key of the round)
+    float sc[4];
 #pragma unroll
-      for (int d = 0; d < kDH; ++d) s = fmaf(sq[d], kv_round<bf16>(sknew[d]), s);
-    } else {
-      const bf16* kr = kb + (size_t)j * kDH;
+    for (int i = 0; i < 4; ++i) {
+      const int j = base + 4 * i;
+      const uint4 kk = (j == pos) ? knew : kr[i];
+      const uint32_t u[4] = {kk.x, kk.y, kk.z, kk.w};
+      float d = 0.f;
 #pragma unroll
-      for (int d = 0; d < kDH; d += 8) {
-        float w[8];
-        ldkv8(kr + d, w);
+      for (int e = 0; e < 4; ++e) {
+        d = fmaf(q[2 * e], __uint_as_float(u[e] << 16), d);
+        d = fmaf(q[2 * e + 1], __uint_as_float(u[e] & 0xffff0000u), d);
+      }
+      d += __shfl_xor_sync(0xffffffffu, d, 1);
+      d += __shfl_xor_sync(0xffffffffu, d, 2);
+      d += __shfl_xor_sync(0xffffffffu, d, 4);
+      sc[i] = (j < j1) ? d : -INFINITY;
+    }
+    uint4 vv[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s = fmaf(sq[d + i], w[i], s);
+    for (int i = 0; i < 4; ++i) vv[i] = (base + 4 * i == pos) ? vnew : vr[i];
+    if (base - g + 256 < j1) {   // next round's chunks (contexts beyond 256 keys per unit)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = base + 256 + 4 * i;
+        const bool ok = j < j1 && j != pos;
+        kr[i] = ok ? __ldcg(reinterpret_cast<const uint4*>(kb + (size_t)j * kDH + sub * 8)) : make_uint4(0, 0, 0, 0);
+        vr[i] = ok ? __ldcg(reinterpret_cast<const uint4*>(vb + (size_t)j * kDH + sub * 8)) : make_uint4(0, 0, 0, 0);
       }
     }
-    sp[j - j0] = s;
-    mloc = fmaxf(mloc, s);
-  }
-  const float m = block_max(mloc, red);
-  float lloc = 0.f;
-  for (int j = j0 + tid; j < j1; j += PNT) {
-    const float pr = expf(sp[j - j0] - m);
-    sp[j - j0] = pr;
-    lloc += pr;
-  }
-  const float l = block_sum(lloc, red);
-  constexpr int NG = PNT / 8;
-  const int g = tid >> 3, dc = (tid & 7) * 8;
-  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int j = j0 + g; j < j1; j += NG) {
-    const float pr = sp[j - j0];
-    float w[8];
-    if (j == pos) {
+    float bm = fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3]));
+    bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 8));
+    bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 16));
+    if (bm == -INFINITY) continue;            // warp-uniform: no key of this round belongs to the warp
+    const float mn = fmaxf(m, bm);
+    const float scale = expf(m - mn);         // 0 on the first round (m = -inf)
+    l *= scale;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) w[i] = kv_round<bf16>(svnew[dc + i]);
-    } else {
-      ldkv8(vb + (size_t)j * kDH + dc, w);
+    for (int e = 0; e < 8; ++e) acc[e] *= scale;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float pr = expf(sc[i] - mn);      // 0 for masked keys
+      l += pr;
+      const uint32_t u[4] = {vv[i].x, vv[i].y, vv[i].z, vv[i].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        acc[2 * e] = fmaf(pr, __uint_as_float(u[e] << 16), acc[2 * e]);
+        acc[2 * e + 1] = fmaf(pr, __uint_as_float(u[e] & 0xffff0000u), acc[2 * e + 1]);
+      }
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = fmaf(pr, w[i], acc[i]);
+    m = mn;
   }
+  // fold the 4 key groups of the warp, then the 16 warps (fixed order)
+  l += __shfl_xor_sync(0xffffffffu, l, 8);
+  l += __shfl_xor_sync(0xffffffffu, l, 16);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) sacc[g * kDH + dc + i] = acc[i];
+  for (int e = 0; e < 8; ++e) {
+    acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
+    acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+  }
+  if (g == 0) {   // (the previous use of this scratch is behind at least one grid barrier)
+    *reinterpret_cast<float4*>(wo + warp * kDH + sub * 8) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(wo + warp * kDH + sub * 8 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    if (sub == 0) { wm[warp] = m; wl[warp] = l; }
+  }
   __syncthreads();
-  float od = 0.f;
-  if (tid < kDH) {
-    for (int q = 0; q < NG; ++q) od += sacc[q * kDH + tid];
-  }
   float* pp = p.part + (((size_t)b * kH + h) * p.nsplit + split) * (kDH + 2);
-  if (tid < kDH) pp[2 + tid] = od;
-  if (tid == 0) { pp[0] = m; pp[1] = l; }
+  if (tid < kDH) {
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < PNW; ++w) M = fmaxf(M, wm[w]);
+    float L = 0.f, O = 0.f;
+#pragma unroll
+    for (int w = 0; w < PNW; ++w) {
+      const float wt = (wm[w] == -INFINITY) ? 0.f : expf(wm[w] - M);
+      L = fmaf(wt, wl[w], L);
+      O = fmaf(wt, wo[w * kDH + tid], O);
+    }
+    pp[2 + tid] = O;
+    if (tid == 0) { pp[0] = M; pp[1] = L; }
+  }
   __syncthreads();
   // ---- rendezvous of the head's key splits (all co-resident: one unit per CTA) ---------------------------------
   att_epoch += p.nsplit;
@@ -202,7 +256,7 @@ __device__ void attn_unit_fused(const PParams& p, int layer, int b, int h, int s
   if (tid < kDH) sq[tid] = att_combined(p, b, h * kDH + tid);
   __syncthreads();
   // ---- out-proj share: rows [r0,r1) x this head's 64 columns --------------------------------------------------------
-  const int grp = lane >> 3, sub = lane & 7;
+  const int grp = lane >> 3;
   float xv[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) xv[i] = sq[sub * 8 + i];
