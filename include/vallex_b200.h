@@ -131,6 +131,10 @@ VX_API int vx_debug_read(vx_engine* e, const char* what, float* dst, int64_t max
  * the engine picks the decode kernel from dtype mode, batch size and context, so bench.py reports this string instead of
  * guessing from the environment.  Valid until the next vx_ar_decode / vx_destroy. */
 VX_API const char* vx_last_decode_kernel(vx_engine* e);
+/* 1 if the last vx_ar_decode had to cut some utterance's budget below min(max_new, 16*S) because S+P+1+budget would not fit
+ * max_ctx (the reference has no such limit: it would run to its 16*S cap, models/vallex.py:577).  The Python mirror raises
+ * instead of returning a silently truncated result. */
+VX_API int vx_ar_ctx_clamped(vx_engine* e);
 
 /* Isolated kernel checks (tests/test_gpu_kernels.py); host fp32 buffers, current CUDA device.
  * vx_debug_gemm_tc: C[M,N] = A[M,K] W[N,K]^T (+bias) through the tcgen05 GEMM (epi 0: bf16 row-major, 1: fp32 += into

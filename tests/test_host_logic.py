@@ -262,6 +262,9 @@ class _FakeEngine:
     def ar_prefill(self):
         pass
 
+    def ctx_clamped(self):
+        return False
+
     def timing(self):
         return {"ms_prefill": 1.0, "ms_decode": 2.0, "ms_nar": 3.0, "decode_steps": 4, "kernel_launches": 5}
 

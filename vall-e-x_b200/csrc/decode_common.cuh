@@ -34,7 +34,9 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& ep
       asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
       if (++spins > (1u << 24)) __trap();  // a lost CTA must not hang the box
     } while ((int)(v - epoch) < 0);
-    // no acquire fence: every cross-CTA mutable value is read with ld.global.cg (L2), never through L1
+    // acquire side of the barrier (PTX memory model): orders this CTA's later reads after the arrivals it observed.  Every
+    // cross-CTA mutable value is additionally read with ld.global.cg (L2), never through L1.
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
     if (prof) { prof[0] = 2; prof[1] = clock64(); prof += 2; }
   }
   __syncthreads();

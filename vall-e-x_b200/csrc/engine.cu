@@ -193,6 +193,7 @@ struct vx_engine {
   int ctx_cap = 0;
   size_t kv_layer_elems = 0;
 
+  bool ctx_clamped = false;                          // last vx_ar_decode: some budget was cut by max_ctx (vx_ar_ctx_clamped)
   std::string decode_kernel;                         // name of the kernel the last vx_ar_decode launched
   float ms_prefill = 0, ms_decode = 0, ms_nar = 0, ms_vocos = 0;
   int64_t decode_steps = 0, launches = 0;
@@ -957,10 +958,12 @@ int vx_ar_decode(vx_engine* e, int max_new, int top_k, float top_p, float temper
   if (max_steps < 1) return fail(VX_ERR_CAPACITY, "vx_ar_decode: no room for new tokens (max_ctx too small)");
   std::vector<int32_t> bud(B);
   int final_ctx = 0;
+  e->ctx_clamped = false;
   for (int b = 0; b < B; ++b) {
     int v = 16 * e->hS[b];
     if (max_new > 0) v = std::min(v, max_new);
-    v = std::min(v, e->max_ctx - (e->hS[b] + e->hP[b] + 1) - 1);
+    const int room = e->max_ctx - (e->hS[b] + e->hP[b] + 1) - 1;
+    if (room < v) { v = room; e->ctx_clamped = true; }   // the KV cache, not EOS / 16*S / max_new, will end this utterance
     bud[b] = v;
     final_ctx = std::max(final_ctx, e->hS[b] + e->hP[b] + 1 + v);
   }
@@ -1324,6 +1327,7 @@ int vx_last_timing(vx_engine* e, float* ms_prefill, float* ms_decode, float* ms_
 }
 
 const char* vx_last_decode_kernel(vx_engine* e) { return e ? e->decode_kernel.c_str() : ""; }
+int vx_ar_ctx_clamped(vx_engine* e) { return (e && e->ctx_clamped) ? 1 : 0; }
 
 int vx_debug_read(vx_engine* e, const char* what, float* dst, int64_t max_elems, int64_t* out_elems) {
   if (!e || !what || !dst) return fail(VX_ERR_ARG, "vx_debug_read: bad arguments");

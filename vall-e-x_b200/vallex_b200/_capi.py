@@ -36,6 +36,7 @@ SIGNATURES = {
     "vx_last_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
                                  C.POINTER(C.c_float), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "vx_last_decode_kernel": (C.c_char_p, [C.c_void_p]),
+    "vx_ar_ctx_clamped": (C.c_int, [C.c_void_p]),
     "vx_debug_read": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     "vx_debug_gemm_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int]),
     "vx_debug_attn_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),

@@ -177,6 +177,10 @@ class Engine:
         return dict(ms_prefill=a.value, ms_decode=b.value, ms_nar=c.value, ms_vocos=d.value, decode_steps=s.value,
                     kernel_launches=k.value)
 
+    def ctx_clamped(self) -> bool:
+        """True if max_ctx (not EOS / 16*S / max_new) limited some utterance's budget in the last ar_decode."""
+        return bool(self._lib.vx_ar_ctx_clamped(self._h))
+
     def last_decode_kernel(self) -> str:
         """Engine-reported name of the kernel the last ar_decode launched."""
         v = self._lib.vx_last_decode_kernel(self._h)

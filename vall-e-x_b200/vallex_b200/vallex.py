@@ -181,6 +181,11 @@ class VALLE:
         toks, lens, slp = eng.ar_decode(max_new=max_new_tokens, top_k=top_k, top_p=1.0, temperature=temperature, seed=seed)
         if int(lens.max()) == 0 and P + 1 == P:  # unreachable with prepend_bos (models/vallex.py:579-582)
             raise SyntaxError("well trained model shouldn't reach here.")
+        if eng.ctx_clamped() and int(lens.max()) >= self._max_ctx - (S + P + 1) - 1:
+            # the reference has no context limit (it would run on to EOS or its 16*S cap, models/vallex.py:574-578): never
+            # hand back a silently truncated utterance
+            raise RuntimeError(f"KV cache exhausted: the utterance filled max_ctx={self._max_ctx} rows (S={S}, P={P}, {int(lens.max())} new "
+                               f"frames) before EOS / the 16*S cap; build VALLE(..., max_ctx=...) larger or pass max_new_tokens")
         # best / worst beam by sum_logprobs / len**length_penalty (models/vallex.py:583-594), chosen on the device; the
         # NAR stages run on the chosen beam only (batch 1), like the reference.  (At the 16*S cap the reference draws one
         # more sample whose logprob enters the ranking before it breaks, models/vallex.py:569-578; the engine stops at the
@@ -224,6 +229,11 @@ class VALLE:
             t_pre = eng.timing()["ms_prefill"]
             _, lens, _ = eng.ar_decode(max_new=max_new_tokens, top_k=top_k, top_p=1.0, temperature=temperature,
                                        seed=seed + c0)
+            if eng.ctx_clamped():
+                for b, (x, y, *_r) in enumerate(chunk):
+                    if int(lens[b]) >= self._max_ctx - (int(x.shape[1]) + int(y.shape[1]) + 1) - 1:
+                        raise RuntimeError(f"KV cache exhausted for utterance {c0 + b}: max_ctx={self._max_ctx} rows filled before EOS / the "
+                                           f"16*S cap; build VALLE(..., max_ctx=...) larger or pass max_new_tokens")
             codes = eng.nar(Tmax=int(lens.max()))
             t = dict(eng.timing(), ms_prefill=t_pre)
             for k, v in t.items():
