@@ -166,16 +166,27 @@ def cfg4_result(B: int, dtype: str = "bf16", reps: int = 1, device: int = 0):
     prm = [rng.integers(0, 1024, size=(P, 8)).astype(np.int32) for _ in range(B)]
     cb0 = rng.integers(0, 1024, size=(B, T)).astype(np.int32)
     tl = np.full((B,), T, np.int32)
+    import torch
+    from vallex_b200 import _capi
+    lib, h = eng.raw()
+    dev = f"cuda:{device}"
+    d_cb0, d_tl = torch.from_numpy(cb0).to(dev), torch.from_numpy(tl).to(dev)
+    d_codes = torch.zeros((B, T, 8), dtype=torch.int32, device=dev)
+    d_codes_t = torch.zeros((8, B, T), dtype=torch.int32, device=dev)
+    d_wave = torch.zeros((B, 320 * T), dtype=torch.float32, device=dev)
     t_nar = t_voc = 0.0
     launches = 0
-    for _ in range(reps + 1):
+    for _ in range(reps + 1):   # operands resident in HBM (device pointers through the C ABI), like the headline's `value` leg
         eng.set_batch(text, lang, prm)
         l0 = eng.timing()["kernel_launches"]
-        codes = eng.nar(cb0=cb0, t_lens=tl)
+        _capi.check(lib.vx_nar(h, _capi.ptr(d_cb0), _capi.ptr(d_tl), T, _capi.ptr(d_codes), _capi.VX_DEVICE, None), "vx_nar")
         t_nar = eng.timing()["ms_nar"]
-        wave = eng.vocos_decode(np.ascontiguousarray(codes.transpose(2, 0, 1)))
+        d_codes_t.copy_(d_codes.permute(2, 0, 1))
+        torch.cuda.current_stream().synchronize()
+        _capi.check(lib.vx_vocos_decode(h, _capi.ptr(d_codes_t), B, T, 2, _capi.ptr(d_wave), _capi.VX_DEVICE, None), "vx_vocos_decode")
         t_voc = eng.timing()["ms_vocos"]
         launches = eng.timing()["kernel_launches"] - l0
+    wave = d_wave.cpu().numpy()
     eng.close()
     assert np.isfinite(wave).all()
     L = S + P + T
