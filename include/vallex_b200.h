@@ -96,6 +96,19 @@ VX_API int vx_ar_prefill(vx_engine* e, void* stream);
  * by vx_ar_budget), out_lens [B] = T_b, out_sum_logprobs [B] nullable (models/vallex.py:572). */
 VX_API int vx_ar_budget(vx_engine* e, int max_new, int* out_max_steps);
 
+/* Continuous batching (engine extension; the reference decodes the sentences of a long text one after another,
+ * utils/generation.py:199-224).  vx_ar_decode_ex is vx_ar_decode with three more controls: `stop_on_finish` != 0 returns as soon
+ * as ONE more utterance has finished (EOS / budget) instead of waiting for the slowest one, `out_finished` [B] reports which
+ * slots are done, and `resume` != 0 continues the paused batch: slots that kept decoding carry on from the token they sampled
+ * last, slots refilled by vx_slot_prefill sample their first token.  out_tokens / out_lens always describe the slot's
+ * CURRENT utterance (tokens [0, T_b)).  vx_slot_prefill puts a new utterance (its own text / languages / prompt; S <= Smax and
+ * P <= Pmax of the vx_set_batch that sized the batch) into a finished slot: it is prefilled alone into the slot's KV region. */
+VX_API int vx_ar_decode_ex(vx_engine* e, int max_new, int top_k, float top_p, float temperature, uint64_t seed, int ignore_eos,
+                    const int32_t* forced_tokens, int32_t* out_tokens, int32_t* out_lens, float* out_sum_logprobs, int resume,
+                    int stop_on_finish, int32_t* out_finished, int mem, void* stream);
+VX_API int vx_slot_prefill(vx_engine* e, int slot, const int32_t* text_ids, int S, const int32_t* lang_ids,
+                    const int32_t* prompt_codes, int P, int mem, void* stream);
+
 /* Replaces: `x.repeat(best_of, 1, 1); y.repeat(best_of, 1)` (models/vallex.py:525-527), where the reference pushes best_of
  * copies of the utterance through the first (full-sequence) iteration.  Here the utterance is prefilled ONCE
  * (vx_set_batch with B = 1, vx_ar_prefill) and vx_ar_fork replicates its decode state -- KV rows of every layer, token buffer,

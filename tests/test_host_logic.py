@@ -250,17 +250,29 @@ def test_long_text_sliding_window_prompt_sequence(tmp_path, monkeypatch, with_pr
 
 
 class _FakeEngine:
-    """Stands in for vallex_b200.engine.Engine: records the batches the host layer forms; utterance b of a batch 'generates'
-    T_b = S_b frames whose codes are (b, t)-dependent."""
+    """Stands in for vallex_b200.engine.Engine: utterance with S phonemes 'generates' T = S frames (token t of an utterance whose
+    first phoneme id is f is (10 f + t) % 1024), one token per slot per step; records the batches, refills and launches."""
     def __init__(self):
-        self.batches, self.seeds = [], []
+        self.batches, self.seeds, self.refills, self.launches = [], [], [], []
 
-    def set_batch(self, texts, langs, prompts):
-        self.cur = (texts, langs, prompts)
+    def _tok(self, text, t):
+        return (int(text[0]) * 10 + t) % 1024
+
+    def set_batch(self, texts, langs, prompts, Smax=0, Pmax=0):
+        self.texts = [np.asarray(t) for t in texts]
+        self.T = [0] * len(texts)
+        self.fin = [0] * len(texts)
+        self.caps = (Smax, Pmax)
+        self.caps_hist = getattr(self, 'caps_hist', []) + [self.caps]
         self.batches.append([int(len(t)) for t in texts])
 
     def ar_prefill(self):
         pass
+
+    def slot_prefill(self, slot, text, lang, prompt):
+        assert self.fin[slot] == 1 and len(text) <= self.caps[0]
+        self.refills.append((slot, int(len(text))))
+        self.texts[slot], self.T[slot], self.fin[slot] = np.asarray(text), 0, 0
 
     def ctx_clamped(self):
         return False
@@ -268,39 +280,72 @@ class _FakeEngine:
     def timing(self):
         return {"ms_prefill": 1.0, "ms_decode": 2.0, "ms_nar": 3.0, "decode_steps": 4, "kernel_launches": 5}
 
+    def _run(self, max_new, stop_on_finish):
+        B = len(self.texts)
+        budget = [min(len(t), max_new) if max_new else len(t) for t in self.texts]
+        steps = max(budget)
+        toks = np.zeros((B, steps), np.int32)
+        start_fin = sum(self.fin)
+        while not all(self.fin):
+            for b in range(B):
+                if not self.fin[b]:
+                    toks[b, self.T[b]] = self._tok(self.texts[b], self.T[b])
+                    self.T[b] += 1
+                    if self.T[b] >= budget[b]:
+                        self.fin[b] = 1
+            if stop_on_finish and sum(self.fin) > start_fin and not all(self.fin):
+                break
+        return toks, np.asarray(self.T, np.int32), np.zeros(B, np.float32), np.asarray(self.fin, np.int32)
+
     def ar_decode(self, max_new=0, top_k=-100, top_p=1.0, temperature=1.0, seed=0, **kw):
         self.seeds.append(seed)
-        lens = np.asarray([len(t) for t in self.cur[0]], np.int32)
-        if max_new:
-            lens = np.minimum(lens, max_new)
-        self.lens = lens
-        return np.zeros((len(lens), int(lens.max())), np.int32), lens, np.zeros(len(lens), np.float32)
+        toks, lens, slp, _ = self._run(max_new, False)
+        for b in range(len(self.texts)):     # a plain launch returns the whole rows
+            toks[b, :lens[b]] = [self._tok(self.texts[b], t) for t in range(lens[b])]
+        return toks, lens, slp
 
-    def nar(self, Tmax=None, **kw):
-        B = len(self.lens)
-        codes = np.zeros((B, Tmax, 8), np.int32)
-        for b in range(B):
-            codes[b, :, :] = (int(self.cur[0][b][0]) * 10 + np.arange(Tmax)[:, None]) % 1024
+    def ar_decode_ex(self, max_new=0, top_k=-100, top_p=1.0, temperature=1.0, seed=0, resume=False, stop_on_finish=False):
+        self.seeds.append(seed)
+        self.launches.append((resume, stop_on_finish))
+        return self._run(max_new, stop_on_finish)       # like the device buffer: only THIS launch's tokens are present
+
+    def nar(self, cb0=None, t_lens=None, Tmax=None):
+        B, Tm = cb0.shape
+        codes = np.zeros((B, Tm, 8), np.int32)
+        codes[:, :, :] = cb0[:, :, None]
         return codes
 
 
 def test_inference_batch_chunks_orders_and_lengths():
-    """VALLE.inference_batch: max_batch-sized ragged chunks, per-item outputs in input order with their own lengths,
-    per-chunk sampler seeds, the same argument checks as .inference (models/vallex.py:485-493)."""
+    """VALLE.inference_batch: per-item outputs in input order with their own lengths; with more items than slots the AR decode is
+    continuously batched (a finished slot is refilled at once, the batch resumes), otherwise / with continuous=False it runs in
+    max_batch-sized ragged chunks; the NAR stages run over the finished utterances in ragged batches; same argument checks as
+    .inference (models/vallex.py:485-493)."""
     m = VALLE(1024, 16, 12, norm_first=True, add_prenet=False, prefix_mode=1, share_embedding=True, nar_scale_factor=1.0,
               prepend_bos=True, num_quantizers=8, max_batch=2)
-    fake = _FakeEngine()
-    m._engine = fake
     S = [5, 3, 7, 4, 6]
     items = [(torch.full((1, s), 10 + i, dtype=torch.long), torch.zeros(1, 2, 8, dtype=torch.long), 1, "en", "zh")
              for i, s in enumerate(S)]
-    outs = m.inference_batch(items, top_k=1, seed=100, quiet=True)
-    assert fake.batches == [[5, 3], [7, 4], [6]]
-    assert fake.seeds == [100, 102, 104]
-    assert [tuple(o.shape) for o in outs] == [(1, s, 8) for s in S]
-    for i, o in enumerate(outs):
-        assert o.dtype == torch.int64
-        assert int(o[0, 0, 0]) == ((10 + i) * 10) % 1024 and int(o[0, -1, 3]) == ((10 + i) * 10 + S[i] - 1) % 1024
+
+    def check(outs):
+        assert [tuple(o.shape) for o in outs] == [(1, s, 8) for s in S]
+        for i, o in enumerate(outs):
+            assert o.dtype == torch.int64
+            assert o[0, :, 0].tolist() == [((10 + i) * 10 + t) % 1024 for t in range(S[i])]
+
+    fake = _FakeEngine()
+    m._engine = fake
+    check(m.inference_batch(items, top_k=1, seed=100, quiet=True))
+    # continuous: slots start with items 0 (5 frames) and 1 (3 frames); slot 1 frees first -> item 2, then slot 0 -> item 3, ...
+    assert fake.batches[0] == [5, 3] and fake.caps_hist[0] == (7, 2)
+    assert fake.refills == [(1, 7), (0, 4), (0, 6)]
+    assert fake.launches[0] == (False, True) and all(r for r, _ in fake.launches[1:]) and fake.launches[-1][1] is False
+    assert fake.batches[1:] == [[5, 3], [7, 4], [6]]                   # the NAR batches, input order
+    assert m.last_timing["decode_launches"] == len(fake.launches) == 4
+    fake = _FakeEngine()
+    m._engine = fake
+    check(m.inference_batch(items, top_k=1, seed=100, quiet=True, continuous=False))
+    assert fake.batches == [[5, 3], [7, 4], [6], [5, 3], [7, 4], [6]] and fake.seeds == [100, 102, 104] and not fake.refills
     assert m.last_timing["ms_decode"] == 6.0 and m.last_timing["ms_prefill"] == 3.0     # summed over the three chunks
     short = m.inference_batch(items[:2], top_k=1, max_new_tokens=2, quiet=True)
     assert [tuple(o.shape) for o in short] == [(1, 2, 8), (1, 2, 8)]

@@ -460,10 +460,11 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_mma_kernel(const PParams p) 
     }
     // ---- S0: sample, append, embed the new token -> xa (models/vallex.py:529-531,568-598) -------------------------------
     for (int b = blockIdx.x; b < B; b += gridDim.x)
-      if (!ld_cg(bt.finished + b)) sample_utterance(p, b, scratch);
+      if (!ld_cg(bt.finished + b) && !(step == 0 && p.resume && !ld_cg(p.pending + b))) sample_utterance(p, b, scratch);   // resumed launch: a continuing utterance sampled its token before the pause
     grid_barrier(p.bar, epoch, prof);
     ++steps;
     if (!p.ignore_eos && ld_cg(bt.n_active) <= 0) break;
+    if (p.stop_below > 0 && ld_cg(bt.n_active) <= p.stop_below) break;   // continuous batching: hand a finished slot back to the host
     if (step == p.max_steps - 1) break;
     const AttnPlan plan = attn_plan(bt);   // contexts are fixed for the 12 layers of this step
     const unsigned live = __ballot_sync(0xffffffffu, plan.n > 0);   // utterances still decoding (bit b)

@@ -66,10 +66,11 @@ __global__ void __launch_bounds__(PNT, 1) ar_decode_persistent_kernel(const PPar
     }
     // ---- S0: sample, append, embed -------------------------------------------------------------------
     for (int b = blockIdx.x; b < B; b += gridDim.x)
-      if (!ld_cg(bt.finished + b)) sample_utterance(p, b, scratch);
+      if (!ld_cg(bt.finished + b) && !(step == 0 && p.resume && !ld_cg(p.pending + b))) sample_utterance(p, b, scratch);   // resumed launch: a continuing utterance sampled its token before the pause
     grid_barrier(p.bar, epoch, prof);
     ++steps;
     if (!p.ignore_eos && ld_cg(bt.n_active) <= 0) break;
+    if (p.stop_below > 0 && ld_cg(bt.n_active) <= p.stop_below) break;   // continuous batching: hand a finished slot back to the host
     if (step == p.max_steps - 1) break;
 
     for (int l = 0; l < kL; ++l) {

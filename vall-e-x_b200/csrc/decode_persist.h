@@ -43,6 +43,9 @@ struct PParams {
   int top_k; float top_p; float temperature; uint64_t seed; int ignore_eos;
   const int32_t* forced; int forced_stride; int32_t* out_tokens; int out_stride;
   int max_steps;
+  int resume;                 // 1: this launch continues a paused batch (vx_ar_decode_resume): at step 0 only slots with pending[b] != 0 sample
+  const int32_t* pending;     // [B] 1: the slot's logits come from a fresh prefill and have not been sampled yet
+  int stop_below;             // > 0: leave the loop as soon as n_active <= stop_below (a slot finished; the host refills it)
   int32_t* steps_done;        // [1]
   long long* prof;            // nullable: [3 CTAs][4096] (tag, clock64) pairs of 4 steps (VX_DECODE_PROF=<first step>)
   int prof_step0;

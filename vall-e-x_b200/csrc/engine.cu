@@ -167,6 +167,9 @@ struct vx_engine {
 
   // batch state
   bool batch_set = false, prefilled = false, decoded = false, forked = false;
+  size_t kv_slot_off = 0;                            // element offset of the slot a single-utterance prefill writes (vx_slot_prefill)
+  std::vector<int32_t> hfin;                         // host mirror of finished[] after the last decode launch
+  Buf d_pending, d_zero;                             // [max_batch] fresh-prefill flags (continuous batching); one zero int
   int B = 0, Smax = 0, Pmax = 0, ymax = 0;
   std::vector<int> hS, hP, hT, h_ar_row0;
   int ar_rows = 0, ar_maxlen = 0;
@@ -373,8 +376,8 @@ int full_layer(vx_engine* e, const LayerW& L, int64_t R, const int32_t* row0, in
   const int wt = e->mode;
   const size_t kvb = kv_esize(e);
   float* x = (float*)e->x.p;
-  void* kc = kv_layer >= 0 ? (char*)e->kc.p + (size_t)kv_layer * e->kv_layer_elems * kvb : nullptr;
-  void* vc = kv_layer >= 0 ? (char*)e->vc.p + (size_t)kv_layer * e->kv_layer_elems * kvb : nullptr;
+  void* kc = kv_layer >= 0 ? (char*)e->kc.p + ((size_t)kv_layer * e->kv_layer_elems + e->kv_slot_off) * kvb : nullptr;
+  void* vc = kv_layer >= 0 ? (char*)e->vc.p + ((size_t)kv_layer * e->kv_layer_elems + e->kv_slot_off) * kvb : nullptr;
   if (e->mode == VX_BF16 && !e->force_simt) {
     launch_layernorm_image(x, nullptr, R, L.n1_g, L.n1_b, ada1, ada1 ? ada1 + kD : nullptr, 1e-5f, e->a_img.p, st);
     // VX_ATTN_T5=3 (experimental): NAR layers (no KV scatter) write the per-head operand images straight from the QKV GEMM
@@ -482,7 +485,7 @@ void vx_destroy(vx_engine* e) {
     if (kv.second.b16) cudaFree(kv.second.b16);
     if (kv.second.img) cudaFree(kv.second.img);
   }
-  Buf* bufs[] = {&e->d_flag, &e->d_text, &e->d_lang, &e->d_prompt, &e->d_S, &e->d_P, &e->d_ar_row0, &e->d_nar_row0, &e->d_T,
+  Buf* bufs[] = {&e->d_pending, &e->d_zero, &e->d_flag, &e->d_text, &e->d_lang, &e->d_prompt, &e->d_S, &e->d_P, &e->d_ar_row0, &e->d_nar_row0, &e->d_T,
                  &e->d_ctx, &e->d_y, &e->d_budget, &e->d_fin, &e->d_slp, &e->d_nact, &e->x, &e->xn, &e->qkv, &e->att,
                  &e->ffh, &e->kc, &e->vc, &e->a_img, &e->qkv16, &e->att_img, &e->h_img, &e->t_img, &e->q_img, &e->k_img, &e->vt_img, &e->xs, &e->xsn, &e->qkvs, &e->atts, &e->ffs, &e->logits, &e->part, &e->tick, &e->p_xb, &e->p_acc, &e->p_pf, &e->p_bar, &e->p_prof,
                  &e->lastmap, &e->out_tok, &e->forced, &e->yemb, &e->yrow0, &e->trow0, &e->tgtmap, &e->nlog, &e->codes,
@@ -799,19 +802,11 @@ int vx_set_batch(vx_engine* e, int B, const int32_t* text_ids, const int32_t* te
   return VX_OK;
 }
 
-int vx_ar_prefill(vx_engine* e, void* stream) {
-  if (!e || !e->batch_set) return fail(VX_ERR_STATE, "vx_ar_prefill: no batch set");
-  CK(cudaSetDevice(e->device));
-  cudaStream_t st = pick(e, stream);
-  const int B = e->B, wt = e->mode;
-  const int64_t R = e->ar_rows;
-  const size_t kvb = kv_esize(e);
-  e->kv_layer_elems = (size_t)e->max_batch * kH * e->ctx_cap * kDH;
+// The AR prefill over the utterances e->bt describes (B of them, R packed rows): embeddings, 12 masked layers with KV scatter,
+// final LayerNorm of each utterance's last row, first-step logits into `logits_out` [B][1025].
+static int prefill_core(vx_engine* e, int B, int64_t R, int maxlen, const int32_t* h_last, float* logits_out, cudaStream_t st) {
+  const int wt = e->mode;
   { int _r = ensure_full_buffers(e, R); if (_r) return _r; }
-  ENS(e->kc, e->kv_layer_elems * kL * kvb); ENS(e->vc, e->kv_layer_elems * kL * kvb);
-  ENS(e->xs, (size_t)e->max_batch * kD * 4); ENS(e->xsn, (size_t)e->max_batch * kD * 4); ENS(e->logits, (size_t)e->max_batch * kARLogits * 4);
-  ENS(e->lastmap, e->max_batch * 4);
-  CK(cudaEventRecord(e->ev0, st));
   const Batch& bt = e->bt;
   float* x = (float*)e->x.p;
   if (e->attn_t5 && e->mode == VX_BF16 && !e->force_simt) CK(cudaMemsetAsync(x, 0, (size_t)e->full_rows * kD * 4, st));  // pad rows stay finite
@@ -820,14 +815,33 @@ int vx_ar_prefill(vx_engine* e, void* stream) {
                     vec(e, "ar_text_position.alpha"), e->pe, bt.ar_row0, x, st);
   launch_embed_audio_prefill(bt, vec(e, "ar_audio_embedding.word_embeddings.weight"), vec(e, "ar_audio_position.alpha"), e->pe, x, st);
   e->launches += 3;
-  for (int l = 0; l < kL; ++l) full_layer(e, e->ar[l], R, bt.ar_row0, 1, e->ar_maxlen, nullptr, nullptr, l, st);
-  std::vector<int32_t> last(B);
-  for (int b = 0; b < B; ++b) last[b] = e->h_ar_row0[b] + e->hS[b] + e->hP[b];
-  memcpy(e->h_pinned, last.data(), B * 4);
+  for (int l = 0; l < kL; ++l) full_layer(e, e->ar[l], R, bt.ar_row0, 1, maxlen, nullptr, nullptr, l, st);
+  memcpy(e->h_pinned, h_last, B * 4);
   CK(cudaMemcpyAsync(e->lastmap.p, e->h_pinned, B * 4, cudaMemcpyHostToDevice, st));
   launch_layernorm(x, (const int32_t*)e->lastmap.p, B, kD, e->ar_norm_g, e->ar_norm_b, nullptr, nullptr, 1e-5f, (float*)e->xsn.p, st);
   e->launches++;
-  linear(e, (float*)e->xsn.p, kD, e->ar_predict, wt, nullptr, (float*)e->logits.p, kARLogits, B, kARLogits, kD, EPI_NONE, st);
+  linear(e, (float*)e->xsn.p, kD, e->ar_predict, wt, nullptr, logits_out, kARLogits, B, kARLogits, kD, EPI_NONE, st);
+  return VX_OK;
+}
+
+int vx_ar_prefill(vx_engine* e, void* stream) {
+  if (!e || !e->batch_set) return fail(VX_ERR_STATE, "vx_ar_prefill: no batch set");
+  CK(cudaSetDevice(e->device));
+  cudaStream_t st = pick(e, stream);
+  const int B = e->B;
+  const size_t kvb = kv_esize(e);
+  e->kv_layer_elems = (size_t)e->max_batch * kH * e->ctx_cap * kDH;
+  ENS(e->kc, e->kv_layer_elems * kL * kvb); ENS(e->vc, e->kv_layer_elems * kL * kvb);
+  ENS(e->xs, (size_t)e->max_batch * kD * 4); ENS(e->xsn, (size_t)e->max_batch * kD * 4); ENS(e->logits, (size_t)e->max_batch * kARLogits * 4);
+  ENS(e->lastmap, e->max_batch * 4);
+  ENS(e->d_pending, e->max_batch * 4); ENS(e->d_zero, 16);
+  CK(cudaMemsetAsync(e->d_pending.p, 0, e->max_batch * 4, st));
+  CK(cudaMemsetAsync(e->d_zero.p, 0, 16, st));
+  CK(cudaEventRecord(e->ev0, st));
+  std::vector<int32_t> last(B);
+  for (int b = 0; b < B; ++b) last[b] = e->h_ar_row0[b] + e->hS[b] + e->hP[b];
+  e->kv_slot_off = 0;
+  { int _r = prefill_core(e, B, e->ar_rows, e->ar_maxlen, last.data(), (float*)e->logits.p, st); if (_r) return _r; }
   CK(cudaMemsetAsync(e->d_T.p, 0, B * 4, st));
   CK(cudaMemsetAsync(e->d_fin.p, 0, B * 4, st));
   CK(cudaMemsetAsync(e->d_slp.p, 0, B * 4, st));
@@ -835,7 +849,75 @@ int vx_ar_prefill(vx_engine* e, void* stream) {
   CK(cudaStreamSynchronize(st));
   CK(cudaEventElapsedTime(&e->ms_prefill, e->ev0, e->ev1));
   CK(cudaGetLastError());
+  e->hfin.assign(B, 0);
   e->prefilled = true; e->decoded = false;
+  return VX_OK;
+}
+
+// Continuous batching: the utterance in `slot` has finished; a new one takes its place while the other slots keep
+// their decode state.  The new utterance is prefilled ALONE (batch-1 view of the slot's rows of every per-utterance array, KV
+// scatter into the slot's cache region, first-step logits into the slot's row) and marked pending, so the next
+// vx_ar_decode_ex(resume = 1) samples its first token while the continuing slots carry on from the token they sampled last.
+int vx_slot_prefill(vx_engine* e, int slot, const int32_t* text_ids, int S, const int32_t* lang_ids, const int32_t* prompt_codes, int P,
+                    int mem, void* stream) {
+  if (!e || !e->batch_set || !e->prefilled) return fail(VX_ERR_STATE, "vx_slot_prefill: call after vx_set_batch + vx_ar_prefill");
+  if (e->forked) return fail(VX_ERR_STATE, "vx_slot_prefill: the batch holds the beams of one utterance");
+  if (slot < 0 || slot >= e->B || !text_ids || !lang_ids || S < 1 || P < 0 || (P > 0 && !prompt_codes))
+    return fail(VX_ERR_ARG, "vx_slot_prefill: bad arguments");
+  if (S > e->Smax || P > e->Pmax) return fail(VX_ERR_CAPACITY, "vx_slot_prefill: S / P exceed the capacity vx_set_batch reserved (Smax, Pmax)");
+  if (S + P + 1 >= e->max_ctx) return fail(VX_ERR_CAPACITY, "vx_slot_prefill: S+P+1 exceeds max_ctx");
+  CK(cudaSetDevice(e->device));
+  cudaStream_t st = pick(e, stream);
+  const int Pm = std::max(e->Pmax, 1);
+  int32_t* d_text = (int32_t*)e->d_text.p + (size_t)slot * e->Smax;
+  int32_t* d_lang = (int32_t*)e->d_lang.p + (size_t)slot * e->Smax;
+  int32_t* d_prm = (int32_t*)e->d_prompt.p + (size_t)slot * Pm * kNQ;
+  int r;
+  if ((r = copy_in(d_text, text_ids, (size_t)S * 4, mem, st))) return r;
+  if ((r = copy_in(d_lang, lang_ids, (size_t)S * 4, mem, st))) return r;
+  if (P > 0 && (r = copy_in(d_prm, prompt_codes, (size_t)P * kNQ * 4, mem, st))) return r;
+  e->h_pinned[0] = S; e->h_pinned[1] = P; e->h_pinned[2] = 1; e->h_pinned[3] = 0;
+  CK(cudaMemcpyAsync((int32_t*)e->d_S.p + slot, e->h_pinned, 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync((int32_t*)e->d_P.p + slot, e->h_pinned + 1, 4, cudaMemcpyHostToDevice, st));
+  ENS(e->d_flag, 16);
+  CK(cudaMemsetAsync(e->d_flag.p, 0, 16, st));
+  check_range_kernel<<<dim3(4, 1), 256, 0, st>>>(d_text, 0, nullptr, 1, S, 0, kTextVocab, 1, (int32_t*)e->d_flag.p);
+  check_range_kernel<<<dim3(4, 1), 256, 0, st>>>(d_lang, 0, nullptr, 1, S, 0, 3, 2, (int32_t*)e->d_flag.p);
+  if (P > 0) check_range_kernel<<<dim3(8, 1), 256, 0, st>>>(d_prm, 0, nullptr, 1, (int64_t)P * kNQ, 0, kVocab, 4, (int32_t*)e->d_flag.p);
+  CK(cudaMemcpyAsync(e->h_pinned + 8, e->d_flag.p, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (e->h_pinned[8] != 0) return fail(VX_ERR_ARG, "vx_slot_prefill: index out of range in text_ids / lang_ids / prompt_codes");
+  // batch-1 view of the slot
+  const Batch full = e->bt;
+  Batch v = full;
+  v.B = 1;
+  v.text_ids = d_text; v.lang_ids = d_lang; v.prompt = d_prm;
+  v.S = full.S + slot; v.P = full.P + slot; v.ar_row0 = (const int32_t*)e->d_zero.p; v.nar_row0 = (const int32_t*)e->d_zero.p;
+  v.T = full.T + slot; v.ctx = full.ctx + slot; v.y = full.y + (size_t)slot * full.ymax;
+  v.budget = full.budget + slot; v.finished = full.finished + slot; v.sum_logprobs = full.sum_logprobs + slot;
+  const int len = S + P + 1;
+  const int64_t R = (e->attn_t5 && e->mode == VX_BF16 && !e->force_simt) ? (len + 127) / 128 * 128 : len;
+  const int32_t last = S + P;
+  CK(cudaEventRecord(e->ev0, st));
+  e->bt = v;
+  e->kv_slot_off = (size_t)slot * kH * e->ctx_cap * kDH;
+  r = prefill_core(e, 1, R, len, &last, (float*)e->logits.p + (size_t)slot * kARLogits, st);
+  e->bt = full;
+  e->kv_slot_off = 0;
+  if (r) return r;
+  CK(cudaMemsetAsync((int32_t*)e->d_T.p + slot, 0, 4, st));
+  CK(cudaMemsetAsync((int32_t*)e->d_fin.p + slot, 0, 4, st));
+  CK(cudaMemsetAsync((float*)e->d_slp.p + slot, 0, 4, st));
+  CK(cudaMemcpyAsync((int32_t*)e->d_pending.p + slot, e->h_pinned + 2, 4, cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(e->ev1, st));
+  CK(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+  e->ms_prefill += ms;
+  CK(cudaGetLastError());
+  e->hS[slot] = S; e->hP[slot] = P;
+  if ((int)e->hfin.size() == e->B) e->hfin[slot] = 0;
+  if ((int)e->hT.size() == e->B) e->hT[slot] = 0;
   return VX_OK;
 }
 
@@ -948,7 +1030,17 @@ static int decode_forward(vx_engine* e, int nsplit, cudaStream_t st) {
 int vx_ar_decode(vx_engine* e, int max_new, int top_k, float top_p, float temperature, uint64_t seed, int ignore_eos,
                  const int32_t* forced_tokens, int32_t* out_tokens, int32_t* out_lens, float* out_sum_logprobs, int mem,
                  void* stream) {
+  return vx_ar_decode_ex(e, max_new, top_k, top_p, temperature, seed, ignore_eos, forced_tokens, out_tokens, out_lens, out_sum_logprobs,
+                         0, 0, nullptr, mem, stream);
+}
+
+int vx_ar_decode_ex(vx_engine* e, int max_new, int top_k, float top_p, float temperature, uint64_t seed, int ignore_eos,
+                    const int32_t* forced_tokens, int32_t* out_tokens, int32_t* out_lens, float* out_sum_logprobs, int resume,
+                    int stop_on_finish, int32_t* out_finished, int mem, void* stream) {
   if (!e || !e->prefilled) return fail(VX_ERR_STATE, "vx_ar_decode: call vx_ar_prefill first");
+  if (resume && !e->decoded) return fail(VX_ERR_STATE, "vx_ar_decode_ex: resume needs a previous decode launch on this batch");
+  if ((resume || stop_on_finish) && (e->decode_graph || e->B > 32)) return fail(VX_ERR_STATE, "vx_ar_decode_ex: resume / stop_on_finish need the persistent decode kernel");
+  if (!resume) e->hfin.assign(e->B, 0);
   if (!(temperature > 0.f)) return fail(VX_ERR_ARG, "vx_ar_decode: temperature must be > 0");
   CK(cudaSetDevice(e->device));
   cudaStream_t st = pick(e, stream);
@@ -979,7 +1071,10 @@ int vx_ar_decode(vx_engine* e, int max_new, int top_k, float top_p, float temper
     if (r) return r;
   }
   memcpy(e->h_pinned, bud.data(), B * 4);
-  e->h_pinned[B] = B;
+  int n_live = 0;
+  for (int b = 0; b < B; ++b) n_live += e->hfin[b] ? 0 : 1;
+  if (n_live == 0) return fail(VX_ERR_STATE, "vx_ar_decode_ex: every slot has finished (refill one with vx_slot_prefill)");
+  e->h_pinned[B] = n_live;
   CK(cudaMemcpyAsync(e->d_budget.p, e->h_pinned, B * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(e->d_nact.p, e->h_pinned + B, 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(e->tick.p, 0, ((size_t)B * kH + 64) * 4, st));
@@ -1032,6 +1127,8 @@ int vx_ar_decode(vx_engine* e, int max_new, int top_k, float top_p, float temper
     pp.top_k = top_k; pp.top_p = top_p; pp.temperature = temperature; pp.seed = seed; pp.ignore_eos = ignore_eos;
     pp.forced = forced_dev; pp.forced_stride = max_steps; pp.out_tokens = (int32_t*)e->out_tok.p; pp.out_stride = max_steps;
     pp.max_steps = max_steps; pp.steps_done = (int32_t*)((char*)e->p_bar.p + 32);
+    pp.resume = resume ? 1 : 0; pp.pending = (const int32_t*)e->d_pending.p;
+    pp.stop_below = (stop_on_finish && n_live > 1) ? n_live - 1 : 0;
     pp.dbg = getenv("VX_DECODE_DBG") ? atoi(getenv("VX_DECODE_DBG")) : 0;
     if (getenv("VX_DECODE_PROF")) {
       ENS(e->p_prof, 3 * 4096 * 8);
@@ -1066,6 +1163,9 @@ int vx_ar_decode(vx_engine* e, int max_new, int top_k, float top_p, float temper
     if (out_sum_logprobs && (r2 = copy_out(out_sum_logprobs, e->d_slp.p, B * 4, mem, st))) return r2;
     e->hT.assign(B, 0);
     CK(cudaMemcpyAsync(e->hT.data(), e->d_T.p, B * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(e->hfin.data(), e->d_fin.p, B * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemsetAsync(e->d_pending.p, 0, e->max_batch * 4, st));   // every live slot has now sampled the logits it had
+    if (out_finished && (r2 = copy_out(out_finished, e->d_fin.p, B * 4, mem, st))) return r2;
     CK(cudaStreamSynchronize(st));
     e->decoded = true;
     return VX_OK;

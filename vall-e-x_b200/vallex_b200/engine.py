@@ -82,13 +82,14 @@ class Engine:
 
     # ---- batch ---------------------------------------------------------------------------
     def set_batch(self, text_ids: Sequence[np.ndarray], lang_ids: Sequence[np.ndarray],
-                  prompts: Sequence[np.ndarray]):
+                  prompts: Sequence[np.ndarray], Smax: int = 0, Pmax: int = 0):
         """text_ids[b] int [S_b]; lang_ids[b] int [S_b] (model numbering en=0 zh=1 ja=2);
-        prompts[b] int [P_b, 8]."""
+        prompts[b] int [P_b, 8].  Smax / Pmax: capacity to reserve per slot (continuous batching refills slots with
+        other utterances through slot_prefill; default: the largest of this batch)."""
         B = len(text_ids)
         self.S = [int(len(t)) for t in text_ids]
         self.P = [int(p.shape[0]) for p in prompts]
-        Smax, Pmax = max(self.S), max(self.P)
+        Smax, Pmax = max(max(self.S), int(Smax)), max(max(self.P), int(Pmax))
         txt = np.zeros((B, Smax), np.int32)
         lng = np.zeros((B, Smax), np.int32)
         prm = np.zeros((B, max(Pmax, 1), NUM_QUANTIZERS), np.int32)
@@ -126,6 +127,29 @@ class Engine:
         n = C.c_int()
         check(self._lib.vx_ar_budget(self._h, int(max_new), C.byref(n)), "vx_ar_budget")
         return n.value
+
+    def slot_prefill(self, slot: int, text_ids: np.ndarray, lang_ids: np.ndarray, prompt: np.ndarray):
+        """Continuous batching: put a new utterance into a finished slot (prefilled alone into the slot's KV region)."""
+        t = np.ascontiguousarray(text_ids, np.int32)
+        l = np.ascontiguousarray(lang_ids, np.int32)
+        pr = np.ascontiguousarray(prompt, np.int32).reshape(-1, NUM_QUANTIZERS)
+        check(self._lib.vx_slot_prefill(self._h, int(slot), ptr(t), int(len(t)), ptr(l), ptr(pr) if pr.shape[0] else None,
+                                        int(pr.shape[0]), VX_HOST, None), "vx_slot_prefill")
+        self.S[slot], self.P[slot] = int(len(t)), int(pr.shape[0])
+
+    def ar_decode_ex(self, max_new: int = 0, top_k: int = -100, top_p: float = 1.0, temperature: float = 1.0, seed: int = 0,
+                     resume: bool = False, stop_on_finish: bool = False):
+        """vx_ar_decode_ex: returns (tokens [B,max_steps], lens [B], sum_logprobs [B], finished [B]) of every slot's CURRENT
+        utterance; stop_on_finish returns as soon as one more slot is done, resume continues the paused batch."""
+        steps = self.ar_budget(max_new)
+        toks = np.zeros((self.B, steps), np.int32)
+        lens = np.zeros((self.B,), np.int32)
+        slp = np.zeros((self.B,), np.float32)
+        fin = np.zeros((self.B,), np.int32)
+        check(self._lib.vx_ar_decode_ex(self._h, int(max_new), int(top_k), float(top_p), float(temperature), int(seed) & (2 ** 64 - 1),
+                                        0, None, ptr(toks), ptr(lens), ptr(slp), int(bool(resume)), int(bool(stop_on_finish)),
+                                        ptr(fin), VX_HOST, None), "vx_ar_decode_ex")
+        return toks, lens, slp, fin
 
     def ar_decode(self, max_new: int = 0, top_k: int = -100, top_p: float = 1.0, temperature: float = 1.0,
                   seed: int = 0, ignore_eos: bool = False, forced: Optional[np.ndarray] = None):

@@ -201,48 +201,110 @@ class VALLE:
         return out.to(x.device) if x.is_cuda else out
 
     def inference_batch(self, items, top_k: int = -100, temperature: float = 1.0, *, max_new_tokens: int = 0,
-                        seed: Optional[int] = None, quiet: bool = False) -> List[torch.Tensor]:
-        """Engine extension (the reference is batch-1 only, models/vallex.py:491): B independent
-        utterances as ONE ragged batch -- one prefill, one persistent decode launch, one NAR pass per `max_batch`
-        chunk.  `items` = sequence of `(x [1,S], y [1,P,8], enroll_x_lens, prompt_language, text_language)` with the
-        meaning of `.inference`'s arguments; returns one LongTensor[1,T_b,8] per item.  Every utterance keeps its own
-        EOS / 16*S cap and (sampling mode) its own Philox stream, so the batch is a vmap of B `.inference` calls."""
+                        seed: Optional[int] = None, quiet: bool = False, continuous: Optional[bool] = None) -> List[torch.Tensor]:
+        """Engine extension (the reference is batch-1 only, models/vallex.py:491): many independent
+        utterances through `max_batch` decode slots.  `items` = sequence of `(x [1,S], y [1,P,8], enroll_x_lens,
+        prompt_language, text_language)` with the meaning of `.inference`'s arguments; returns one LongTensor[1,T_b,8] per item,
+        in input order.  Every utterance keeps its own EOS / 16*S cap and (sampling mode) its own Philox stream, so the result
+        is a vmap of `.inference` calls.
+        AR decode is CONTINUOUSLY batched when there are more items than slots (`continuous`, default on): the persistent
+        decode kernel hands a slot back as soon as its utterance finishes (vx_ar_decode_ex stop_on_finish), the next pending
+        utterance is prefilled alone into that slot (vx_slot_prefill) and the batch resumes -- nobody waits for the slowest
+        utterance of a chunk.  The NAR stages then run over the finished utterances in ragged batches of `max_batch`."""
         items = list(items)
+        if not items:
+            return []
         seed = _resolve_seed(seed)
-        outs: List[Optional[torch.Tensor]] = [None] * len(items)
         eng = self.engine
-        timing: dict = {}
-        for c0 in range(0, len(items), self._max_batch):
-            chunk = items[c0:c0 + self._max_batch]
-            texts, langs, prompts = [], [], []
-            for x, y, enroll_x_lens, prompt_language, text_language in chunk:
-                assert x.ndim == 2 and x.shape[0] == 1, x.shape
-                assert y.ndim == 3 and y.shape[0] == 1, y.shape
-                S, P = int(x.shape[1]), int(y.shape[1])
-                assert S > 0
-                texts.append(x[0].detach().to("cpu").numpy().astype(np.int32))
-                prompts.append(y[0].detach().to("cpu").numpy().astype(np.int32).reshape(P, NUM_QUANTIZERS))
-                _check_ids(texts[-1], prompts[-1])
-                langs.append(self._lang_ids(S, int(enroll_x_lens), prompt_language, text_language))
-            eng.set_batch(texts, langs, prompts)
+        MB = self._max_batch
+        prepared = []
+        for x, y, enroll_x_lens, prompt_language, text_language in items:
+            assert x.ndim == 2 and x.shape[0] == 1, x.shape
+            assert y.ndim == 3 and y.shape[0] == 1, y.shape
+            S, P = int(x.shape[1]), int(y.shape[1])
+            assert S > 0
+            text = x[0].detach().to("cpu").numpy().astype(np.int32)
+            prompt = y[0].detach().to("cpu").numpy().astype(np.int32).reshape(P, NUM_QUANTIZERS)
+            _check_ids(text, prompt)
+            prepared.append((text, self._lang_ids(S, int(enroll_x_lens), prompt_language, text_language), prompt))
+        if continuous is None:
+            continuous = len(items) > MB
+        n = len(items)
+        cb0: List[Optional[np.ndarray]] = [None] * n
+        timing = {"ms_prefill": 0.0, "ms_decode": 0.0, "ms_nar": 0.0, "decode_steps": 0, "decode_launches": 0}
+
+        def check_room(i, T):
+            text, _, prompt = prepared[i]
+            if T >= self._max_ctx - (len(text) + prompt.shape[0] + 1) - 1 and (not max_new_tokens or T < max_new_tokens) and T < 16 * len(text):
+                raise RuntimeError(f"KV cache exhausted for utterance {i}: max_ctx={self._max_ctx} rows filled before EOS / the 16*S cap; "
+                                   f"build VALLE(..., max_ctx=...) larger or pass max_new_tokens")
+
+        # ---- AR decode --------------------------------------------------------------------------------------------------
+        if continuous:
+            Smax = max(len(t) for t, _, _ in prepared)
+            Pmax = max(p.shape[0] for _, _, p in prepared)
+            first = list(range(min(MB, n)))
+            nxt = len(first)
+            slot_item = list(first)                      # item index held by each slot (-1: idle)
+            acc = [[] for _ in first]                    # tokens gathered so far for the slot's current utterance
+            eng.set_batch([prepared[i][0] for i in first], [prepared[i][1] for i in first], [prepared[i][2] for i in first],
+                          Smax=Smax, Pmax=Pmax)
             eng.ar_prefill()
-            t_pre = eng.timing()["ms_prefill"]
-            _, lens, _ = eng.ar_decode(max_new=max_new_tokens, top_k=top_k, top_p=1.0, temperature=temperature,
-                                       seed=seed + c0)
-            if eng.ctx_clamped():
-                for b, (x, y, *_r) in enumerate(chunk):
-                    if int(lens[b]) >= self._max_ctx - (int(x.shape[1]) + int(y.shape[1]) + 1) - 1:
-                        raise RuntimeError(f"KV cache exhausted for utterance {c0 + b}: max_ctx={self._max_ctx} rows filled before EOS / the "
-                                           f"16*S cap; build VALLE(..., max_ctx=...) larger or pass max_new_tokens")
-            codes = eng.nar(Tmax=int(lens.max()))
-            t = dict(eng.timing(), ms_prefill=t_pre)
-            for k, v in t.items():
-                timing[k] = timing.get(k, 0) + v if isinstance(v, (int, float)) else v
-            for b, (x, y, *_rest) in enumerate(chunk):
-                T = int(lens[b])
+            timing["ms_prefill"] += eng.timing()["ms_prefill"]
+            resume, launch = False, 0
+            have = [0] * len(first)                      # tokens already copied out per slot
+            while any(i >= 0 for i in slot_item):
+                toks, lens, _, fin = eng.ar_decode_ex(max_new=max_new_tokens, top_k=top_k, top_p=1.0, temperature=temperature,
+                                                      seed=seed + 7919 * launch, resume=resume, stop_on_finish=nxt < n)
+                t = eng.timing()
+                timing["ms_decode"] += t["ms_decode"]; timing["decode_steps"] += t["decode_steps"]; timing["decode_launches"] += 1
+                resume, launch = True, launch + 1
+                for s_, i in enumerate(slot_item):
+                    if i < 0:
+                        continue
+                    T = int(lens[s_])
+                    acc[s_].append(toks[s_, have[s_]:T].copy())      # the device buffer is cleared every launch
+                    have[s_] = T
+                    if fin[s_]:
+                        cb0[i] = np.concatenate(acc[s_]) if acc[s_] else np.zeros((0,), np.int32)
+                        check_room(i, T)
+                        if nxt < n:                                   # refill the slot
+                            eng.slot_prefill(s_, *prepared[nxt])
+                            slot_item[s_], acc[s_], have[s_] = nxt, [], 0
+                            nxt += 1
+                        else:
+                            slot_item[s_] = -1
+                timing["ms_prefill"] = eng.timing()["ms_prefill"] if False else timing["ms_prefill"]
+        else:
+            for c0 in range(0, n, MB):
+                idx = list(range(c0, min(c0 + MB, n)))
+                eng.set_batch([prepared[i][0] for i in idx], [prepared[i][1] for i in idx], [prepared[i][2] for i in idx])
+                eng.ar_prefill()
+                timing["ms_prefill"] += eng.timing()["ms_prefill"]
+                toks, lens, _ = eng.ar_decode(max_new=max_new_tokens, top_k=top_k, top_p=1.0, temperature=temperature, seed=seed + c0)
+                t = eng.timing()
+                timing["ms_decode"] += t["ms_decode"]; timing["decode_steps"] += t["decode_steps"]; timing["decode_launches"] += 1
+                for b, i in enumerate(idx):
+                    cb0[i] = toks[b, :int(lens[b])].copy()
+                    check_room(i, int(lens[b]))
+        # ---- NAR: the finished utterances in ragged batches -----------------------------------------------------------------
+        outs: List[Optional[torch.Tensor]] = [None] * n
+        for c0 in range(0, n, MB):
+            idx = list(range(c0, min(c0 + MB, n)))
+            Tm = max(int(len(cb0[i])) for i in idx)
+            tok = np.zeros((len(idx), max(Tm, 1)), np.int32)
+            for b, i in enumerate(idx):
+                tok[b, :len(cb0[i])] = cb0[i]
+            eng.set_batch([prepared[i][0] for i in idx], [prepared[i][1] for i in idx], [prepared[i][2] for i in idx])
+            codes = eng.nar(cb0=tok[:, :Tm], t_lens=np.asarray([len(cb0[i]) for i in idx], np.int32))
+            timing["ms_nar"] += eng.timing()["ms_nar"]
+            for b, i in enumerate(idx):
+                T = int(len(cb0[i]))
                 if not quiet:
-                    print(f"VALL-E EOS [{int(y.shape[1])} -> {int(y.shape[1]) + 1 + T}]")
+                    P = int(prepared[i][2].shape[0])
+                    print(f"VALL-E EOS [{P} -> {P + 1 + T}]")
                 out = torch.from_numpy(codes[b:b + 1, :T].astype(np.int64))
-                outs[c0 + b] = out.to(x.device) if x.is_cuda else out
+                x = items[i][0]
+                outs[i] = out.to(x.device) if x.is_cuda else out
         self.last_timing = timing
         return outs
