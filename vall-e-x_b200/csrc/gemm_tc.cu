@@ -123,9 +123,31 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const bf16* __restrict_
       tc_fence_after();
       const int64_t row = (int64_t)mt * 128 + q * 32 + lane;
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+      // residual epilogues: the fp32 residual chunk of the NEXT 32 columns is requested before this chunk's accumulator is
+      // read, so the read-modify-write does not sit behind a fresh HBM/L2 round trip per chunk (54 % of the epilogue warps'
+      // stall samples were these loads, profiles/r01_prof_gemm.md)
+      constexpr bool kRes = (EPI == TC_F32_RESIDUAL || EPI == TC_F32_SCALE_RESIDUAL);
+      float4 rnext[8];
+      if constexpr (kRes) {
+        if (row < M) {
+          const float* o = reinterpret_cast<const float*>(out) + row * ldc + nt * BN;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rnext[i] = *reinterpret_cast<const float4*>(o + 4 * i);
+        }
+      }
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float v[32];
+        float4 rcur[8];
+        if constexpr (kRes) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rcur[i] = rnext[i];
+          if (row < M && c0 + 32 < BN) {
+            const float* o = reinterpret_cast<const float*>(out) + row * ldc + nt * BN + c0 + 32;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rnext[i] = *reinterpret_cast<const float4*>(o + 4 * i);
+          }
+        }
         tmem_ld32(taddr + c0, v);
         const int n0 = nt * BN + c0;
         if (bias) {
@@ -206,7 +228,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const bf16* __restrict_
             float* o = reinterpret_cast<float*>(out) + row * ldc + n0;   // Vocos pwconv2: x += gamma[n] * (acc + bias[n])
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              float4 r = *reinterpret_cast<const float4*>(o + i);
+              float4 r = rcur[i >> 2];
               const float4 g = __ldg(reinterpret_cast<const float4*>(aux + n0 + i));
               r.x = fmaf(g.x, v[i], r.x); r.y = fmaf(g.y, v[i + 1], r.y); r.z = fmaf(g.z, v[i + 2], r.z); r.w = fmaf(g.w, v[i + 3], r.w);
               *reinterpret_cast<float4*>(o + i) = r;
@@ -215,7 +237,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const bf16* __restrict_
             float* o = reinterpret_cast<float*>(out) + row * ldc + n0;
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              float4 r = *reinterpret_cast<const float4*>(o + i);
+              float4 r = rcur[i >> 2];
               r.x += v[i]; r.y += v[i + 1]; r.z += v[i + 2]; r.w += v[i + 3];
               *reinterpret_cast<float4*>(o + i) = r;
             }
