@@ -34,16 +34,11 @@ def test_tcgen05_gemm(M, N, K, epi):
     assert err < tol * max(1.0, ref.abs().max().item())
 
 
-@pytest.mark.parametrize("variant", ["tc", "t5", "t5max"])
+@pytest.mark.parametrize("variant", ["tc", "t5"])
 @pytest.mark.parametrize("S,length,mode", [(6, 12, 1), (30, 200, 1), (122, 348, 1), (20, 64, 0), (40, 300, 0), (314, 1814, 0)])
-def test_tensor_core_attention(S, length, mode, variant, monkeypatch):
-    """variant tc: mma.sync flash attention (default); t5: tcgen05/TMEM two-pass attention (VX_ATTN_T5=1); t5max: the same
-    with a max-only statistics pass (VX_ATTN_T5=2; written after the round-1 GPU budget ran out -> VX_TEST_EXPERIMENTAL=1)."""
-    import os
-    if variant == "t5max":
-        if os.environ.get("VX_TEST_EXPERIMENTAL") != "1":
-            pytest.skip("not yet run on a B200; set VX_TEST_EXPERIMENTAL=1")
-        monkeypatch.setenv("VX_ATTN_T5", "2")
+def test_tensor_core_attention(S, length, mode, variant):
+    """variant t5: tcgen05/TMEM single-pass attention (default for prefill + NAR in bf16 mode); tc: the mma.sync flash attention
+    (VX_ATTN_T5=0)."""
     from vallex_b200 import _capi
     lib = _capi.lib()
     g = torch.Generator().manual_seed(S * 1000 + length)

@@ -1,20 +1,18 @@
-// tcgen05 / TMEM attention for the full-sequence passes (bf16 mode): S = Q K^T and O = P V on the 5th-generation
-// tensor cores, accumulators in TMEM, operands staged by the TMA engine (cp.async.bulk) as tile images.
+// tcgen05 / TMEM attention for the full-sequence passes (bf16 mode; default, VX_ATTN_T5=0 selects the mma.sync kernel of
+// attention_tc.cu): S = Q K^T and O = P V on the 5th-generation tensor cores, accumulators in TMEM, operands staged by the
+// TMA engine (cp.async.bulk) as tile images.
 //
-// One CTA = 128 query rows of one (utterance, head); 128 threads, thread t owns query row t (= TMEM lane t), so the
-// softmax statistics are per-thread registers -- no shuffles, no shared-memory reductions.  Two passes over the key
-// tiles (128 keys each):
-//   pass 1: S_j = Q K_j^T (4 x tcgen05.mma M128 N128 K16) -> tcgen05.ld -> running row max m and row sum l;
-//   pass 2: S_j again, P_j = exp2(S_j - m) / l written as bf16 into shared memory in the K-major 128B-swizzled image a
-//           tcgen05 A operand wants, then O += P_j V_j (8 x tcgen05.mma M128 N64 K16).  Because m and l are final,
-//           O never needs the online-softmax rescale (no TMEM read-modify-write); the price is a second QK^T, which
-//           the tensor pipe does in ~260 cycles per tile while the exponentials (SFU) are the real bound.
-// Two CTAs are resident per SM (112 KB shared memory, 256 TMEM columns each): while one runs its softmax the other
-// one's MMAs and copies proceed, so the synchronous in-CTA flow needs no warp specialisation.
+// One CTA = 128 query rows of one (utterance, head); 256 threads: warps 0-3 own query rows 0..127 (= TMEM lanes) x key columns
+// [0,32) of every 64-key tile, warps 4-7 the same rows x [32,64), so the softmax statistics are per-thread registers -- no
+// shuffles, no shared-memory reductions.  ONE sweep over the key tiles (single-pass online softmax, see the kernel comment);
+// S is double-buffered in TMEM so Q K^T of tile j+1 runs under the softmax of tile j, P is double-buffered in shared memory
+// (written as the K-major 128B-swizzled image a tcgen05 A operand wants) so O += P_j V_j runs under the softmax of tile j+1.
+// Two CTAs are resident per SM (108 KB shared memory, 256 TMEM columns each).
 //   mode 0: bidirectional (NAR, modules/activation.py:566-585)
 //   mode 1: AR prefill mask (models/vallex.py:534-549): key j visible to query i iff j < S or j <= i.
-// Operands (built by pack_qkv_heads_kernel from the QKV GEMM's row-major bf16 output; utterances start on 128-row
-// boundaries so a key tile is exactly one image block):
+// Operands (written by the QKV GEMM's TC_EPI_QKV_HEADS epilogue for the NAR layers, by pack_qkv_heads_kernel from the row-major
+// bf16 QKV for the prefill layers, whose KV scatter wants the row-major form; utterances start on 128-row boundaries so a key
+// tile is exactly one image block):
 //   q_img, k_img : per head, tile image of [rows, 64]     (block = 128 rows x 64 d, 16 KB)
 //   vt_img       : per head, per 64-key block, [64 d rows x 128 B] K-major swizzled (V transposed: B operand of P V)
 // Output: bf16 tile image [rows, 1024] = the A operand of the out-proj GEMM.
@@ -75,31 +73,53 @@ __device__ __forceinline__ uint32_t t5_pack(float a, float b) {  // cvt.rn.bf16x
   return r;
 }
 
-// 256 threads: warps 0-3 own rows 0..127 x key columns [0,32) of every 64-key tile, warps 4-7 the same rows x [32,64).
-// S is double-buffered in TMEM so the MMA of tile j+1 runs under the softmax of tile j; P is double-buffered in shared
-// memory so O += P_j V_j runs under the softmax of tile j+1.
-// MAXONLY (VX_ATTN_T5=2, experimental): pass 1 tracks only the row maximum (no exponentials), pass 2 accumulates the row sum
-// while it forms P = exp2(S - m) and the epilogue scales O by 1/l -- half the MUFU work of the statistics pass.
-template <bool MAXONLY>
+// 32 lanes x 32 consecutive fp32 columns <- 32 registers per thread (the inverse of tmem_ld32)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+      "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+      "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+      "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+      "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// =================================================================================================================
+// Single pass: one sweep over the key tiles with an online softmax whose running row maximum is
+// only raised LAZILY -- when a tile's row maximum exceeds the maximum in use by more than 2^8 -- so the rescale of the
+// O accumulator (TMEM read-modify-write by the warp that owns the rows, after the P V products in flight have drained) is
+// rare after the first tiles; P = exp2(S - m_used) stays <= 256 and the row sum l carries the same scale, so the final
+// O / l is exact softmax.  (Round 1's two-pass kernel -- statistics pass, then P V -- recomputed Q K^T and re-read K: it only
+// tied the mma.sync kernel; this one is 9 % faster on a whole NAR pass, profiles/r02_attention.log.)  The two column halves of a row (keys 0-31 / 32-63 of every 64-key tile) are INDEPENDENT online softmaxes
+// with their own accumulators O_a / O_b in TMEM (the P V product of a tile is issued as two K-halves), so no per-tile
+// exchange of row maxima is needed (in the first version that block barrier was 45 % of the stall samples); the halves are
+// merged once in the epilogue.
+// =================================================================================================================
 __global__ void __launch_bounds__(256, 2) attn_t5_kernel(Batch bt, const uint8_t* __restrict__ q_img,
-                                                         const uint8_t* __restrict__ k_img,
-                                                         const uint8_t* __restrict__ vt_img, int64_t R,
-                                                         const int32_t* __restrict__ row0, int mode,
-                                                         uint8_t* __restrict__ out_img) {
+                                                                 const uint8_t* __restrict__ k_img,
+                                                                 const uint8_t* __restrict__ vt_img, int64_t R,
+                                                                 const int32_t* __restrict__ row0, int mode,
+                                                                 uint8_t* __restrict__ out_img) {
   extern __shared__ __align__(1024) uint8_t t5_raw[];
   uint8_t* smem = t5_raw;
-  if ((smem_u32(smem) & 1023u) != 0) __trap();  // the 128-byte swizzle needs 1024-byte aligned operand tiles
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sQ = smem + T5_Q;
   uint8_t* sK = smem + T5_K;
   uint8_t* sV = smem + T5_V;
   uint8_t* sP = smem + T5_P;
-  float2* sstat = reinterpret_cast<float2*>(smem + T5_ST);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T5_BAR);
-  uint64_t* qbar = bars;         // Q landed
+  uint64_t* qbar = bars;
   uint64_t* kfull = bars + 1;    // [3]
   uint64_t* vfull = bars + 4;    // [4]
-  uint64_t* sfull = bars + 8;    // [2]  S_j in TMEM
-  uint64_t* pvdone = bars + 10;  // [2]  O += P_j V_j finished (P buffer and V slot reusable)
+  uint64_t* sfull = bars + 8;    // [2]
+  uint64_t* pvdone = bars + 10;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 128;
@@ -107,16 +127,16 @@ __global__ void __launch_bounds__(256, 2) attn_t5_kernel(Batch bt, const uint8_t
   const int len = (mode == 1) ? S + bt.P[b] + 1 : S + bt.P[b] + bt.T[b];
   if (q0 >= len) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int half = warp >> 2;                 // which 32 of the tile's 64 key columns
-  const int rloc = (warp & 3) * 32 + lane;    // query row inside the tile = TMEM lane
-  const int64_t r0 = row0[b];                 // multiple of 128
+  const int half = warp >> 2;
+  const int rloc = (warp & 3) * 32 + lane;
+  const int64_t r0 = row0[b];
   int kend = len;
   if (mode == 1) kend = min(len, max(S, q0 + 128));
-  const int nkt = (kend + 63) >> 6;           // 64-key tiles
+  const int nkt = (kend + 63) >> 6;
   const size_t head_bytes = (size_t)R * 128;
   const uint8_t* qsrc = q_img + (size_t)h * head_bytes + (size_t)((r0 + q0) >> 7) * 16384;
-  const uint8_t* ksrc = k_img + (size_t)h * head_bytes + (size_t)(r0 >> 7) * 16384;   // + j * 8192 (64 rows x 128 B)
-  const uint8_t* vsrc = vt_img + ((size_t)h * (R / 64) + (size_t)(r0 >> 6)) * 8192;    // + j * 8192
+  const uint8_t* ksrc = k_img + (size_t)h * head_bytes + (size_t)(r0 >> 7) * 16384;
+  const uint8_t* vsrc = vt_img + ((size_t)h * (R / 64) + (size_t)(r0 >> 6)) * 8192;
 
   if (tid == 0) {
     mbar_init(qbar, 1);
@@ -130,20 +150,26 @@ __global__ void __launch_bounds__(256, 2) attn_t5_kernel(Batch bt, const uint8_t
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tO = tmem + 128;
+  const uint32_t tO = tmem + 128 + half * 64;   // this column half's own accumulator: O_a at columns 128..191, O_b at 192..255
+  const uint32_t tOa = tmem + 128, tOb = tmem + 192;
   const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
 
-  // barrier phase counters (every thread performs every wait, so these stay uniform)
-  uint32_t kph = 0, vph = 0, sph = 0, pph = 0;  // bit i = parity of barrier i of the group
+  uint32_t kph = 0, vph = 0, sph = 0, pph = 0;
+  int pv_waited = -1;   // P V products of tiles <= pv_waited are known complete (every thread waits each completion once, in order)
   auto wait_k = [&](int slot) { mbar_wait(&kfull[slot], (kph >> slot) & 1); kph ^= 1u << slot; };
   auto wait_s = [&](int buf) { mbar_wait(&sfull[buf], (sph >> buf) & 1); sph ^= 1u << buf; };
-  auto wait_pv = [&](int buf) { mbar_wait(&pvdone[buf], (pph >> buf) & 1); pph ^= 1u << buf; };
-
+  auto ensure_pv = [&](int t) {
+    while (pv_waited < t) {
+      ++pv_waited;
+      const int buf = pv_waited & 1;
+      mbar_wait(&pvdone[buf], (pph >> buf) & 1);
+      pph ^= 1u << buf;
+    }
+  };
   constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
-  const float sl2 = 0.125f * 1.44269504088896340736f;  // 1/sqrt(64) * log2(e)
+  const float sl2 = 0.125f * 1.44269504088896340736f;
   const int qi = q0 + rloc;
-
-  auto issue_k = [&](int j) {  // thread 0
+  auto issue_k = [&](int j) {
     mbar_expect_tx(&kfull[j % 3], 8192);
     bulk_g2s(sK + (j % 3) * 8192, ksrc + (size_t)j * 8192, 8192, &kfull[j % 3]);
   };
@@ -151,14 +177,14 @@ __global__ void __launch_bounds__(256, 2) attn_t5_kernel(Batch bt, const uint8_t
     mbar_expect_tx(&vfull[j & 3], 8192);
     bulk_g2s(sV + (j & 3) * 8192, vsrc + (size_t)j * 8192, 8192, &vfull[j & 3]);
   };
-  auto mma_s = [&](int j) {  // thread 0: S_j = Q K_j^T -> TMEM buffer j & 1
+  auto mma_s = [&](int j) {
     tc_fence_after();
     const uint64_t ad = umma_desc_sw128(smem_u32(sQ)), bd = umma_desc_sw128(smem_u32(sK + (j % 3) * 8192));
 #pragma unroll
     for (int k = 0; k < 4; ++k) umma_bf16(tmem + (j & 1) * 64, ad + 2 * k, bd + 2 * k, idesc, k ? 1u : 0u);
     umma_commit(&sfull[j & 1]);
   };
-  auto tile_full = [&](int j) {  // every key of tile j visible to every row of this CTA
+  auto tile_full = [&](int j) {
     const int k0 = j * 64;
     return (k0 + 64 <= len) && (mode == 0 || k0 + 64 <= S || k0 + 63 <= q0);
   };
@@ -172,9 +198,10 @@ __global__ void __launch_bounds__(256, 2) attn_t5_kernel(Batch bt, const uint8_t
     mbar_expect_tx(qbar, 16384);
     bulk_g2s(sQ, qsrc, 16384, qbar);
     for (int j = 0; j < 3 && j < nkt; ++j) issue_k(j);
+    for (int j = 0; j < 2 && j < nkt; ++j) issue_v(j);
   }
-  // ---------------- pass 1: row max and row sum of this thread's column half -----------------------------------
-  float m_run = -INFINITY, l_run = 0.f;
+  float m_used = -INFINITY;   // the row maximum this half's exponentials use
+  float l_part = 0.f;         // this half's row sum, in the scale of m_used
   mbar_wait(qbar, 0);
   wait_k(0);
   if (tid == 0) mma_s(0);
@@ -184,13 +211,14 @@ __global__ void __launch_bounds__(256, 2) attn_t5_kernel(Batch bt, const uint8_t
       if (tid == 0) mma_s(j + 1);       // runs under the softmax of tile j
     }
     wait_s(j & 1);
-    if (tid == 0 && j + 3 < nkt) issue_k(j + 3);  // S_j is complete: its K slot is free
+    if (tid == 0 && j + 3 < nkt) issue_k(j + 3);
     tc_fence_after();
     float v[32];
     tmem_ld32(tmem + (j & 1) * 64 + lane_addr + half * 32, v);
     const int kb = j * 64 + half * 32;
+    const bool full = tile_full(j);
     float mx = -INFINITY;
-    if (tile_full(j)) {
+    if (full) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) mx = fmaxf(mx, v[i]);
     } else {
@@ -200,107 +228,78 @@ __global__ void __launch_bounds__(256, 2) attn_t5_kernel(Batch bt, const uint8_t
         mx = fmaxf(mx, v[i]);
       }
     }
-    const float m_new = fmaxf(m_run, mx * sl2);
-    if constexpr (MAXONLY) {
-      m_run = m_new;
-    } else if (m_new != -INFINITY) {
-      float s = 0.f;
+    const float m_tile = mx * sl2;
+    const bool need = m_tile > m_used + 8.0f;     // -inf + 8 = -inf: the first visible key always raises the maximum
+    if (__any_sync(0xffffffffu, need)) {
+      const float scale = need ? t5_ex2(m_used - m_tile) : 1.0f;   // ex2(-inf) = 0 on the first raise
+      if (need) m_used = m_tile;
+      l_part *= scale;
+      if (j > 0) {                      // this warp owns its rows of its half's accumulator: O_h *= scale once P V products have drained
+        ensure_pv(j - 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 64; c += 32) {
+          float o[32];
+          tmem_ld32(tO + lane_addr + c, o);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) s += t5_ex2(fmaf(v[i], sl2, -m_new));
-      l_run = l_run * t5_ex2(m_run - m_new) + s;   // ex2(-inf) = 0 covers the first tile
-      m_run = m_new;
+          for (int i = 0; i < 32; ++i) o[i] *= scale;
+          tmem_st32(tO + lane_addr + c, o);
+        }
+        tc_fence_before();
+      }
     }
-    tc_fence_before();
-    __syncthreads();  // both halves have read S_j: its TMEM buffer may take S_{j+2}
-  }
-  // combine the two column halves of every row
-  sstat[tid] = make_float2(m_run, l_run);
-  __syncthreads();
-  {
-    const float2 o = sstat[tid ^ 128];
-    const float m = fmaxf(m_run, o.x);
-    const float l = (m == -INFINITY) ? 1.f : l_run * t5_ex2(m_run - m) + o.y * t5_ex2(o.x - m);
-    m_run = m;
-    l_run = l;
-  }
-  const float inv_l = MAXONLY ? 1.0f : 1.0f / l_run;
-  float l_acc = 0.f;   // MAXONLY: row sum of this thread's column half, accumulated in pass 2
-  // ---------------- pass 2: P = exp2(S - m) / l, O += P V ---------------------------------------------------------
-  if (tid == 0) {
-    for (int j = 0; j < 3 && j < nkt; ++j) issue_k(j);
-    for (int j = 0; j < 2 && j < nkt; ++j) issue_v(j);
-  }
-  wait_k(0);
-  if (tid == 0) mma_s(0);
-  for (int j = 0; j < nkt; ++j) {
-    if (j + 1 < nkt) {
-      wait_k((j + 1) % 3);
-      if (tid == 0) mma_s(j + 1);
-    }
-    wait_s(j & 1);
-    if (tid == 0 && j + 3 < nkt) issue_k(j + 3);
-    tc_fence_after();
-    float v[32];
-    tmem_ld32(tmem + (j & 1) * 64 + lane_addr + half * 32, v);
-    const int kb = j * 64 + half * 32;
     uint32_t pk[16];
-    if (tile_full(j)) {
+    float ls = 0.f;
+    const float mu = (m_used == -INFINITY) ? 0.f : m_used;   // a half that has seen no visible key yet: every P is ex2(-inf) = 0
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        const float p0 = t5_ex2(fmaf(v[i], sl2, -m_run)) * inv_l, p1 = t5_ex2(fmaf(v[i + 1], sl2, -m_run)) * inv_l;
-        if constexpr (MAXONLY) l_acc += p0 + p1;
-        pk[i >> 1] = t5_pack(p0, p1);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        const float p0 = visible(kb + i) ? t5_ex2(fmaf(v[i], sl2, -m_run)) * inv_l : 0.f;
-        const float p1 = visible(kb + i + 1) ? t5_ex2(fmaf(v[i + 1], sl2, -m_run)) * inv_l : 0.f;
-        if constexpr (MAXONLY) l_acc += p0 + p1;
-        pk[i >> 1] = t5_pack(p0, p1);
-      }
+    for (int i = 0; i < 32; i += 2) {
+      const float p0 = t5_ex2(fmaf(v[i], sl2, -mu)), p1 = t5_ex2(fmaf(v[i + 1], sl2, -mu));   // masked: ex2(-inf) = 0
+      ls += p0 + p1;
+      pk[i >> 1] = t5_pack(p0, p1);
     }
-    if (j >= 2) wait_pv(j & 1);                    // O += P_{j-2} V_{j-2} done: P buffer j&1 and V slot (j-2)&3 are free
-    if (tid == 0 && j + 2 < nkt) issue_v(j + 2);
-    // row rloc, keys half*32 .. +31 of the tile -> chunks half*4 .. +3 of the 128-byte row, swizzled by (row & 7)
+    l_part += ls;
+    ensure_pv(j - 2);                   // O += P_{j-2} V_{j-2} done: P buffer j&1 and V slot (j-2)&3 are free
+    if (tid == 0 && j + 2 < nkt && j >= 0) issue_v(j + 2);
     uint8_t* prow = sP + (j & 1) * 16384 + rloc * 128;
 #pragma unroll
     for (int q = 0; q < 4; ++q)
       *reinterpret_cast<uint4*>(prow + (((half * 4 + q) ^ (rloc & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-    fence_proxy_async();   // P was written through the generic proxy, the MMA reads it through the async proxy
+    fence_proxy_async();
     tc_fence_before();
-    __syncthreads();       // also: both halves have read S_j
+    __syncthreads();                    // (2) P_j complete, S_j consumed by both halves, any O rescale finished
     if (tid == 0) {
       mbar_wait(&vfull[j & 3], (vph >> (j & 3)) & 1);
       tc_fence_after();
       const uint64_t ad = umma_desc_sw128(smem_u32(sP + (j & 1) * 16384)), bd = umma_desc_sw128(smem_u32(sV + (j & 3) * 8192));
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) umma_bf16(tO, ad + 2 * ks, bd + 2 * ks, idesc, (j | ks) ? 1u : 0u);
+      for (int ks = 0; ks < 4; ++ks)    // keys 0-31 of the tile accumulate into O_a, keys 32-63 into O_b
+        umma_bf16(ks < 2 ? tOa : tOb, ad + 2 * ks, bd + 2 * ks, idesc, (j | (ks & 1)) ? 1u : 0u);
       umma_commit(&pvdone[j & 1]);
     }
-    vph ^= 1u << (j & 3);  // every thread tracks the V phases (only thread 0 waits)
+    vph ^= 1u << (j & 3);
   }
-  for (int j = max(nkt - 2, 0); j < nkt; ++j) wait_pv(j & 1);  // the last two P V products
+  ensure_pv(nkt - 1);
   tc_fence_after();
-  // ---------------- epilogue: O (already normalised unless MAXONLY) -> bf16 tile image ------------------------------------
-  float o_scale = 1.0f;
-  if constexpr (MAXONLY) {   // row sum = the two column halves together
-    __syncthreads();
-    sstat[tid] = make_float2(l_acc, 0.f);
-    __syncthreads();
-    const float l = l_acc + sstat[tid ^ 128].x;
-    o_scale = (l > 0.f) ? 1.0f / l : 0.f;
-  }
+  // ---------------- epilogue: O / l -> bf16 tile image ---------------------------------------------------------------------
+  float2* sml = reinterpret_cast<float2*>(smem + T5_ST);    // [256] (m_used, l_part) of every (row, half)
+  sml[tid] = make_float2(m_used, l_part);
+  __syncthreads();
+  const float2 other = sml[tid ^ 128];
+  const float M = fmaxf(m_used, other.x);
+  const float s_self = (m_used == -INFINITY) ? 0.f : t5_ex2(m_used - M), s_other = (other.x == -INFINITY) ? 0.f : t5_ex2(other.x - M);
+  const float l = l_part * s_self + other.y * s_other;
+  const float inv = (l > 0.f) ? 1.0f / l : 0.f;
+  const float sa = (half == 0 ? s_self : s_other) * inv, sb = (half == 0 ? s_other : s_self) * inv;
   {
-    float v[32];
-    tmem_ld32(tO + lane_addr + half * 32, v);
-    if constexpr (MAXONLY) {
+    float v[32], w[32];
+    tmem_ld32(tOa + lane_addr + half * 32, v);   // output columns half*32 .. +31 of this row from BOTH accumulators
+    tmem_ld32(tOb + lane_addr + half * 32, w);
+    // (a half that never saw a visible key has scale 0 and an accumulator that was never written: select, do not multiply)
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] *= o_scale;
-    }
+    for (int i = 0; i < 32; ++i) v[i] = (sa != 0.f ? v[i] * sa : 0.f) + (sb != 0.f ? w[i] * sb : 0.f);
     if (qi < len) {
       const int64_t grow = r0 + qi;
-      uint8_t* slot = out_img + tile_image_offset(grow, h * kDH, kD) - (((int)(grow & 7)) << 4);  // start of the 128-byte row slot
+      uint8_t* slot = out_img + tile_image_offset(grow, h * kDH, kD) - (((int)(grow & 7)) << 4);
       const int swz = (int)(grow & 7);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -323,20 +322,11 @@ void launch_attn_t5(const Batch& bt, const void* q_img, const void* k_img, const
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_done[dev & 63]) {
-    cudaFuncSetAttribute(attn_t5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_BYTES);
-    cudaFuncSetAttribute(attn_t5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_BYTES);
+    cudaFuncSetAttribute(attn_t5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_BYTES);
     attr_done[dev & 63] = true;
   }
-  const char* env = getenv("VX_ATTN_T5");
-  if (env && (env[0] == '2' || env[0] == '3')) {
-    attn_t5_kernel<true><<<dim3((max_len + 127) / 128, kH, bt.B), 256, T5_BYTES, st>>>(bt, (const uint8_t*)q_img, (const uint8_t*)k_img,
-                                                                             (const uint8_t*)vt_img, R, row0, mode,
-                                                                             (uint8_t*)out_img);
-  } else {
-    attn_t5_kernel<false><<<dim3((max_len + 127) / 128, kH, bt.B), 256, T5_BYTES, st>>>(bt, (const uint8_t*)q_img, (const uint8_t*)k_img,
-                                                                             (const uint8_t*)vt_img, R, row0, mode,
-                                                                             (uint8_t*)out_img);
-  }
+  attn_t5_kernel<<<dim3((max_len + 127) / 128, kH, bt.B), 256, T5_BYTES, st>>>(bt, (const uint8_t*)q_img, (const uint8_t*)k_img,
+                                                                    (const uint8_t*)vt_img, R, row0, mode, (uint8_t*)out_img);
 }
 
 }  // namespace vx

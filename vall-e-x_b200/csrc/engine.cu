@@ -183,7 +183,7 @@ struct vx_engine {
   int decode_fused_maxb = 2;
   void* ff2_t_blob = nullptr;                        // 12 x [4096][1024] bf16
   bool attn_t5 = false;
-  bool attn_t5_fuse = false;                         // VX_ATTN_T5=3: QKV GEMM epilogue writes the per-head operand images (NAR layers)                              // VX_ATTN_T5=1: tcgen05/TMEM attention instead of mma.sync
+  bool attn_t5_fuse = false;                         // the QKV GEMM epilogue writes the per-head operand images (NAR layers)
   int64_t full_rows = 0;                             // packed rows of the current full-sequence pass (128-aligned starts)
   Buf xs, xsn, qkvs, atts, ffs, logits, part, tick;  // decode-step scratch
   Buf p_xb, p_acc;                                 // fused decode variant: mid-layer residual, fixed-point accumulators
@@ -466,9 +466,9 @@ int vx_create(int device, int max_batch, int max_ctx, int dtype_mode, vx_engine*
   const char* fu = getenv("VX_DECODE_FUSED");   // unset: fused kernel for B <= 2 (validated sizes); 1: B <= 8; 0: never
   e->decode_fused = !(fu && fu[0] == '0');
   e->decode_fused_maxb = (fu && fu[0] == '1') ? 8 : 2;
-  const char* t5 = getenv("VX_ATTN_T5");
-  e->attn_t5 = t5 && (t5[0] == '1' || t5[0] == '2' || t5[0] == '3');   // 2: max-only statistics pass; 3: + head images from the GEMM epilogue
-  e->attn_t5_fuse = t5 && t5[0] == '3';
+  const char* t5 = getenv("VX_ATTN_T5");   // tcgen05/TMEM attention for prefill + NAR (default); VX_ATTN_T5=0: the mma.sync kernel
+  e->attn_t5 = !(t5 && t5[0] == '0');
+  e->attn_t5_fuse = e->attn_t5;             // the QKV GEMM epilogue writes the per-head operand images of the NAR layers
   const char* dg = getenv("VX_DECODE_GRAPH");
   e->decode_graph = dg && dg[0] == '1';
   e->num_sms = prop.multiProcessorCount;
