@@ -120,7 +120,8 @@ __global__ void __launch_bounds__(256, 2) attn_t5_kernel(Batch bt, const uint8_t
   uint64_t* vfull = bars + 4;    // [4]
   uint64_t* sfull = bars + 8;    // [2]
   uint64_t* pvdone = bars + 10;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* pfull = bars + 12;   // [2]  all 256 threads have written their part of P_j (and consumed S_j)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 128;
   const int S = bt.S[b];
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(256, 2) attn_t5_kernel(Batch bt, const uint8_t
     mbar_init(qbar, 1);
     for (int i = 0; i < 3; ++i) mbar_init(&kfull[i], 1);
     for (int i = 0; i < 4; ++i) mbar_init(&vfull[i], 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&sfull[i], 1); mbar_init(&pvdone[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sfull[i], 1); mbar_init(&pvdone[i], 1); mbar_init(&pfull[i], 256); }
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<256>(tmem_slot);
@@ -202,16 +203,19 @@ __global__ void __launch_bounds__(256, 2) attn_t5_kernel(Batch bt, const uint8_t
   }
   float m_used = -INFINITY;   // the row maximum this half's exponentials use
   float l_part = 0.f;         // this half's row sum, in the scale of m_used
-  mbar_wait(qbar, 0);
-  wait_k(0);
-  if (tid == 0) mma_s(0);
+  // No block-wide barrier inside the loop: a thread owns its (row, column half) and meets the others only through mbarriers --
+  // sfull (S_j in TMEM), pfull (P_j complete: 256 arrivals), pvdone (O += P_j V_j finished).  Thread 0 additionally issues the
+  // copies and the MMAs; the other warps run ahead of it as far as the double buffers allow.
+  uint32_t pfph = 0;
+  if (tid == 0) {
+    mbar_wait(qbar, 0);
+    wait_k(0);
+    mma_s(0);
+    if (nkt > 1) { wait_k(1); mma_s(1); }
+  }
   for (int j = 0; j < nkt; ++j) {
-    if (j + 1 < nkt) {
-      wait_k((j + 1) % 3);
-      if (tid == 0) mma_s(j + 1);       // runs under the softmax of tile j
-    }
     wait_s(j & 1);
-    if (tid == 0 && j + 3 < nkt) issue_k(j + 3);
+    if (tid == 0 && j + 3 < nkt) issue_k(j + 3);     // S_j is complete: its K slot is free
     tc_fence_after();
     float v[32];
     tmem_ld32(tmem + (j & 1) * 64 + lane_addr + half * 32, v);
@@ -259,15 +263,17 @@ __global__ void __launch_bounds__(256, 2) attn_t5_kernel(Batch bt, const uint8_t
     }
     l_part += ls;
     ensure_pv(j - 2);                   // O += P_{j-2} V_{j-2} done: P buffer j&1 and V slot (j-2)&3 are free
-    if (tid == 0 && j + 2 < nkt && j >= 0) issue_v(j + 2);
+    if (tid == 0 && j + 2 < nkt) issue_v(j + 2);
     uint8_t* prow = sP + (j & 1) * 16384 + rloc * 128;
 #pragma unroll
     for (int q = 0; q < 4; ++q)
       *reinterpret_cast<uint4*>(prow + (((half * 4 + q) ^ (rloc & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();                    // (2) P_j complete, S_j consumed by both halves, any O rescale finished
+    fence_proxy_async();                // P was written through the generic proxy, the MMA reads it through the async proxy
+    tc_fence_before();                  // ... and this thread's TMEM reads of S_j / writes of O_h are ordered before the arrival
+    mbar_arrive(&pfull[j & 1]);
     if (tid == 0) {
+      mbar_wait(&pfull[j & 1], (pfph >> (j & 1)) & 1);   // every thread's part of P_j is in place, S_j is consumed, rescales are done
+      pfph ^= 1u << (j & 1);
       mbar_wait(&vfull[j & 3], (vph >> (j & 3)) & 1);
       tc_fence_after();
       const uint64_t ad = umma_desc_sw128(smem_u32(sP + (j & 1) * 16384)), bd = umma_desc_sw128(smem_u32(sV + (j & 3) * 8192));
@@ -275,6 +281,10 @@ __global__ void __launch_bounds__(256, 2) attn_t5_kernel(Batch bt, const uint8_t
       for (int ks = 0; ks < 4; ++ks)    // keys 0-31 of the tile accumulate into O_a, keys 32-63 into O_b
         umma_bf16(ks < 2 ? tOa : tOb, ad + 2 * ks, bd + 2 * ks, idesc, (j | (ks & 1)) ? 1u : 0u);
       umma_commit(&pvdone[j & 1]);
+      if (j + 2 < nkt) {                // S buffer j&1 is free: Q K^T of tile j+2 runs under the softmax of tile j+1
+        wait_k((j + 2) % 3);
+        mma_s(j + 2);
+      }
     }
     vph ^= 1u << (j & 3);
   }

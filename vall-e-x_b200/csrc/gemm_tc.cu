@@ -394,13 +394,17 @@ __global__ void __launch_bounds__(256) layernorm_image_kernel(const float* __res
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
     const int c0 = it * 256 + lane * 8;
-    float y[8];
+    float g[8], be[8], y[8];
+    load8(gamma + c0, g);     // 128-bit loads (the scalar form issued 128 LDGs per thread and made the kernel LSU-bound)
+    load8(beta + c0, be);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float t = (v[it][i] - mean) * rstd;
-      t = t * __ldg(gamma + c0 + i) + __ldg(beta + c0 + i);
-      if (ada_w) t = __ldg(ada_w + c0 + i) * t + __ldg(ada_b + c0 + i);
-      y[i] = t;
+    for (int i = 0; i < 8; ++i) y[i] = ((v[it][i] - mean) * rstd) * g[i] + be[i];
+    if (ada_w) {
+      float aw[8], ab[8];
+      load8(ada_w + c0, aw);
+      load8(ada_b + c0, ab);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] = aw[i] * y[i] + ab[i];
     }
     uint4 p;
     p.x = pk(y[0], y[1]); p.y = pk(y[2], y[3]); p.z = pk(y[4], y[5]); p.w = pk(y[6], y[7]);
