@@ -2,7 +2,8 @@
 // attention_tc.cu): S = Q K^T and O = P V on the 5th-generation tensor cores, accumulators in TMEM, operands staged by the
 // TMA engine (cp.async.bulk) as tile images.
 //
-// One CTA = 128 query rows of one (utterance, head); 256 threads: warps 0-3 own query rows 0..127 (= TMEM lanes) x key columns
+// One CTA = 128 query rows of one (utterance, head); 288 threads = 8 softmax warps + 1 controller warp (one lane issues every bulk
+// copy and MMA): warps 0-3 own query rows 0..127 (= TMEM lanes) x key columns
 // [0,32) of every 64-key tile, warps 4-7 the same rows x [32,64), so the softmax statistics are per-thread registers -- no
 // shuffles, no shared-memory reductions.  ONE sweep over the key tiles (single-pass online softmax, see the kernel comment);
 // S is double-buffered in TMEM so Q K^T of tile j+1 runs under the softmax of tile j, P is double-buffered in shared memory
@@ -102,7 +103,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
 // exchange of row maxima is needed (in the first version that block barrier was 45 % of the stall samples); the halves are
 // merged once in the epilogue.
 // =================================================================================================================
-__global__ void __launch_bounds__(256, 2) attn_t5_kernel(Batch bt, const uint8_t* __restrict__ q_img,
+__global__ void __launch_bounds__(288, 2) attn_t5_kernel(Batch bt, const uint8_t* __restrict__ q_img,
                                                                  const uint8_t* __restrict__ k_img,
                                                                  const uint8_t* __restrict__ vt_img, int64_t R,
                                                                  const int32_t* __restrict__ row0, int mode,
@@ -195,105 +196,108 @@ __global__ void __launch_bounds__(256, 2) attn_t5_kernel(Batch bt, const uint8_t
     return vis;
   };
 
-  if (tid == 0) {
-    mbar_expect_tx(qbar, 16384);
-    bulk_g2s(sQ, qsrc, 16384, qbar);
-    for (int j = 0; j < 3 && j < nkt; ++j) issue_k(j);
-    for (int j = 0; j < 2 && j < nkt; ++j) issue_v(j);
-  }
   float m_used = -INFINITY;   // the row maximum this half's exponentials use
   float l_part = 0.f;         // this half's row sum, in the scale of m_used
-  // No block-wide barrier inside the loop: a thread owns its (row, column half) and meets the others only through mbarriers --
-  // sfull (S_j in TMEM), pfull (P_j complete: 256 arrivals), pvdone (O += P_j V_j finished).  Thread 0 additionally issues the
-  // copies and the MMAs; the other warps run ahead of it as far as the double buffers allow.
-  uint32_t pfph = 0;
-  if (tid == 0) {
-    mbar_wait(qbar, 0);
-    wait_k(0);
-    mma_s(0);
-    if (nkt > 1) { wait_k(1); mma_s(1); }
-  }
-  for (int j = 0; j < nkt; ++j) {
-    wait_s(j & 1);
-    if (tid == 0 && j + 3 < nkt) issue_k(j + 3);     // S_j is complete: its K slot is free
-    tc_fence_after();
-    float v[32];
-    tmem_ld32(tmem + (j & 1) * 64 + lane_addr + half * 32, v);
-    const int kb = j * 64 + half * 32;
-    const bool full = tile_full(j);
-    float mx = -INFINITY;
-    if (full) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, v[i]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        v[i] = visible(kb + i) ? v[i] : -INFINITY;
-        mx = fmaxf(mx, v[i]);
-      }
-    }
-    const float m_tile = mx * sl2;
-    const bool need = m_tile > m_used + 8.0f;     // -inf + 8 = -inf: the first visible key always raises the maximum
-    if (__any_sync(0xffffffffu, need)) {
-      const float scale = need ? t5_ex2(m_used - m_tile) : 1.0f;   // ex2(-inf) = 0 on the first raise
-      if (need) m_used = m_tile;
-      l_part *= scale;
-      if (j > 0) {                      // this warp owns its rows of its half's accumulator: O_h *= scale once P V products have drained
-        ensure_pv(j - 1);
+  // No block-wide barrier inside the loop: a softmax thread (warps 0-7) owns its (row, column half) and meets the others only
+  // through mbarriers -- sfull (S_j in TMEM), pfull (P_j complete: 256 arrivals), pvdone (O += P_j V_j finished).  Warp 8 is the
+  // controller: one lane issues every bulk copy and every MMA, so no softmax warp lags behind doing that work.
+  if (warp == 8) {
+    if (lane == 0) {
+      uint32_t pfph = 0;
+      mbar_expect_tx(qbar, 16384);
+      bulk_g2s(sQ, qsrc, 16384, qbar);
+      for (int j = 0; j < 3 && j < nkt; ++j) issue_k(j);
+      for (int j = 0; j < 2 && j < nkt; ++j) issue_v(j);
+      mbar_wait(qbar, 0);
+      wait_k(0);
+      mma_s(0);
+      if (nkt > 1) { wait_k(1); mma_s(1); }
+      for (int j = 0; j < nkt; ++j) {
+        wait_s(j & 1);
+        if (j + 3 < nkt) issue_k(j + 3);               // S_j is complete: its K slot is free
+        ensure_pv(j - 2);                              // O += P_{j-2} V_{j-2} done: V slot (j-2)&3 is free
+        if (j + 2 < nkt) issue_v(j + 2);
+        mbar_wait(&pfull[j & 1], (pfph >> (j & 1)) & 1);   // every thread's part of P_j is in place, S_j is consumed, rescales are done
+        pfph ^= 1u << (j & 1);
+        mbar_wait(&vfull[j & 3], (vph >> (j & 3)) & 1);
+        vph ^= 1u << (j & 3);
         tc_fence_after();
-#pragma unroll 1
-        for (int c = 0; c < 64; c += 32) {
-          float o[32];
-          tmem_ld32(tO + lane_addr + c, o);
+        const uint64_t ad = umma_desc_sw128(smem_u32(sP + (j & 1) * 16384)), bd = umma_desc_sw128(smem_u32(sV + (j & 3) * 8192));
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] *= scale;
-          tmem_st32(tO + lane_addr + c, o);
+        for (int ks = 0; ks < 4; ++ks)    // keys 0-31 of the tile accumulate into O_a, keys 32-63 into O_b
+          umma_bf16(ks < 2 ? tOa : tOb, ad + 2 * ks, bd + 2 * ks, idesc, (j | (ks & 1)) ? 1u : 0u);
+        umma_commit(&pvdone[j & 1]);
+        if (j + 2 < nkt) {                // S buffer j&1 is free: Q K^T of tile j+2 runs under the softmax of tile j+1
+          wait_k((j + 2) % 3);
+          mma_s(j + 2);
         }
-        tc_fence_before();
       }
     }
-    uint32_t pk[16];
-    float ls = 0.f;
-    const float mu = (m_used == -INFINITY) ? 0.f : m_used;   // a half that has seen no visible key yet: every P is ex2(-inf) = 0
-#pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      const float p0 = t5_ex2(fmaf(v[i], sl2, -mu)), p1 = t5_ex2(fmaf(v[i + 1], sl2, -mu));   // masked: ex2(-inf) = 0
-      ls += p0 + p1;
-      pk[i >> 1] = t5_pack(p0, p1);
-    }
-    l_part += ls;
-    ensure_pv(j - 2);                   // O += P_{j-2} V_{j-2} done: P buffer j&1 and V slot (j-2)&3 are free
-    if (tid == 0 && j + 2 < nkt) issue_v(j + 2);
-    uint8_t* prow = sP + (j & 1) * 16384 + rloc * 128;
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      *reinterpret_cast<uint4*>(prow + (((half * 4 + q) ^ (rloc & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-    fence_proxy_async();                // P was written through the generic proxy, the MMA reads it through the async proxy
-    tc_fence_before();                  // ... and this thread's TMEM reads of S_j / writes of O_h are ordered before the arrival
-    mbar_arrive(&pfull[j & 1]);
-    if (tid == 0) {
-      mbar_wait(&pfull[j & 1], (pfph >> (j & 1)) & 1);   // every thread's part of P_j is in place, S_j is consumed, rescales are done
-      pfph ^= 1u << (j & 1);
-      mbar_wait(&vfull[j & 3], (vph >> (j & 3)) & 1);
+  } else {
+    for (int j = 0; j < nkt; ++j) {
+      wait_s(j & 1);
       tc_fence_after();
-      const uint64_t ad = umma_desc_sw128(smem_u32(sP + (j & 1) * 16384)), bd = umma_desc_sw128(smem_u32(sV + (j & 3) * 8192));
+      float v[32];
+      tmem_ld32(tmem + (j & 1) * 64 + lane_addr + half * 32, v);
+      const int kb = j * 64 + half * 32;
+      float mx = -INFINITY;
+      if (tile_full(j)) {
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks)    // keys 0-31 of the tile accumulate into O_a, keys 32-63 into O_b
-        umma_bf16(ks < 2 ? tOa : tOb, ad + 2 * ks, bd + 2 * ks, idesc, (j | (ks & 1)) ? 1u : 0u);
-      umma_commit(&pvdone[j & 1]);
-      if (j + 2 < nkt) {                // S buffer j&1 is free: Q K^T of tile j+2 runs under the softmax of tile j+1
-        wait_k((j + 2) % 3);
-        mma_s(j + 2);
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, v[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          v[i] = visible(kb + i) ? v[i] : -INFINITY;
+          mx = fmaxf(mx, v[i]);
+        }
       }
+      const float m_tile = mx * sl2;
+      const bool need = m_tile > m_used + 8.0f;     // -inf + 8 = -inf: the first visible key always raises the maximum
+      if (__any_sync(0xffffffffu, need)) {
+        const float scale = need ? t5_ex2(m_used - m_tile) : 1.0f;   // ex2(-inf) = 0 on the first raise
+        if (need) m_used = m_tile;
+        l_part *= scale;
+        if (j > 0) {                      // this warp owns its rows of its half's accumulator: O_h *= scale once P V products have drained
+          ensure_pv(j - 1);
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < 64; c += 32) {
+            float o[32];
+            tmem_ld32(tO + lane_addr + c, o);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] *= scale;
+            tmem_st32(tO + lane_addr + c, o);
+          }
+          tc_fence_before();
+        }
+      }
+      uint32_t pk[16];
+      float ls = 0.f;
+      const float mu = (m_used == -INFINITY) ? 0.f : m_used;   // a half that has seen no visible key yet: every P is ex2(-inf) = 0
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const float p0 = t5_ex2(fmaf(v[i], sl2, -mu)), p1 = t5_ex2(fmaf(v[i + 1], sl2, -mu));   // masked: ex2(-inf) = 0
+        ls += p0 + p1;
+        pk[i >> 1] = t5_pack(p0, p1);
+      }
+      l_part += ls;
+      ensure_pv(j - 2);                   // O += P_{j-2} V_{j-2} done: P buffer j&1 is free
+      uint8_t* prow = sP + (j & 1) * 16384 + rloc * 128;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<uint4*>(prow + (((half * 4 + q) ^ (rloc & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      fence_proxy_async();                // P was written through the generic proxy, the MMA reads it through the async proxy
+      tc_fence_before();                  // ... and this thread's TMEM reads of S_j / writes of O_h are ordered before the arrival
+      mbar_arrive(&pfull[j & 1]);
     }
-    vph ^= 1u << (j & 3);
+    ensure_pv(nkt - 1);
   }
-  ensure_pv(nkt - 1);
   tc_fence_after();
   // ---------------- epilogue: O / l -> bf16 tile image ---------------------------------------------------------------------
   float2* sml = reinterpret_cast<float2*>(smem + T5_ST);    // [256] (m_used, l_part) of every (row, half)
-  sml[tid] = make_float2(m_used, l_part);
+  if (warp < 8) sml[tid] = make_float2(m_used, l_part);
   __syncthreads();
+  if (warp < 8) {
   const float2 other = sml[tid ^ 128];
   const float M = fmaxf(m_used, other.x);
   const float s_self = (m_used == -INFINITY) ? 0.f : t5_ex2(m_used - M), s_other = (other.x == -INFINITY) ? 0.f : t5_ex2(other.x - M);
@@ -320,6 +324,7 @@ __global__ void __launch_bounds__(256, 2) attn_t5_kernel(Batch bt, const uint8_t
       }
     }
   }
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc<256>(tmem);
@@ -335,7 +340,7 @@ void launch_attn_t5(const Batch& bt, const void* q_img, const void* k_img, const
     cudaFuncSetAttribute(attn_t5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_BYTES);
     attr_done[dev & 63] = true;
   }
-  attn_t5_kernel<<<dim3((max_len + 127) / 128, kH, bt.B), 256, T5_BYTES, st>>>(bt, (const uint8_t*)q_img, (const uint8_t*)k_img,
+  attn_t5_kernel<<<dim3((max_len + 127) / 128, kH, bt.B), 288, T5_BYTES, st>>>(bt, (const uint8_t*)q_img, (const uint8_t*)k_img,
                                                                     (const uint8_t*)vt_img, R, row0, mode, (uint8_t*)out_img);
 }
 
