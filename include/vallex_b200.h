@@ -134,6 +134,33 @@ VX_API int vx_nar(vx_engine* e, const int32_t* cb0, const int32_t* t_lens, int T
 VX_API int vx_vocos_decode(vx_engine* e, const int32_t* codes, int B, int T, int bandwidth_id, float* wave, int mem,
                     void* stream);
 
+/* ---- Prompt making: EnCodec 24 kHz encoder + residual vector quantiser ---------------------------------
+ * Replaces: `AudioTokenizer(device)` = `EncodecModel.encodec_model_24khz()` + `set_target_bandwidth(6.0)` +
+ * `remove_encodec_weight_norm` (data/tokenizer.py:63-88) and `AudioTokenizer.encode` / `tokenize_audio`
+ * (data/tokenizer.py:98-111) as called by `make_prompt` (utils/prompt_making.py:57-84).  Its own handle, like the
+ * reference's separate `codec` global (utils/generation.py:41-45,86-87).  sm_100 devices only; no CPU fallback. */
+typedef struct vx_encodec vx_encodec;
+VX_API int vx_encodec_create(int device, vx_encodec** out);
+VX_API void vx_encodec_destroy(vx_encodec* e);
+/* `key` is a key of the `encodec` package's `EncodecModel.state_dict()`: `encoder.model.<i>...conv.conv.{weight,bias}` (or
+ * `weight_g` + `weight_v` when weight norm was not removed), `encoder.model.13.lstm.{weight,bias}_{ih,hh}_l{0,1}`,
+ * `quantizer.vq.layers.<q>._codebook.embed` [1024,128] for q = 0.. (at least the 8 tables of 6 kbps).  Host fp32, row-major.
+ * Decoder keys are not on this path and are rejected by the Python mirror, not here.  vx_encodec_finalize is strict: every
+ * encoder tensor present with the right shape. */
+VX_API int vx_encodec_load_weight(vx_encodec* e, const char* key, const float* data, const int64_t* shape, int ndim);
+VX_API int vx_encodec_finalize(vx_encodec* e);
+VX_API int vx_encodec_num_codebooks(vx_encodec* e);
+/* T for an n-sample waveform: ceil at each of the four strided convolutions (2, 4, 5, 8) = the length of `encode`'s codes. */
+VX_API int64_t vx_encodec_frames(int64_t n_samples);
+/* Replaces: `codec.encode(wav)` for ONE mono 24 kHz waveform (the reference passes [1,1,N], data/tokenizer.py:104-110;
+ * `segment=None` and `normalize=False` for this model, so there is one frame and no scale).  wav [n_samples] fp32;
+ * n_q codebooks (8 at the reference's 6 kbps); out_codes [n_q, T] int32, T = vx_encodec_frames(n_samples).
+ * Non-finite samples -> VX_ERR_ARG. */
+VX_API int vx_encodec_encode(vx_encodec* e, const float* wav, int64_t n_samples, int n_q, int32_t* out_codes, int mem, void* stream);
+/* parity hooks: the encoder output [128, T] of the last vx_encodec_encode (host fp32); its CUDA-event time, frames, launches */
+VX_API int vx_encodec_embeddings(vx_encodec* e, float* dst, int64_t max_elems, int64_t* out_elems);
+VX_API int vx_encodec_last_timing(vx_encodec* e, float* ms, int64_t* frames, int64_t* kernel_launches);
+
 /* Measurement hooks (bench.py): CUDA-event durations (ms) of the last prefill / decode / nar / vocos
  * call on the engine's stream, the number of decode steps and kernels launched by the last call, and
  * debug access to device-side intermediates for the layer-by-layer parity tests. */

@@ -1,0 +1,179 @@
+"""EnCodec encoder + RVQ (reference data/tokenizer.py:63-111, utils/prompt_making.py:57-84).
+
+CPU: oracle/encodec_oracle.py reproduces the codes transformers' EncodecModel (an independent port of the `encodec` package,
+which cannot be installed here) produced on the same seeded weights and waveforms (tests/golden/make_encodec_golden.py), and
+is checked live against transformers when it is importable.
+GPU: the sm_100a path behind the C ABI (`vx_encodec_*`, through the `AudioTokenizer` mirror) reproduces those codes.  Integer
+bar: every code equal, except decisions whose reference top-1/top-2 distance gap is below MARGIN (fp32 reassociation of a
+~45 GFLOP encoder); after such a flip the deeper levels of that frame quantise a different residual and are not compared.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from oracle.encodec_oracle import OracleEncodec, n_q_for_bandwidth
+from vallex_b200.weights import synthetic_encodec_state_dict
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+CASES = ["encodec_tiny", "encodec_short", "encodec_3s", "encodec_ragged"]
+MARGIN = 2e-3
+
+
+def _load(name):
+    return dict(np.load(os.path.join(GOLD, name + ".npz")))
+
+
+def compare_codes(got, want, margins):
+    """got / want [n_q, T]; returns (number of exact frames, list of (q, t, margin) first flips)."""
+    flips = []
+    for t in range(want.shape[1]):
+        for q in range(want.shape[0]):
+            if got[q, t] != want[q, t]:
+                flips.append((q, t, float(margins[q, t])))
+                break
+    return want.shape[1] - len(flips), flips
+
+
+def test_bandwidth_to_codebooks():
+    assert n_q_for_bandwidth(6.0) == 8 and n_q_for_bandwidth(1.5) == 2 and n_q_for_bandwidth(24.0) == 32
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_reproduces_transformers_codes(name):
+    g = _load(name)
+    ora = OracleEncodec(synthetic_encodec_state_dict(int(g["seed"])))
+    wav = torch.from_numpy(g["wav"]).view(1, 1, -1)
+    emb = ora.encoder(wav)
+    assert emb.shape == (1, 128, g["codes"].shape[-1])
+    np.testing.assert_allclose(emb.mean(dim=2).numpy(), g["emb_mean"], atol=2e-5)
+    np.testing.assert_allclose(emb[0, :, :4].numpy(), g["emb_head"][:, : emb.shape[-1]], atol=1e-4)
+    codes = ora.encode(wav)[0][0].numpy()
+    assert np.array_equal(codes, g["codes"].astype(np.int64))
+
+
+def test_oracle_live_against_transformers():
+    pytest.importorskip("transformers")
+    import sys
+    sys.path.insert(0, GOLD)
+    from make_encodec_golden import hf_model, synth_wave
+    sd = synthetic_encodec_state_dict(1)
+    model = hf_model(sd)
+    wav = torch.from_numpy(synth_wave(np.random.default_rng(11), 9001)).view(1, 1, -1)
+    with torch.no_grad():
+        want = model.encode(wav, bandwidth=6.0).audio_codes[0]
+    got = OracleEncodec(sd).encode(wav)[0][0]
+    assert torch.equal(got, want)
+
+
+def test_oracle_weight_norm_form():
+    """weight_g / weight_v (checkpoint before `remove_encodec_weight_norm`) gives the same codes as the folded weight."""
+    sd = synthetic_encodec_state_dict(0)
+    wn = {}
+    for k, v in sd.items():
+        if k.endswith(".conv.conv.weight"):
+            wn[k[:-6] + "weight_g"] = v.flatten(1).norm(dim=1).view(-1, 1, 1)
+            wn[k[:-6] + "weight_v"] = v * 3.0          # any positive rescale of v cancels
+        else:
+            wn[k] = v
+    wav = torch.from_numpy(_load("encodec_tiny")["wav"]).view(1, 1, -1)
+    assert torch.equal(OracleEncodec(wn).encode(wav)[0][0], OracleEncodec(sd).encode(wav)[0][0])
+
+
+# ---------------------------------------------------------------- GPU ----
+@pytest.fixture(scope="module")
+def tok():
+    from vallex_b200.tokenizer import AudioTokenizer
+    t = AudioTokenizer("cuda:0", state_dict=synthetic_encodec_state_dict(0))
+    yield t
+    t.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_gpu_codes_match_reference_port(tok, name):
+    g = _load(name)
+    wav = torch.from_numpy(g["wav"]).view(1, 1, -1)
+    out = tok.encode(wav)
+    assert len(out) == 1 and out[0][1] is None
+    codes = out[0][0]
+    assert codes.dtype == torch.int64 and tuple(codes.shape) == (1, 8, g["codes"].shape[-1])
+    exact, flips = compare_codes(codes[0].cpu().numpy(), g["codes"][0].astype(np.int64), g["margins"][0])
+    print(f"{name}: {exact}/{g['codes'].shape[-1]} frames exact, flips {flips}")
+    assert all(m < MARGIN for _, _, m in flips), flips
+    assert len(flips) <= max(1, g["codes"].shape[-1] // 50)
+    emb = tok.embeddings()
+    np.testing.assert_allclose(emb.mean(dim=1).numpy(), g["emb_mean"][0], atol=5e-5)
+    np.testing.assert_allclose(emb[:, :4].numpy(), g["emb_head"][:, : emb.shape[-1]], atol=2e-4)
+
+
+@pytest.mark.gpu
+def test_gpu_encoder_against_oracle_15s(tok):
+    """The reference's longest prompt (15 s, utils/prompt_making.py:60-62): embeddings against the oracle, codes by the margin rule."""
+    import sys
+    sys.path.insert(0, GOLD)
+    from make_encodec_golden import synth_wave
+    wav = torch.from_numpy(synth_wave(np.random.default_rng(5), 15 * 24000)).view(1, 1, -1)
+    ora = OracleEncodec(synthetic_encodec_state_dict(0))
+    emb_o = ora.encoder(wav)
+    want, margins = ora.quantize(emb_o, return_margins=True)
+    got = tok.encode(wav)[0][0][0].cpu().numpy()
+    emb = tok.embeddings()
+    assert emb.shape == (128, 1125)
+    err = float((emb - emb_o[0]).abs().max())
+    exact, flips = compare_codes(got, want[0].numpy(), margins[0].numpy())
+    print(f"15 s: max |emb - oracle| {err:.3e}; {exact}/1125 frames exact; flips {flips}; {tok.last_timing()}")
+    assert err < 5e-4
+    assert all(m < MARGIN for _, _, m in flips) and len(flips) <= 20
+
+
+@pytest.mark.gpu
+def test_gpu_weight_norm_and_errors(tok):
+    from vallex_b200._capi import VallexB200Error
+    from vallex_b200.tokenizer import AudioTokenizer
+    sd = synthetic_encodec_state_dict(0)
+    wn = {}
+    for k, v in sd.items():
+        if k.endswith(".conv.conv.weight"):
+            wn[k[:-6] + "weight_g"] = v.flatten(1).norm(dim=1).view(-1, 1, 1)
+            wn[k[:-6] + "weight_v"] = v * 0.5
+        else:
+            wn[k] = v
+    g = _load("encodec_tiny")
+    wav = torch.from_numpy(g["wav"]).view(1, 1, -1)
+    t2 = AudioTokenizer("cuda:0", state_dict=wn)
+    assert torch.equal(t2.encode(wav)[0][0], tok.encode(wav)[0][0])
+    t2.close()
+    bad = dict(sd)
+    del bad["encoder.model.13.lstm.weight_hh_l1"]
+    with pytest.raises(VallexB200Error):
+        AudioTokenizer("cuda:0", state_dict=bad)
+    with pytest.raises(ValueError):
+        tok.encode(torch.zeros(1, 2, 100))
+    nan = wav.clone()
+    nan[0, 0, 3] = float("nan")
+    with pytest.raises(VallexB200Error):
+        tok.encode(nan)
+
+
+@pytest.mark.gpu
+def test_gpu_make_prompt_npz(tok, tmp_path):
+    """make_prompt writes the npz `generate_audio(prompt=...)` reads (utils/prompt_making.py:57-84, utils/generation.py:103-123)."""
+    from vallex_b200 import generation, prompt_making
+    prompt_making.codec = tok
+    g = _load("encodec_3s")
+    wav = torch.from_numpy(g["wav"]).view(1, -1)
+    stereo_48k = torch.cat([wav, wav], dim=0)          # stereo -> mono mean is the identity here; same rate: no resampling
+    path = prompt_making.make_prompt("unit", (stereo_48k, 24000), transcript=([5, 6, 7, 8], "en"), save_dir=str(tmp_path))
+    d = np.load(path)
+    assert d["audio_tokens"].shape == (1, 225, 8) and d["audio_tokens"].dtype == np.int64
+    assert d["text_tokens"].tolist() == [[5, 6, 7, 8]] and int(d["lang_code"]) == 2
+    exact, flips = compare_codes(d["audio_tokens"][0].T, g["codes"][0].astype(np.int64), g["margins"][0])
+    assert all(m < MARGIN for _, _, m in flips)
+    audio_prompts, text_prompts, lang_pr = generation._load_prompt(path)
+    assert tuple(audio_prompts.shape) == (1, 225, 8) and lang_pr == "en"
+    with pytest.raises(ValueError):
+        prompt_making.make_prompt("long", (torch.zeros(1, 16 * 24000), 24000), transcript=([5], "en"), save_dir=str(tmp_path))
+    prompt_making.codec = None

@@ -25,6 +25,9 @@ int fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
 }
+}  // namespace
+int vx_fail(int code, const std::string& msg) { return fail(code, msg); }  // for the other translation units (encodec.cu)
+namespace {
 #define CK(call)                                                                                   \
   do {                                                                                             \
     cudaError_t _e = (call);                                                                       \

@@ -44,6 +44,15 @@ SIGNATURES = {
     "vx_debug_gemm_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int]),
     "vx_debug_attn_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "vx_debug_attn_t5": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "vx_encodec_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "vx_encodec_destroy": (None, [C.c_void_p]),
+    "vx_encodec_load_weight": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int]),
+    "vx_encodec_finalize": (C.c_int, [C.c_void_p]),
+    "vx_encodec_num_codebooks": (C.c_int, [C.c_void_p]),
+    "vx_encodec_frames": (C.c_int64, [C.c_int64]),
+    "vx_encodec_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "vx_encodec_embeddings": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "vx_encodec_last_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
 }
 
 

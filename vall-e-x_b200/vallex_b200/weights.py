@@ -132,6 +132,51 @@ def synthetic_vocos_state_dict(seed: int = 0) -> "OrderedDict[str, torch.Tensor]
     return sd
 
 
+# ---- EnCodec 24 kHz encoder + RVQ (reference data/tokenizer.py:63-111) ----
+# Key layout of `encodec.EncodecModel.encodec_model_24khz().state_dict()` after the reference's
+# `remove_encodec_weight_norm` (data/tokenizer.py:31-60): `encoder.model.<i>` is the SEANet nn.Sequential
+# (conv, 4 x [resnet block, ELU, strided conv], LSTM, ELU, conv), `quantizer.vq.layers.<q>._codebook.embed` the RVQ tables.
+# The `encodec` package is third party and not installed here: names follow its public source layout (from memory);
+# the architecture is cross-checked against transformers' port of the same model (tests/golden/make_encodec_golden.py).
+ENCODEC_RATIOS = (2, 4, 5, 8)  # encoder order = reversed SEANet `ratios` [8,5,4,2]
+ENCODEC_FILTERS = 32
+ENCODEC_DIM = 128
+ENCODEC_CODEBOOKS = 32  # 24 kbps table; 6 kbps (data/tokenizer.py:71) uses the first 8
+ENCODEC_BINS = 1024
+
+
+def encodec_conv_specs():
+    """(state-dict prefix, C_out, C_in, kernel, stride, dilation) of every encoder convolution, in execution order;
+    resnet blocks contribute (block.1 k3, block.3 k1, shortcut k1)."""
+    specs = [("encoder.model.0.conv.conv", ENCODEC_FILTERS, 1, 7, 1, 1)]
+    dim, idx = ENCODEC_FILTERS, 1
+    for r in ENCODEC_RATIOS:
+        specs.append((f"encoder.model.{idx}.block.1.conv.conv", dim // 2, dim, 3, 1, 1))
+        specs.append((f"encoder.model.{idx}.block.3.conv.conv", dim, dim // 2, 1, 1, 1))
+        specs.append((f"encoder.model.{idx}.shortcut.conv.conv", dim, dim, 1, 1, 1))
+        specs.append((f"encoder.model.{idx + 2}.conv.conv", 2 * dim, dim, 2 * r, r, 1))
+        dim, idx = 2 * dim, idx + 3
+    specs.append((f"encoder.model.{idx + 2}.conv.conv", ENCODEC_DIM, dim, 7, 1, 1))  # idx = 13 is the LSTM
+    return specs
+
+
+def synthetic_encodec_state_dict(seed: int = 0, codebooks: int = 8) -> "OrderedDict[str, torch.Tensor]":
+    g = torch.Generator(device="cpu")
+    g.manual_seed(9000011 * (seed + 1))
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for prefix, co, ci, k, _s, _d in encodec_conv_specs():
+        sd[f"{prefix}.weight"] = _normal(g, (co, ci, k), math.sqrt(2.0 / (ci * k)))
+        sd[f"{prefix}.bias"] = _uniform(g, (co,), 1.0 / math.sqrt(ci * k))
+    h = ENCODEC_FILTERS * 16
+    for layer in range(2):
+        for n, shape in (("weight_ih", (4 * h, h)), ("weight_hh", (4 * h, h)), ("bias_ih", (4 * h,)), ("bias_hh", (4 * h,))):
+            sd[f"encoder.model.13.lstm.{n}_l{layer}"] = _uniform(g, shape, 1.0 / math.sqrt(h))
+    for q in range(codebooks):
+        # residuals shrink level by level in a trained RVQ; mimic that so deep levels are exercised at small magnitudes
+        sd[f"quantizer.vq.layers.{q}._codebook.embed"] = _normal(g, (ENCODEC_BINS, ENCODEC_DIM), 0.6 * 0.8 ** q)
+    return sd
+
+
 _EXPECTED = None
 
 
