@@ -177,3 +177,31 @@ def test_gpu_make_prompt_npz(tok, tmp_path):
     with pytest.raises(ValueError):
         prompt_making.make_prompt("long", (torch.zeros(1, 16 * 24000), 24000), transcript=([5], "en"), save_dir=str(tmp_path))
     prompt_making.codec = None
+
+
+@pytest.mark.gpu
+def test_gpu_real_encodec_package_if_present():
+    """SURVEY 8(f1) for this row: where the `encodec` package and its checkpoint are reachable (ENCODEC_B200_WEIGHTS or
+    ./checkpoints/encodec_24khz-d7cc33bc.th), pin the engine against the package the reference actually calls
+    (data/tokenizer.py:69-72: encodec_model_24khz, 6 kbps, weight norm removed)."""
+    encodec_pkg = pytest.importorskip("encodec")
+    path = os.environ.get("ENCODEC_B200_WEIGHTS", "./checkpoints/encodec_24khz-d7cc33bc.th")
+    if not os.path.isfile(path):
+        pytest.skip("real EnCodec weights not present")
+    import sys
+    sys.path.insert(0, GOLD)
+    from make_encodec_golden import synth_wave
+    from vallex_b200.tokenizer import AudioTokenizer
+    model = encodec_pkg.EncodecModel.encodec_model_24khz(pretrained=False)
+    sd = torch.load(path, map_location="cpu")
+    model.load_state_dict(sd)
+    model.set_target_bandwidth(6.0)
+    model.eval()
+    wav = torch.from_numpy(synth_wave(np.random.default_rng(9), 5 * 24000)).view(1, 1, -1)
+    with torch.no_grad():
+        want = model.encode(wav)[0][0]
+    t = AudioTokenizer("cuda:0", state_dict=sd)
+    got = t.encode(wav)[0][0].cpu()
+    t.close()
+    assert got.shape == want.shape
+    assert float((got[:, 0] == want[:, 0]).float().mean()) > 0.99      # first level; deeper levels follow any flip

@@ -61,7 +61,7 @@ void launch_pack_qkv_heads(const void* qkv_bf16, int64_t R, void* q_img, void* k
 
 // shared memory: Q 16 KB | K ring 3 x 8 KB | V^T ring 4 x 8 KB | P 2 x 16 KB | row stats 2 KB | barriers
 constexpr int T5_Q = 0, T5_K = 16384, T5_V = T5_K + 3 * 8192, T5_P = T5_V + 4 * 8192, T5_ST = T5_P + 2 * 16384,
-              T5_BAR = T5_ST + 2048, T5_BYTES = T5_BAR + 128;
+              T5_BAR = T5_ST + 2048, T5_BYTES = T5_BAR + 256;
 
 __device__ __forceinline__ float t5_ex2(float x) {  // single MUFU.EX2; ex2(-inf) = 0
   float y;
@@ -71,6 +71,24 @@ __device__ __forceinline__ float t5_ex2(float x) {  // single MUFU.EX2; ex2(-inf
 __device__ __forceinline__ uint32_t t5_pack(float a, float b) {  // cvt.rn.bf16x2.f32, low half = a
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+
+// packed fp32 pairs (sm_100: FFMA2 / FADD2 take two fp32 lanes of a 64-bit register per instruction)
+__device__ __forceinline__ uint64_t t5_pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void t5_unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t t5_fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t t5_add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
 
@@ -121,8 +139,9 @@ __global__ void __launch_bounds__(288, 2) attn_t5_kernel(Batch bt, const uint8_t
   uint64_t* vfull = bars + 4;    // [4]
   uint64_t* sfull = bars + 8;    // [2]
   uint64_t* pvdone = bars + 10;  // [2]
-  uint64_t* pfull = bars + 12;   // [2]  all 256 threads have written their part of P_j (and consumed S_j)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* pfull = bars + 12;   // [2]  all 8 softmax warps have written their part of P_j
+  uint64_t* sread = bars + 14;   // [2]  all 8 softmax warps hold S_j in registers: its TMEM buffer may be overwritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 128;
   const int S = bt.S[b];
@@ -144,7 +163,7 @@ __global__ void __launch_bounds__(288, 2) attn_t5_kernel(Batch bt, const uint8_t
     mbar_init(qbar, 1);
     for (int i = 0; i < 3; ++i) mbar_init(&kfull[i], 1);
     for (int i = 0; i < 4; ++i) mbar_init(&vfull[i], 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&sfull[i], 1); mbar_init(&pvdone[i], 1); mbar_init(&pfull[i], 256); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sfull[i], 1); mbar_init(&pvdone[i], 1); mbar_init(&pfull[i], 8); mbar_init(&sread[i], 8); }
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<256>(tmem_slot);
@@ -212,12 +231,20 @@ __global__ void __launch_bounds__(288, 2) attn_t5_kernel(Batch bt, const uint8_t
       wait_k(0);
       mma_s(0);
       if (nkt > 1) { wait_k(1); mma_s(1); }
+      uint32_t srph = 0;
       for (int j = 0; j < nkt; ++j) {
-        wait_s(j & 1);
-        if (j + 3 < nkt) issue_k(j + 3);               // S_j is complete: its K slot is free
+        // Q K^T of tile j+2 goes out as soon as every softmax warp holds S_j in registers (early in tile j's softmax), not after
+        // P_j is complete: in the previous order the softmax warps spent 20 % of their samples waiting for S (profiles/r02_prof_attn_b8.md)
+        if (j + 2 < nkt) {
+          mbar_wait(&sread[j & 1], (srph >> (j & 1)) & 1);
+          srph ^= 1u << (j & 1);
+          if (j + 3 < nkt) issue_k(j + 3);             // S_j was read, so its MMA is complete: K slot j % 3 is free
+          wait_k((j + 2) % 3);
+          mma_s(j + 2);
+        }
         ensure_pv(j - 2);                              // O += P_{j-2} V_{j-2} done: V slot (j-2)&3 is free
         if (j + 2 < nkt) issue_v(j + 2);
-        mbar_wait(&pfull[j & 1], (pfph >> (j & 1)) & 1);   // every thread's part of P_j is in place, S_j is consumed, rescales are done
+        mbar_wait(&pfull[j & 1], (pfph >> (j & 1)) & 1);   // every warp's part of P_j is in place, rescales are done
         pfph ^= 1u << (j & 1);
         mbar_wait(&vfull[j & 3], (vph >> (j & 3)) & 1);
         vph ^= 1u << (j & 3);
@@ -227,10 +254,6 @@ __global__ void __launch_bounds__(288, 2) attn_t5_kernel(Batch bt, const uint8_t
         for (int ks = 0; ks < 4; ++ks)    // keys 0-31 of the tile accumulate into O_a, keys 32-63 into O_b
           umma_bf16(ks < 2 ? tOa : tOb, ad + 2 * ks, bd + 2 * ks, idesc, (j | (ks & 1)) ? 1u : 0u);
         umma_commit(&pvdone[j & 1]);
-        if (j + 2 < nkt) {                // S buffer j&1 is free: Q K^T of tile j+2 runs under the softmax of tile j+1
-          wait_k((j + 2) % 3);
-          mma_s(j + 2);
-        }
       }
     }
   } else {
@@ -239,6 +262,9 @@ __global__ void __launch_bounds__(288, 2) attn_t5_kernel(Batch bt, const uint8_t
       tc_fence_after();
       float v[32];
       tmem_ld32(tmem + (j & 1) * 64 + lane_addr + half * 32, v);
+      tc_fence_before();                  // this warp's TMEM read of S_j is ordered before the arrival that lets S_{j+2} overwrite it
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sread[j & 1]);
       const int kb = j * 64 + half * 32;
       float mx = -INFINITY;
       if (tile_full(j)) {
@@ -272,23 +298,36 @@ __global__ void __launch_bounds__(288, 2) attn_t5_kernel(Batch bt, const uint8_t
         }
       }
       uint32_t pk[16];
-      float ls = 0.f;
       const float mu = (m_used == -INFINITY) ? 0.f : m_used;   // a half that has seen no visible key yet: every P is ex2(-inf) = 0
+      // packed fp32 pairs (FFMA2 / FADD2): half the scale-and-shift and row-sum instructions; two independent sum chains
+      const uint64_t sl2x2 = t5_pack2(sl2, sl2), nmux2 = t5_pack2(-mu, -mu);
+      uint64_t ls_a = 0ull, ls_b = 0ull;    // (+0, +0)
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        const float p0 = t5_ex2(fmaf(v[i], sl2, -mu)), p1 = t5_ex2(fmaf(v[i + 1], sl2, -mu));   // masked: ex2(-inf) = 0
-        ls += p0 + p1;
+      for (int i = 0; i < 32; i += 4) {
+        float a0, a1, b0, b1;
+        t5_unpack2(t5_fma2(t5_pack2(v[i], v[i + 1]), sl2x2, nmux2), a0, a1);
+        t5_unpack2(t5_fma2(t5_pack2(v[i + 2], v[i + 3]), sl2x2, nmux2), b0, b1);
+        const float p0 = t5_ex2(a0), p1 = t5_ex2(a1), p2 = t5_ex2(b0), p3 = t5_ex2(b1);   // masked: ex2(-inf) = 0
+        ls_a = t5_add2(ls_a, t5_pack2(p0, p1));
+        ls_b = t5_add2(ls_b, t5_pack2(p2, p3));
         pk[i >> 1] = t5_pack(p0, p1);
+        pk[(i >> 1) + 1] = t5_pack(p2, p3);
       }
-      l_part += ls;
+      {
+        float s0, s1, s2, s3;
+        t5_unpack2(ls_a, s0, s1);
+        t5_unpack2(ls_b, s2, s3);
+        l_part += (s0 + s1) + (s2 + s3);
+      }
       ensure_pv(j - 2);                   // O += P_{j-2} V_{j-2} done: P buffer j&1 is free
       uint8_t* prow = sP + (j & 1) * 16384 + rloc * 128;
 #pragma unroll
       for (int q = 0; q < 4; ++q)
         *reinterpret_cast<uint4*>(prow + (((half * 4 + q) ^ (rloc & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
       fence_proxy_async();                // P was written through the generic proxy, the MMA reads it through the async proxy
-      tc_fence_before();                  // ... and this thread's TMEM reads of S_j / writes of O_h are ordered before the arrival
-      mbar_arrive(&pfull[j & 1]);
+      tc_fence_before();                  // ... and this thread's TMEM writes of O_h (rescale) are ordered before the arrival
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pfull[j & 1]);
     }
     ensure_pv(nkt - 1);
   }

@@ -7,7 +7,7 @@
 //              (TMA engine) through a kStages-deep mbarrier ring;
 //   warp 1   : allocates TMEM; one elected lane issues tcgen05.mma (M=128, N=BN, K=16; 4 per 64-wide k block),
 //              tcgen05.commit frees each ring slot and publishes a finished accumulator;
-//   warps 2-5: epilogue -- tcgen05.ld the 128 x BN fp32 accumulator (double-buffered in TMEM, so the next tile's
+//   warps 2-9: epilogue (two per TMEM lane quarter, half the columns each) -- tcgen05.ld the 128 x BN fp32 accumulator (double-buffered in TMEM, so the next tile's
 //              MMAs overlap), add bias / ReLU / residual, store bf16 row-major, bf16 tile image or fp32.
 // Bound: tensor pipe (dense bf16).  Tiles are walked m-fastest so CTAs running concurrently share the same
 // weight blocks through L2.  modules/activation.py:144,166; modules/transformer.py:371-373; models/vallex.py:677.
@@ -29,16 +29,23 @@ struct TcCfg {
   static constexpr int kBBytes = kBlockBytes * (BN / 128);
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 256 /*barriers*/ + 8 * 4096 /*epilogue staging, 4 KB per warp*/;
 };
 
+// 8 epilogue warps: two per TMEM lane quarter, each owning half of the tile's columns.  With 4 warps (round 1/2) a K = 1024 tile's
+// epilogue (a 128 x 256 fp32 read-modify-write through 128 threads, one dependent L2/HBM round trip per 32-column chunk) took ~16 us
+// against 4.3 us of MMAs -- the out-proj GEMM ran at 26 % tensor-pipe activity (profiles/r02_prof_gemm_b8.md).
+constexpr int kEpiWarps = 8;
+constexpr int kTcThreads = 64 + 32 * kEpiWarps;
+
 template <int BN, int EPI>
-__global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const bf16* __restrict__ A, const bf16* __restrict__ W,
+__global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const bf16* __restrict__ A, const bf16* __restrict__ W,
                                                          const float* __restrict__ bias, void* __restrict__ out,
                                                          int64_t ldc, int64_t M, int N, int K, const float* __restrict__ aux) {
   using Cfg = TcCfg<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();   // the swizzled operand stages need 1024-byte alignment
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
   uint64_t* empty = full + Cfg::kStages;
   uint64_t* tfull = empty + Cfg::kStages;
@@ -53,7 +60,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const bf16* __restrict_
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -112,141 +119,163 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const bf16* __restrict_
       }
     }
   } else {
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ---- epilogue: TMEM -> registers -> (shared-memory transpose) -> global -------------------------------------------------
+    // tcgen05.ld hands a thread ONE accumulator row (32 consecutive columns per chunk), so direct stores put every lane of a
+    // warp on a different 128-byte line: 32 L1 wavefronts per instruction.  Measured (profiles/r02_prof_gemm_b8.md): the fp32
+    // read-modify-write of a 128 x 256 tile cost ~16 us against 4.3 us of MMAs (out-proj at 26 % tensor activity, no gain from
+    // doubling the epilogue warps: the LSU, not latency, was the limit) and the 2-byte V^T scatter ~17 us per tile.  Each warp
+    // therefore stages its 32 x 32 chunk in a swizzled 4 KB buffer and re-reads it so that 8 (fp32) or 4 (bf16) lanes cover one
+    // row: every global instruction touches 4-8 full lines.
+    const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    const int chalf = (warp - 2) >> 2;             // which half of the tile's columns this warp owns
+    constexpr int kChunks = BN / 2 / 32;           // 32-column chunks per warp
+    float* stg = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256) + (warp - 2) * 1024;
+    constexpr bool kRes = (EPI == TC_F32_RESIDUAL || EPI == TC_F32_SCALE_RESIDUAL);
+    constexpr bool kF32Out = kRes || EPI == TC_F32;
+    const int c4 = lane & 7, r4 = lane >> 3;       // fp32 outputs: lane = (row r4 + 4 i, columns 4 c4 .. +3)
+    const int c8 = lane & 3, r8 = lane >> 2;       // bf16 outputs: lane = (row r8 + 8 i, columns 8 c8 .. +7)
+    auto pk = [](float a, float b) {
+      return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(b)) << 16);
+    };
     uint32_t acc_phase[2] = {0, 0};
     int it = 0;
     for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
       const int mt = t % m_tiles, nt = t / m_tiles;
+      const int64_t wrow0 = (int64_t)mt * 128 + q * 32;    // first row of this warp's 32
+      const int cbase = chalf * (BN / 2);
+      // residual epilogues: the first chunks of the warp's fp32 residual slice are requested BEFORE waiting for the accumulator,
+      // the rest two chunks ahead (profiles/r01_prof_gemm.md: 54 % of the epilogue warps' stall samples were these loads)
+      float4 rA[8], rB[8];     // residual of the chunk being folded / of the next one; chunk cc + 2 is requested when cc is done
+      if constexpr (kRes) {
+        const float* o = reinterpret_cast<const float*>(out) + nt * BN + cbase + c4 * 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (wrow0 + r4 + 4 * i < M) {
+            rA[i] = *reinterpret_cast<const float4*>(o + (wrow0 + r4 + 4 * i) * ldc);
+            if (kChunks > 1) rB[i] = *reinterpret_cast<const float4*>(o + (wrow0 + r4 + 4 * i) * ldc + 32);
+          }
+      }
       mbar_wait(&tfull[acc], acc_phase[acc]);
       acc_phase[acc] ^= 1;
       tc_fence_after();
-      const int64_t row = (int64_t)mt * 128 + q * 32 + lane;
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
-      // residual epilogues: the fp32 residual chunk of the NEXT 32 columns is requested before this chunk's accumulator is
-      // read, so the read-modify-write does not sit behind a fresh HBM/L2 round trip per chunk (54 % of the epilogue warps'
-      // stall samples were these loads, profiles/r01_prof_gemm.md)
-      constexpr bool kRes = (EPI == TC_F32_RESIDUAL || EPI == TC_F32_SCALE_RESIDUAL);
-      float4 rnext[8];
-      if constexpr (kRes) {
-        if (row < M) {
-          const float* o = reinterpret_cast<const float*>(out) + row * ldc + nt * BN;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) rnext[i] = *reinterpret_cast<const float4*>(o + 4 * i);
-        }
-      }
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        float v[32];
-        float4 rcur[8];
-        if constexpr (kRes) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) rcur[i] = rnext[i];
-          if (row < M && c0 + 32 < BN) {
-            const float* o = reinterpret_cast<const float*>(out) + row * ldc + nt * BN + c0 + 32;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) rnext[i] = *reinterpret_cast<const float4*>(o + 4 * i);
-          }
-        }
-        tmem_ld32(taddr + c0, v);
+      for (int cc = 0; cc < kChunks; ++cc) {
+        const int c0 = cbase + cc * 32;
         const int n0 = nt * BN + c0;
-        if (bias) {
+        float v[32];
+        tmem_ld32(taddr + c0, v);
+        // stage: row `lane`, 16-byte chunk c at position c ^ (lane & 7) (conflict-free for the row-wise write and both read maps)
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += __ldg(bias + n0 + i);
-        }
-        if (row < M) {
-          if constexpr (EPI == TC_BF16_ROW) {
-            bf16* o = reinterpret_cast<bf16*>(out) + row * ldc + n0;
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<float4*>(stg + lane * 32 + ((c ^ (lane & 7)) << 2)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        __syncwarp();
+        if constexpr (kF32Out) {
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c4 * 4));
+          float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+          if constexpr (EPI == TC_F32_SCALE_RESIDUAL) g4 = __ldg(reinterpret_cast<const float4*>(aux + n0 + c4 * 4));
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              uint4 p;
-              p.x = __bfloat16_as_ushort(__float2bfloat16_rn(v[i])) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[i + 1])) << 16);
-              p.y = __bfloat16_as_ushort(__float2bfloat16_rn(v[i + 2])) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[i + 3])) << 16);
-              p.z = __bfloat16_as_ushort(__float2bfloat16_rn(v[i + 4])) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[i + 5])) << 16);
-              p.w = __bfloat16_as_ushort(__float2bfloat16_rn(v[i + 6])) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[i + 7])) << 16);
-              *reinterpret_cast<uint4*>(o + i) = p;
-            }
-          } else if constexpr (EPI == TC_BF16_IMAGE_RELU) {
-            uint8_t* img = reinterpret_cast<uint8_t*>(out);
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              uint4 p;
-              auto pk = [](float a, float b) {
-                return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(fmaxf(a, 0.f))) |
-                       ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(fmaxf(b, 0.f))) << 16);
-              };
-              p.x = pk(v[i], v[i + 1]); p.y = pk(v[i + 2], v[i + 3]); p.z = pk(v[i + 4], v[i + 5]); p.w = pk(v[i + 6], v[i + 7]);
-              *reinterpret_cast<uint4*>(img + tile_image_offset(row, n0 + i, N)) = p;
-            }
-          } else if constexpr (EPI == TC_QKV_HEADS) {
-            // N = 3 x 1024: columns n0..n0+31 belong to q|k|v `which`, head h, dims d0..d0+31.  q and k: per-head K-major tile
-            // images [R,64]; v: transposed per 64-key block, [64 d rows x 64 keys] (the B operand of P V) -- same layouts as
-            // pack_qkv_heads_kernel (attention_t5.cu), written straight from the accumulator.  ldc = R (multiple of 128).
-            const int which = n0 / kD, hc = n0 % kD, h = hc >> 6, d0 = hc & 63;
-            uint8_t* base = reinterpret_cast<uint8_t*>(out) + (size_t)which * ((size_t)ldc * kD * 2);
-            auto pk = [](float a, float b) {
-              return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(b)) << 16);
-            };
-            if (which < 2) {
-              uint8_t* img = base + (size_t)h * ((size_t)ldc * 128);
-#pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                uint4 p;
-                p.x = pk(v[i], v[i + 1]); p.y = pk(v[i + 2], v[i + 3]); p.z = pk(v[i + 4], v[i + 5]); p.w = pk(v[i + 6], v[i + 7]);
-                *reinterpret_cast<uint4*>(img + tile_image_offset(row, d0 + i, 64)) = p;
+          for (int i = 0; i < 8; ++i) {
+            const int rr = r4 + 4 * i;
+            const int64_t row = wrow0 + rr;
+            float4 a = *reinterpret_cast<const float4*>(stg + rr * 32 + ((c4 ^ (rr & 7)) << 2));
+            a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
+            if (row < M) {
+              float* o = reinterpret_cast<float*>(out) + row * ldc + n0 + c4 * 4;
+              if constexpr (EPI == TC_F32_RESIDUAL) {
+                float4 r = rA[i];
+                r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w;
+                *reinterpret_cast<float4*>(o) = r;
+              } else if constexpr (EPI == TC_F32_SCALE_RESIDUAL) {   // Vocos pwconv2: x += gamma[n] * (acc + bias[n])
+                float4 r = rA[i];
+                r.x = fmaf(g4.x, a.x, r.x); r.y = fmaf(g4.y, a.y, r.y); r.z = fmaf(g4.z, a.z, r.z); r.w = fmaf(g4.w, a.w, r.w);
+                *reinterpret_cast<float4*>(o) = r;
+              } else {
+                *reinterpret_cast<float4*>(o) = a;
               }
-            } else {
+            }
+          }
+          if constexpr (kRes) {   // rotate: the next chunk's residual becomes current, chunk cc + 2 is requested
+            const float* o = reinterpret_cast<const float*>(out) + nt * BN + cbase + (cc + 2) * 32 + c4 * 4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              rA[i] = rB[i];
+              if (cc + 2 < kChunks && wrow0 + r4 + 4 * i < M) rB[i] = *reinterpret_cast<const float4*>(o + (wrow0 + r4 + 4 * i) * ldc);
+            }
+          }
+        } else if (EPI == TC_QKV_HEADS && n0 >= 2 * kD) {
+          // V columns: transposed per 64-key block, [64 d rows x 64 keys] K-major swizzled (the B operand of P V).  Lane = head
+          // dim d; 8 consecutive keys (rows of the chunk) form one 16-byte chunk of the block's row d.  ldc = R (multiple of 128).
+          const int hc = n0 % kD, h = hc >> 6, d = (hc & 63) + lane;
+          const float bd = bias ? __ldg(bias + n0 + lane) : 0.f;
+          uint8_t* base = reinterpret_cast<uint8_t*>(out) + (size_t)2 * ((size_t)ldc * kD * 2);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float e[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int rr = 8 * g + j;
+              e[j] = stg[rr * 32 + ((((lane >> 2) ^ (rr & 7))) << 2) + (lane & 3)] + bd;
+            }
+            const int64_t row = wrow0 + 8 * g;
+            if (row < M) {
               uint8_t* vb = base + ((size_t)h * (size_t)(ldc / 64) + (size_t)(row >> 6)) * 8192;
-              const int kc = (int)((row & 63) >> 3), kl = (int)(row & 7);
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const int d = d0 + i;
-                *reinterpret_cast<uint16_t*>(vb + d * 128 + ((kc ^ (d & 7)) << 4) + kl * 2) = __bfloat16_as_ushort(__float2bfloat16_rn(v[i]));
-              }
+              const int kc = (int)((row & 63) >> 3);
+              *reinterpret_cast<uint4*>(vb + d * 128 + ((kc ^ (d & 7)) << 4)) =
+                  make_uint4(pk(e[0], e[1]), pk(e[2], e[3]), pk(e[4], e[5]), pk(e[6], e[7]));
             }
-          } else if constexpr (EPI == TC_GELU_SPLIT3) {
-            // Vocos pwconv1: GELU(acc + bias) as the NEXT contraction's split-3 operand image [rows, 3N] = [hi | hi | lo]
-            // (bf16 x 3: a*b ~ a_hi*b_hi + a_hi*b_lo + a_lo*b_hi against the weight image [hi | lo | hi])
-            uint8_t* img = reinterpret_cast<uint8_t*>(out);
+          }
+        } else {
+          // bf16 outputs: lane = (row r8 + 8 i, columns 8 c8 .. +7): 16-byte stores, 4 lanes per row
+          float bb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (bias) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c8 * 8)), b1 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c8 * 8 + 4));
+            bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+          }
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
+          for (int i = 0; i < 4; ++i) {
+            const int rr = r8 + 8 * i;
+            const int64_t row = wrow0 + rr;
+            const float4 a0 = *reinterpret_cast<const float4*>(stg + rr * 32 + (((2 * c8) ^ (rr & 7)) << 2));
+            const float4 a1 = *reinterpret_cast<const float4*>(stg + rr * 32 + (((2 * c8 + 1) ^ (rr & 7)) << 2));
+            float y[8] = {a0.x + bb[0], a0.y + bb[1], a0.z + bb[2], a0.w + bb[3], a1.x + bb[4], a1.y + bb[5], a1.z + bb[6], a1.w + bb[7]};
+            if (row >= M) continue;
+            const int nc = n0 + c8 * 8;
+            if constexpr (EPI == TC_BF16_ROW) {
+              *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(out) + row * ldc + nc) = make_uint4(pk(y[0], y[1]), pk(y[2], y[3]), pk(y[4], y[5]), pk(y[6], y[7]));
+            } else if constexpr (EPI == TC_BF16_IMAGE_RELU) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) y[e] = fmaxf(y[e], 0.f);
+              *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out) + tile_image_offset(row, nc, N)) =
+                  make_uint4(pk(y[0], y[1]), pk(y[2], y[3]), pk(y[4], y[5]), pk(y[6], y[7]));
+            } else if constexpr (EPI == TC_QKV_HEADS) {
+              // q and k columns: per-head K-major tile images [R,64] (same layouts as pack_qkv_heads_kernel, attention_t5.cu)
+              const int which = nc / kD, hc = nc % kD, h = hc >> 6, d0 = hc & 63;
+              uint8_t* img = reinterpret_cast<uint8_t*>(out) + (size_t)which * ((size_t)ldc * kD * 2) + (size_t)h * ((size_t)ldc * 128);
+              *reinterpret_cast<uint4*>(img + tile_image_offset(row, d0, 64)) = make_uint4(pk(y[0], y[1]), pk(y[2], y[3]), pk(y[4], y[5]), pk(y[6], y[7]));
+            } else if constexpr (EPI == TC_GELU_SPLIT3) {
+              // Vocos pwconv1: GELU(acc + bias) as the NEXT contraction's split-3 operand image [rows, 3N] = [hi | hi | lo]
+              // (bf16 x 3: a*b ~ a_hi*b_hi + a_hi*b_lo + a_lo*b_hi against the weight image [hi | lo | hi])
               uint32_t hw[4], lw[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float x0 = tc_gelu_exact(v[i + 2 * e]), x1 = tc_gelu_exact(v[i + 2 * e + 1]);
+                const float x0 = tc_gelu_exact(y[2 * e]), x1 = tc_gelu_exact(y[2 * e + 1]);
                 const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
                 const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
                 hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
                 lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
               }
+              uint8_t* img = reinterpret_cast<uint8_t*>(out);
               const uint4 hp = make_uint4(hw[0], hw[1], hw[2], hw[3]), lp = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-              *reinterpret_cast<uint4*>(img + tile_image_offset(row, n0 + i, 3 * N)) = hp;
-              *reinterpret_cast<uint4*>(img + tile_image_offset(row, N + n0 + i, 3 * N)) = hp;
-              *reinterpret_cast<uint4*>(img + tile_image_offset(row, 2 * N + n0 + i, 3 * N)) = lp;
+              *reinterpret_cast<uint4*>(img + tile_image_offset(row, nc, 3 * N)) = hp;
+              *reinterpret_cast<uint4*>(img + tile_image_offset(row, N + nc, 3 * N)) = hp;
+              *reinterpret_cast<uint4*>(img + tile_image_offset(row, 2 * N + nc, 3 * N)) = lp;
             }
-          } else if constexpr (EPI == TC_F32_SCALE_RESIDUAL) {
-            float* o = reinterpret_cast<float*>(out) + row * ldc + n0;   // Vocos pwconv2: x += gamma[n] * (acc + bias[n])
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              float4 r = rcur[i >> 2];
-              const float4 g = __ldg(reinterpret_cast<const float4*>(aux + n0 + i));
-              r.x = fmaf(g.x, v[i], r.x); r.y = fmaf(g.y, v[i + 1], r.y); r.z = fmaf(g.z, v[i + 2], r.z); r.w = fmaf(g.w, v[i + 3], r.w);
-              *reinterpret_cast<float4*>(o + i) = r;
-            }
-          } else if constexpr (EPI == TC_F32_RESIDUAL) {
-            float* o = reinterpret_cast<float*>(out) + row * ldc + n0;
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              float4 r = rcur[i >> 2];
-              r.x += v[i]; r.y += v[i + 1]; r.z += v[i + 2]; r.w += v[i + 3];
-              *reinterpret_cast<float4*>(o + i) = r;
-            }
-          } else {
-            float* o = reinterpret_cast<float*>(out) + row * ldc + n0;
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
           }
         }
+        __syncwarp();   // the staging buffer is rewritten by the next chunk
       }
       tc_fence_before();
       __syncwarp();
@@ -271,7 +300,7 @@ static void tc_launch(const bf16* A, const bf16* W, const float* bias, void* out
   }
   const int tiles = (int)((M + 127) / 128) * (N / BN);
   const int grid = tiles < kSMs ? tiles : kSMs;
-  gemm_tc_kernel<BN, EPI><<<grid, 192, Cfg::kSmemBytes, st>>>(A, W, bias, out, ldc, M, N, K, aux);
+  gemm_tc_kernel<BN, EPI><<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(A, W, bias, out, ldc, M, N, K, aux);
 }
 
 // epi: TcEpi.  N % 256 == 0 uses 128x256 tiles (shared-memory read rate of the A/B operands stays under
