@@ -149,6 +149,59 @@ def cfg3_result(B: int, steps: int = 1500, dtype: str = "bf16", reps: int = 1, d
                          "bytes_per_step": bytes_step, "avg_step_us": t_step * 1e6}}
 
 
+def prompt_result(seconds: float = 15.0, reps: int = 3, device: int = 0):
+    """SURVEY.md 8(f4) prompt making: EnCodec 24 kHz encoder + 8-level RVQ of ONE mono clip of the reference's longest allowed
+    prompt length (utils/prompt_making.py:60-62) through the public mirror `AudioTokenizer.encode` (host waveform in, host codes out,
+    both copies inside the timed region), checked against the oracle's codes; the oracle port's wall time on the host cores beside it."""
+    import time
+
+    import torch
+
+    from oracle.encodec_oracle import OracleEncodec
+    from vallex_b200.tokenizer import AudioTokenizer
+    from vallex_b200.weights import synthetic_encodec_state_dict
+    sd = synthetic_encodec_state_dict(0)
+    n = int(seconds * 24000)
+    rng = np.random.default_rng(5)
+    t = np.arange(n) / 24000.0
+    wav = (0.4 * np.sin(2 * np.pi * 140.0 * t + 3.0 * np.sin(2 * np.pi * 0.7 * t)) * (0.5 + 0.5 * np.sin(2 * np.pi * 2.3 * t))
+           + 0.02 * rng.standard_normal(n)).astype(np.float32)
+    wav = torch.from_numpy(wav).view(1, 1, n)
+    tok = AudioTokenizer(f"cuda:{device}", state_dict=sd)
+    tok.encode(wav)
+    wall, dev = [], []
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        codes = tok.encode(wav)[0][0]
+        torch.cuda.synchronize()
+        wall.append(time.perf_counter() - t0)
+        dev.append(tok.last_timing()["ms"])
+    launches = tok.last_timing()["kernel_launches"]
+    tok.close()
+    ora = OracleEncodec(sd)
+    t0 = time.perf_counter()
+    want, margins = ora.quantize(ora.encoder(wav), return_margins=True)
+    cpu_s = time.perf_counter() - t0
+    got = codes.cpu()
+    flips = []   # reference top-1/top-2 gap at the FIRST differing level of a frame (deeper levels then quantise another residual)
+    for f in range(want.shape[-1]):
+        for q in range(8):
+            if got[0, q, f] != want[0, q, f]:
+                flips.append(float(margins[0, q, f]))
+                break
+    first_flip_frames = len(flips)
+    T = int(codes.shape[-1])
+    return {"workload": f"prompt making (SURVEY 8(f4)): EnCodec 24 kHz encoder + 8-level RVQ, one {seconds:g} s mono clip ({n} samples -> {T} frames), "
+                        "host waveform in, host codes out", "dtype": "f32", "device_ms": min(dev), "e2e_ms": 1e3 * min(wall),
+            "frames_per_s": T / min(wall), "x_realtime": seconds / min(wall), "gpu_launches": launches,
+            "parity": {"checker": "oracle/encodec_oracle.py (pinned to transformers' EncodecModel)", "frames": T,
+                       "frames_with_a_differing_code": first_flip_frames,
+                       "max_reference_margin_at_a_difference": (max(flips) if flips else None), "margin_rule": 2e-3,
+                       "ok": all(m < 2e-3 for m in flips)},
+            "cpu_oracle_s": cpu_s, "cpu_threads": torch.get_num_threads()}
+
+
 def cfg4_result(B: int, dtype: str = "bf16", reps: int = 1, device: int = 0):
     """BASELINE.json configs[3]: NAR 7-codebook pass + Vocos decode, 1500-frame sequences (S=314, P=225, T=1275), batch B on
     this GPU.  Tensor roofline of the NAR contractions (SURVEY.md 8(d) FLOP count) against the measured sustained bf16 rate."""
@@ -528,7 +581,7 @@ def main():
         m._engine = None
         torch.cuda.empty_cache()
         out["configs"] = {"cfg3_B8": cfg3_result(8, 1500, a.dtype, device=local), "cfg3_B32": cfg3_result(32, 1500, a.dtype, device=local),
-                          "cfg4_B64": cfg4_result(64, a.dtype, device=local)}
+                          "cfg4_B64": cfg4_result(64, a.dtype, device=local), "prompt_15s": prompt_result(15.0, device=local)}
     if not a.no_cpu_baseline and world == 1:   # the CPU baseline leg is timed on rank 0 at N=1 only
         out["cpu_baseline"] = cpu_reference_sample(a.cpu_ar_steps)
     if parity is not None and not parity["ok"]:

@@ -59,9 +59,9 @@ void launch_pack_qkv_heads(const void* qkv_bf16, int64_t R, void* q_img, void* k
                                                                (uint8_t*)vt_img);
 }
 
-// shared memory: Q 16 KB | K ring 3 x 8 KB | V^T ring 4 x 8 KB | P 2 x 16 KB | row stats 2 KB | barriers
-constexpr int T5_Q = 0, T5_K = 16384, T5_V = T5_K + 3 * 8192, T5_P = T5_V + 4 * 8192, T5_ST = T5_P + 2 * 16384,
-              T5_BAR = T5_ST + 2048, T5_BYTES = T5_BAR + 256;
+// shared memory: Q 16 KB | K ring 2 x 16 KB | V^T ring 2 x 16 KB | P 32 KB | barriers  (2 CTAs per SM)
+constexpr int T5_Q = 0, T5_K = 16384, T5_V = T5_K + 2 * 16384, T5_P = T5_V + 2 * 16384, T5_ST = T5_P /* the epilogue's row statistics reuse the P buffer */,
+              T5_BAR = T5_P + 32768, T5_BYTES = T5_BAR + 256;   // 114,944 B: two CTAs per SM
 
 __device__ __forceinline__ float t5_ex2(float x) {  // single MUFU.EX2; ex2(-inf) = 0
   float y;
@@ -111,15 +111,18 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
 }
 
 // =================================================================================================================
-// Single pass: one sweep over the key tiles with an online softmax whose running row maximum is
-// only raised LAZILY -- when a tile's row maximum exceeds the maximum in use by more than 2^8 -- so the rescale of the
-// O accumulator (TMEM read-modify-write by the warp that owns the rows, after the P V products in flight have drained) is
-// rare after the first tiles; P = exp2(S - m_used) stays <= 256 and the row sum l carries the same scale, so the final
-// O / l is exact softmax.  (Round 1's two-pass kernel -- statistics pass, then P V -- recomputed Q K^T and re-read K: it only
-// tied the mma.sync kernel; this one is 9 % faster on a whole NAR pass, profiles/r02_attention.log.)  The two column halves of a row (keys 0-31 / 32-63 of every 64-key tile) are INDEPENDENT online softmaxes
-// with their own accumulators O_a / O_b in TMEM (the P V product of a tile is issued as two K-halves), so no per-tile
-// exchange of row maxima is needed (in the first version that block barrier was 45 % of the stall samples); the halves are
-// merged once in the epilogue.
+// Single pass over 128-KEY tiles: one sweep with an online softmax whose running row maximum is only raised LAZILY -- when a
+// tile's row maximum exceeds the maximum in use by more than 2^8 -- so the rescale of the O accumulator (TMEM read-modify-write by
+// the warp that owns the rows, after the P V products in flight have drained) is rare after the first tiles; P = exp2(S - m_used)
+// stays <= 256 and the row sum l carries the same scale, so the final O / l is exact softmax.  The two column halves of a row
+// (keys 0-63 / 64-127 of every tile) are INDEPENDENT online softmaxes with their own accumulators O_a / O_b in TMEM (the P V
+// product of a tile is issued as two K-halves), so no per-tile exchange of row maxima is needed; the halves are merged once in
+// the epilogue.  A thread reads its 64 scores twice from TMEM (maximum, then 2 x 32 exponentials) instead of holding 64
+// registers; S is single-buffered: its TMEM columns are free as soon as every warp has its last 32 scores in registers, so
+// Q K^T of tile j+1 runs under the exponentials of tile j.
+// History: two-pass kernel (round 1, tied mma.sync) -> single pass, 64-key tiles (-9 % NAR) -> no block barrier, controller warp
+// (-12 %) -> 128-key tiles (this version): the per-tile synchronisation / address / polling overhead was ~40 % of the 340
+// instructions a warp issued per 64-key tile (profiles/r02_prof_attn_b8.md).
 // =================================================================================================================
 __global__ void __launch_bounds__(288, 2) attn_t5_kernel(Batch bt, const uint8_t* __restrict__ q_img,
                                                                  const uint8_t* __restrict__ k_img,
@@ -135,13 +138,13 @@ __global__ void __launch_bounds__(288, 2) attn_t5_kernel(Batch bt, const uint8_t
   uint8_t* sP = smem + T5_P;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T5_BAR);
   uint64_t* qbar = bars;
-  uint64_t* kfull = bars + 1;    // [3]
-  uint64_t* vfull = bars + 4;    // [4]
-  uint64_t* sfull = bars + 8;    // [2]
-  uint64_t* pvdone = bars + 10;  // [2]
-  uint64_t* pfull = bars + 12;   // [2]  all 8 softmax warps have written their part of P_j
-  uint64_t* sread = bars + 14;   // [2]  all 8 softmax warps hold S_j in registers: its TMEM buffer may be overwritten
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* kfull = bars + 1;    // [2]
+  uint64_t* vfull = bars + 3;    // [2]
+  uint64_t* sfull = bars + 5;    // [2]  S_j complete in TMEM (alternating by tile parity; one TMEM buffer)
+  uint64_t* pvdone = bars + 7;   // [2]  O += P_j V_j finished
+  uint64_t* pfull = bars + 9;    // [2]  all 8 softmax warps have written their part of P_j
+  uint64_t* sread = bars + 11;   // [2]  all 8 softmax warps hold the last of S_j in registers: the TMEM buffer may be overwritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 128;
   const int S = bt.S[b];
@@ -153,25 +156,26 @@ __global__ void __launch_bounds__(288, 2) attn_t5_kernel(Batch bt, const uint8_t
   const int64_t r0 = row0[b];
   int kend = len;
   if (mode == 1) kend = min(len, max(S, q0 + 128));
-  const int nkt = (kend + 63) >> 6;
+  const int nkt = (kend + 127) >> 7;
   const size_t head_bytes = (size_t)R * 128;
   const uint8_t* qsrc = q_img + (size_t)h * head_bytes + (size_t)((r0 + q0) >> 7) * 16384;
-  const uint8_t* ksrc = k_img + (size_t)h * head_bytes + (size_t)(r0 >> 7) * 16384;
-  const uint8_t* vsrc = vt_img + ((size_t)h * (R / 64) + (size_t)(r0 >> 6)) * 8192;
+  const uint8_t* ksrc = k_img + (size_t)h * head_bytes + (size_t)(r0 >> 7) * 16384;            // 128-key block = 16 KB
+  const uint8_t* vsrc = vt_img + ((size_t)h * (R / 64) + (size_t)(r0 >> 6)) * 8192;           // two 64-key blocks = 16 KB
 
   if (tid == 0) {
     mbar_init(qbar, 1);
-    for (int i = 0; i < 3; ++i) mbar_init(&kfull[i], 1);
-    for (int i = 0; i < 4; ++i) mbar_init(&vfull[i], 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&sfull[i], 1); mbar_init(&pvdone[i], 1); mbar_init(&pfull[i], 8); mbar_init(&sread[i], 8); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kfull[i], 1); mbar_init(&vfull[i], 1); mbar_init(&sfull[i], 1); mbar_init(&pvdone[i], 1);
+      mbar_init(&pfull[i], 8); mbar_init(&sread[i], 8);
+    }
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<256>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t tO = tmem + 128 + half * 64;   // this column half's own accumulator: O_a at columns 128..191, O_b at 192..255
+  const uint32_t tmem = *tmem_slot;                // S at columns 0..127
+  const uint32_t tO = tmem + 128 + half * 64;      // this column half's own accumulator: O_a at columns 128..191, O_b at 192..255
   const uint32_t tOa = tmem + 128, tOb = tmem + 192;
   const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
 
@@ -187,27 +191,27 @@ __global__ void __launch_bounds__(288, 2) attn_t5_kernel(Batch bt, const uint8_t
       pph ^= 1u << buf;
     }
   };
-  constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
+  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128), idesc_pv = umma_idesc_bf16(128, 64);
   const float sl2 = 0.125f * 1.44269504088896340736f;
   const int qi = q0 + rloc;
   auto issue_k = [&](int j) {
-    mbar_expect_tx(&kfull[j % 3], 8192);
-    bulk_g2s(sK + (j % 3) * 8192, ksrc + (size_t)j * 8192, 8192, &kfull[j % 3]);
+    mbar_expect_tx(&kfull[j & 1], 16384);
+    bulk_g2s(sK + (j & 1) * 16384, ksrc + (size_t)j * 16384, 16384, &kfull[j & 1]);
   };
   auto issue_v = [&](int j) {
-    mbar_expect_tx(&vfull[j & 3], 8192);
-    bulk_g2s(sV + (j & 3) * 8192, vsrc + (size_t)j * 8192, 8192, &vfull[j & 3]);
+    mbar_expect_tx(&vfull[j & 1], 16384);
+    bulk_g2s(sV + (j & 1) * 16384, vsrc + (size_t)j * 16384, 16384, &vfull[j & 1]);
   };
   auto mma_s = [&](int j) {
     tc_fence_after();
-    const uint64_t ad = umma_desc_sw128(smem_u32(sQ)), bd = umma_desc_sw128(smem_u32(sK + (j % 3) * 8192));
+    const uint64_t ad = umma_desc_sw128(smem_u32(sQ)), bd = umma_desc_sw128(smem_u32(sK + (j & 1) * 16384));
 #pragma unroll
-    for (int k = 0; k < 4; ++k) umma_bf16(tmem + (j & 1) * 64, ad + 2 * k, bd + 2 * k, idesc, k ? 1u : 0u);
+    for (int k = 0; k < 4; ++k) umma_bf16(tmem, ad + 2 * k, bd + 2 * k, idesc_s, k ? 1u : 0u);
     umma_commit(&sfull[j & 1]);
   };
   auto tile_full = [&](int j) {
-    const int k0 = j * 64;
-    return (k0 + 64 <= len) && (mode == 0 || k0 + 64 <= S || k0 + 63 <= q0);
+    const int k0 = j * 128;
+    return (k0 + 128 <= len) && (mode == 0 || k0 + 128 <= S || k0 + 127 <= q0);
   };
   auto visible = [&](int kj) {
     bool vis = kj < len;
@@ -218,63 +222,61 @@ __global__ void __launch_bounds__(288, 2) attn_t5_kernel(Batch bt, const uint8_t
   float m_used = -INFINITY;   // the row maximum this half's exponentials use
   float l_part = 0.f;         // this half's row sum, in the scale of m_used
   // No block-wide barrier inside the loop: a softmax thread (warps 0-7) owns its (row, column half) and meets the others only
-  // through mbarriers -- sfull (S_j in TMEM), pfull (P_j complete: 256 arrivals), pvdone (O += P_j V_j finished).  Warp 8 is the
-  // controller: one lane issues every bulk copy and every MMA, so no softmax warp lags behind doing that work.
+  // through mbarriers -- sfull (S_j in TMEM), sread (S_j consumed), pfull (P_j complete), pvdone (O += P_j V_j finished).  Warp 8
+  // is the controller: one lane issues every bulk copy and every MMA, so no softmax warp lags behind doing that work.
   if (warp == 8) {
     if (lane == 0) {
-      uint32_t pfph = 0;
+      uint32_t pfph = 0, srph = 0;
       mbar_expect_tx(qbar, 16384);
       bulk_g2s(sQ, qsrc, 16384, qbar);
-      for (int j = 0; j < 3 && j < nkt; ++j) issue_k(j);
-      for (int j = 0; j < 2 && j < nkt; ++j) issue_v(j);
+      for (int j = 0; j < 2 && j < nkt; ++j) { issue_k(j); issue_v(j); }
       mbar_wait(qbar, 0);
       wait_k(0);
       mma_s(0);
-      if (nkt > 1) { wait_k(1); mma_s(1); }
-      uint32_t srph = 0;
       for (int j = 0; j < nkt; ++j) {
-        // Q K^T of tile j+2 goes out as soon as every softmax warp holds S_j in registers (early in tile j's softmax), not after
-        // P_j is complete: in the previous order the softmax warps spent 20 % of their samples waiting for S (profiles/r02_prof_attn_b8.md)
-        if (j + 2 < nkt) {
-          mbar_wait(&sread[j & 1], (srph >> (j & 1)) & 1);
-          srph ^= 1u << (j & 1);
-          if (j + 3 < nkt) issue_k(j + 3);             // S_j was read, so its MMA is complete: K slot j % 3 is free
-          wait_k((j + 2) % 3);
-          mma_s(j + 2);
+        // Q K^T of tile j+1 goes out as soon as every softmax warp holds the last of S_j in registers
+        mbar_wait(&sread[j & 1], (srph >> (j & 1)) & 1);
+        srph ^= 1u << (j & 1);
+        if (j + 2 < nkt) issue_k(j + 2);                 // S_j was read, so its MMA is complete: K slot j & 1 is free
+        if (j + 1 < nkt) { wait_k((j + 1) & 1); mma_s(j + 1); }
+        if (j >= 1) {                                    // O += P_{j-1} V_{j-1} done: V slot (j+1) & 1 is free
+          ensure_pv(j - 1);
+          if (j + 1 < nkt) issue_v(j + 1);
         }
-        ensure_pv(j - 2);                              // O += P_{j-2} V_{j-2} done: V slot (j-2)&3 is free
-        if (j + 2 < nkt) issue_v(j + 2);
         mbar_wait(&pfull[j & 1], (pfph >> (j & 1)) & 1);   // every warp's part of P_j is in place, rescales are done
         pfph ^= 1u << (j & 1);
-        mbar_wait(&vfull[j & 3], (vph >> (j & 3)) & 1);
-        vph ^= 1u << (j & 3);
+        mbar_wait(&vfull[j & 1], (vph >> (j & 1)) & 1);
+        vph ^= 1u << (j & 1);
         tc_fence_after();
-        const uint64_t ad = umma_desc_sw128(smem_u32(sP + (j & 1) * 16384)), bd = umma_desc_sw128(smem_u32(sV + (j & 3) * 8192));
+        const uint32_t pa = smem_u32(sP), va = smem_u32(sV + (j & 1) * 16384);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)    // keys 0-31 of the tile accumulate into O_a, keys 32-63 into O_b
-          umma_bf16(ks < 2 ? tOa : tOb, ad + 2 * ks, bd + 2 * ks, idesc, (j | (ks & 1)) ? 1u : 0u);
+        for (int ks = 0; ks < 8; ++ks) {   // keys 0-63 of the tile (P block 0, V^T block 0) accumulate into O_a, keys 64-127 into O_b
+          const uint64_t ad = umma_desc_sw128(pa + (ks >> 2) * 16384) + 2 * (ks & 3);
+          const uint64_t bd = umma_desc_sw128(va + (ks >> 2) * 8192) + 2 * (ks & 3);
+          umma_bf16(ks < 4 ? tOa : tOb, ad, bd, idesc_pv, (j | (ks & 3)) ? 1u : 0u);
+        }
         umma_commit(&pvdone[j & 1]);
       }
     }
   } else {
+    const uint32_t tS = tmem + lane_addr + half * 64;
     for (int j = 0; j < nkt; ++j) {
       wait_s(j & 1);
       tc_fence_after();
-      float v[32];
-      tmem_ld32(tmem + (j & 1) * 64 + lane_addr + half * 32, v);
-      tc_fence_before();                  // this warp's TMEM read of S_j is ordered before the arrival that lets S_{j+2} overwrite it
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sread[j & 1]);
-      const int kb = j * 64 + half * 32;
+      const int kb = j * 128 + half * 64;
+      const bool full = tile_full(j);
+      // pass 1: the row maximum over this half's 64 scores
       float mx = -INFINITY;
-      if (tile_full(j)) {
+#pragma unroll 1
+      for (int sub = 0; sub < 2; ++sub) {
+        float v[32];
+        tmem_ld32(tS + sub * 32, v);
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, v[i]);
-      } else {
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, v[i]);
+        } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          v[i] = visible(kb + i) ? v[i] : -INFINITY;
-          mx = fmaxf(mx, v[i]);
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, visible(kb + sub * 32 + i) ? v[i] : -INFINITY);
         }
       }
       const float m_tile = mx * sl2;
@@ -297,21 +299,41 @@ __global__ void __launch_bounds__(288, 2) attn_t5_kernel(Batch bt, const uint8_t
           tc_fence_before();
         }
       }
-      uint32_t pk[16];
       const float mu = (m_used == -INFINITY) ? 0.f : m_used;   // a half that has seen no visible key yet: every P is ex2(-inf) = 0
       // packed fp32 pairs (FFMA2 / FADD2): half the scale-and-shift and row-sum instructions; two independent sum chains
       const uint64_t sl2x2 = t5_pack2(sl2, sl2), nmux2 = t5_pack2(-mu, -mu);
       uint64_t ls_a = 0ull, ls_b = 0ull;    // (+0, +0)
+      uint8_t* prow = sP + half * 16384 + rloc * 128;      // this half's 64 keys = P block `half`, row rloc
+      // pass 2: exponentials, 32 scores at a time
+#pragma unroll 1
+      for (int sub = 0; sub < 2; ++sub) {
+        float v[32];
+        tmem_ld32(tS + sub * 32, v);
+        if (sub == 1) {                     // S_j is in registers: let the controller overwrite the TMEM buffer with S_{j+1}
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sread[j & 1]);
+        }
+        if (!full) {
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        float a0, a1, b0, b1;
-        t5_unpack2(t5_fma2(t5_pack2(v[i], v[i + 1]), sl2x2, nmux2), a0, a1);
-        t5_unpack2(t5_fma2(t5_pack2(v[i + 2], v[i + 3]), sl2x2, nmux2), b0, b1);
-        const float p0 = t5_ex2(a0), p1 = t5_ex2(a1), p2 = t5_ex2(b0), p3 = t5_ex2(b1);   // masked: ex2(-inf) = 0
-        ls_a = t5_add2(ls_a, t5_pack2(p0, p1));
-        ls_b = t5_add2(ls_b, t5_pack2(p2, p3));
-        pk[i >> 1] = t5_pack(p0, p1);
-        pk[(i >> 1) + 1] = t5_pack(p2, p3);
+          for (int i = 0; i < 32; ++i) v[i] = visible(kb + sub * 32 + i) ? v[i] : -INFINITY;
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          float a0, a1, b0, b1;
+          t5_unpack2(t5_fma2(t5_pack2(v[i], v[i + 1]), sl2x2, nmux2), a0, a1);
+          t5_unpack2(t5_fma2(t5_pack2(v[i + 2], v[i + 3]), sl2x2, nmux2), b0, b1);
+          const float p0 = t5_ex2(a0), p1 = t5_ex2(a1), p2 = t5_ex2(b0), p3 = t5_ex2(b1);   // masked: ex2(-inf) = 0
+          ls_a = t5_add2(ls_a, t5_pack2(p0, p1));
+          ls_b = t5_add2(ls_b, t5_pack2(p2, p3));
+          pk[i >> 1] = t5_pack(p0, p1);
+          pk[(i >> 1) + 1] = t5_pack(p2, p3);
+        }
+        if (sub == 0) ensure_pv(j - 1);     // O += P_{j-1} V_{j-1} done: the P buffer is free
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(prow + (((sub * 4 + q) ^ (rloc & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
       }
       {
         float s0, s1, s2, s3;
@@ -319,11 +341,6 @@ __global__ void __launch_bounds__(288, 2) attn_t5_kernel(Batch bt, const uint8_t
         t5_unpack2(ls_b, s2, s3);
         l_part += (s0 + s1) + (s2 + s3);
       }
-      ensure_pv(j - 2);                   // O += P_{j-2} V_{j-2} done: P buffer j&1 is free
-      uint8_t* prow = sP + (j & 1) * 16384 + rloc * 128;
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        *reinterpret_cast<uint4*>(prow + (((half * 4 + q) ^ (rloc & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
       fence_proxy_async();                // P was written through the generic proxy, the MMA reads it through the async proxy
       tc_fence_before();                  // ... and this thread's TMEM writes of O_h (rescale) are ordered before the arrival
       __syncwarp();

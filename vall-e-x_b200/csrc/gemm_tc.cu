@@ -11,6 +11,8 @@
 //              MMAs overlap), add bias / ReLU / residual, store bf16 row-major, bf16 tile image or fp32.
 // Bound: tensor pipe (dense bf16).  Tiles are walked m-fastest so CTAs running concurrently share the same
 // weight blocks through L2.  modules/activation.py:144,166; modules/transformer.py:371-373; models/vallex.py:677.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_common.cuh"
@@ -387,7 +389,18 @@ void launch_pack_split3_weight(const float* src, int64_t rows, int K_src, int64_
 }
 
 // LayerNorm / AdaLN rows -> bf16 tile image (the A operand of the next GEMM); same math as layernorm_kernel.
-// One warp per row (values in registers, shuffle reductions only), 8 rows per CTA; HBM bound: 4 KB in, 2 KB out per row.
+// One warp per row (values in registers, shuffle reductions only); HBM/L2 bound: 4 KB in, 2 KB out per row.  Persistent: a fixed
+// grid of 8-warp CTAs strides over the rows and every warp requests its NEXT row before it reduces the current one (the
+// one-row-per-warp launch ran at half the copy rate: 27.7 us for 15,360 rows, profiles/r02_launches_cfg4_b8.md), and the affine
+// vectors (gamma, beta, AdaLN weight / bias: the same 16 KB for every row) are read once per warp, not once per row.
+__device__ __forceinline__ void ln_row_load(const float* __restrict__ x, int64_t src, int lane, float4 (&v)[8]) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const float* p = x + src * kD + it * 256 + lane * 8;
+    v[2 * it] = *reinterpret_cast<const float4*>(p);
+    v[2 * it + 1] = *reinterpret_cast<const float4*>(p + 4);
+  }
+}
 __global__ void __launch_bounds__(256) layernorm_image_kernel(const float* __restrict__ x,
                                                               const int32_t* __restrict__ row_map, int64_t rows,
                                                               const float* __restrict__ gamma,
@@ -396,55 +409,74 @@ __global__ void __launch_bounds__(256) layernorm_image_kernel(const float* __res
                                                               const float* __restrict__ ada_b, float eps,
                                                               uint8_t* __restrict__ img) {
   const int lane = threadIdx.x & 31;
-  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (r >= rows) return;
-  const int64_t src = row_map ? row_map[r] : r;
-  float v[4][8];
-  float s = 0.f;
-#pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int c0 = it * 256 + lane * 8;
-    const float4 a = *reinterpret_cast<const float4*>(x + src * kD + c0);
-    const float4 b = *reinterpret_cast<const float4*>(x + src * kD + c0 + 4);
-    v[it][0] = a.x; v[it][1] = a.y; v[it][2] = a.z; v[it][3] = a.w; v[it][4] = b.x; v[it][5] = b.y; v[it][6] = b.z; v[it][7] = b.w;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s += v[it][i];
+  const int64_t nwarps = (int64_t)gridDim.x * 8;
+  int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  // y = ((v - mean) * rstd) * g + be, then (AdaLN) aw * y + ab, in exactly this order (modules/transformer.py:17-80,83-108);
+  // the four affine vectors live in shared memory for the CTA's lifetime
+  __shared__ __align__(16) float aff[4][kD];
+  for (int i = threadIdx.x; i < kD; i += 256) {
+    aff[0][i] = gamma[i]; aff[1][i] = beta[i];
+    if (ada_w) { aff[2][i] = ada_w[i]; aff[3][i] = ada_b[i]; }
   }
-  const float mean = warp_sum(s) / (float)kD;
-  float qv = 0.f;
-#pragma unroll
-  for (int it = 0; it < 4; ++it)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { const float d = v[it][i] - mean; qv += d * d; }
-  const float rstd = 1.0f / sqrtf(warp_sum(qv) / (float)kD + eps);
+  __syncthreads();
+  if (r >= rows) return;
   auto pk = [](float a, float b) {
     return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(b)) << 16);
   };
+  float4 cur[8], nxt[8];
+  ln_row_load(x, row_map ? row_map[r] : r, lane, cur);
+  for (; r < rows; r += nwarps) {
+    const int64_t rn = r + nwarps;
+    if (rn < rows) ln_row_load(x, row_map ? row_map[rn] : rn, lane, nxt);
+    float v[4][8];
+    float s = 0.f;
 #pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int c0 = it * 256 + lane * 8;
-    float g[8], be[8], y[8];
-    load8(gamma + c0, g);     // 128-bit loads (the scalar form issued 128 LDGs per thread and made the kernel LSU-bound)
-    load8(beta + c0, be);
+    for (int it = 0; it < 4; ++it) {
+      const float4 a = cur[2 * it], b = cur[2 * it + 1];
+      v[it][0] = a.x; v[it][1] = a.y; v[it][2] = a.z; v[it][3] = a.w; v[it][4] = b.x; v[it][5] = b.y; v[it][6] = b.z; v[it][7] = b.w;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) y[i] = ((v[it][i] - mean) * rstd) * g[i] + be[i];
-    if (ada_w) {
-      float aw[8], ab[8];
-      load8(ada_w + c0, aw);
-      load8(ada_b + c0, ab);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) y[i] = aw[i] * y[i] + ab[i];
+      for (int i = 0; i < 8; ++i) s += v[it][i];
     }
-    uint4 p;
-    p.x = pk(y[0], y[1]); p.y = pk(y[2], y[3]); p.z = pk(y[4], y[5]); p.w = pk(y[6], y[7]);
-    *reinterpret_cast<uint4*>(img + tile_image_offset(r, c0, kD)) = p;
+    const float mean = warp_sum(s) / (float)kD;
+    float qv = 0.f;
+#pragma unroll
+    for (int it = 0; it < 4; ++it)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float d = v[it][i] - mean; qv += d * d; }
+    const float rstd = 1.0f / sqrtf(warp_sum(qv) / (float)kD + eps);
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int c0 = it * 256 + lane * 8;
+      float y[8], g[8], be[8];
+      *reinterpret_cast<float4*>(g) = *reinterpret_cast<const float4*>(&aff[0][c0]);
+      *reinterpret_cast<float4*>(g + 4) = *reinterpret_cast<const float4*>(&aff[0][c0 + 4]);
+      *reinterpret_cast<float4*>(be) = *reinterpret_cast<const float4*>(&aff[1][c0]);
+      *reinterpret_cast<float4*>(be + 4) = *reinterpret_cast<const float4*>(&aff[1][c0 + 4]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] = ((v[it][i] - mean) * rstd) * g[i] + be[i];
+      if (ada_w) {
+        *reinterpret_cast<float4*>(g) = *reinterpret_cast<const float4*>(&aff[2][c0]);
+        *reinterpret_cast<float4*>(g + 4) = *reinterpret_cast<const float4*>(&aff[2][c0 + 4]);
+        *reinterpret_cast<float4*>(be) = *reinterpret_cast<const float4*>(&aff[3][c0]);
+        *reinterpret_cast<float4*>(be + 4) = *reinterpret_cast<const float4*>(&aff[3][c0 + 4]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = g[i] * y[i] + be[i];
+      }
+      uint4 p;
+      p.x = pk(y[0], y[1]); p.y = pk(y[2], y[3]); p.z = pk(y[4], y[5]); p.w = pk(y[6], y[7]);
+      *reinterpret_cast<uint4*>(img + tile_image_offset(r, c0, kD)) = p;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
   }
 }
 void launch_layernorm_image(const float* x, const int32_t* row_map, int64_t rows, const float* gamma,
                             const float* beta, const float* ada_w, const float* ada_b, float eps, void* img,
                             cudaStream_t st) {
   if (rows <= 0) return;
-  layernorm_image_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, row_map, rows, gamma, beta, ada_w, ada_b, eps, (uint8_t*)img);
+  const int64_t want = (rows + 7) / 8;
+  const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)kSMs * 2);   // 2 CTAs of 8 warps per SM resident (110 registers)
+  layernorm_image_kernel<<<grid, 256, 0, st>>>(x, row_map, rows, gamma, beta, ada_w, ada_b, eps, (uint8_t*)img);
 }
 
 }  // namespace vx
