@@ -500,3 +500,26 @@ def test_real_checkpoint_if_present():
 def test_smoke_entry():
     import __graft_entry__ as ge
     ge.smoke()
+
+
+def test_nar_row_chunks_equal_one_pass(monkeypatch):
+    """vx_nar runs the 12-layer stack chunk by chunk over the utterances (L2 residency at large batches); utterances are independent
+    (models/vallex.py:491), every one starts on a 128-row tile boundary, so chunked and unchunked codes must be IDENTICAL -- here
+    with chunks of one or two utterances of a ragged bf16 batch against one pass."""
+    names = ["tiny_en", "noprompt_en", "mixlang", "tiny_en", "mid_ja"]
+    gs = [load_golden(n) for n in names]
+    sd = state_dict_for(0)
+    t_lens = np.asarray([40, 17, 33, 1, 25], np.int32)
+    cb0 = np.random.default_rng(11).integers(0, 1024, size=(len(gs), 40)).astype(np.int32)
+    res = {}
+    for rows in ("0", "256", "100000"):
+        monkeypatch.setenv("VX_NAR_CHUNK_ROWS", rows)
+        m = _valle(sd, "bf16", max_ctx=1024, max_batch=len(gs))
+        eng = m.engine
+        langs = [m._lang_ids(len(g["x"]), int(g["Lp"]), g["prompt_language_arg"], g["text_language_arg"]) for g in gs]
+        eng.set_batch([g["x"].astype(np.int32) for g in gs], langs, [g["prompt"].astype(np.int32) for g in gs])
+        res[rows] = eng.nar(cb0=cb0, t_lens=t_lens).copy()
+        eng.close()
+    for b, t in enumerate(t_lens):
+        assert np.array_equal(res["0"][b, :t], res["256"][b, :t]), b
+        assert np.array_equal(res["0"][b, :t], res["100000"][b, :t]), b

@@ -374,15 +374,21 @@ int linear(vx_engine* e, const float* A, int64_t lda, const void* W, int wt, con
 // fp32 mode (or VX_FORCE_SIMT=1): exact SIMT kernels.  bf16 mode: LN -> bf16 tile image -> tcgen05 GEMMs with fused
 // epilogues, mma.sync flash attention.
 int full_layer(vx_engine* e, const LayerW& L, int64_t R, const int32_t* row0, int attn_mode, int maxlen,
-               const float* ada1, const float* ada2, int kv_layer, cudaStream_t st) {
-  const Batch& bt = e->bt;
+               const float* ada1, const float* ada2, int kv_layer, cudaStream_t st, int64_t R0 = 0, int b0 = 0, int nb = -1) {
+  // [R0, R0 + R) / utterances [b0, b0 + nb): the row range this call covers (NAR chunks, see vx_nar); default = everything
+  Batch bt = e->bt;
+  if (nb >= 0) { bt.B = nb; bt.S += b0; bt.P += b0; bt.T += b0; row0 += b0; }
   const int wt = e->mode;
   const size_t kvb = kv_esize(e);
-  float* x = (float*)e->x.p;
+  float* x = (float*)e->x.p + (size_t)R0 * kD;
   void* kc = kv_layer >= 0 ? (char*)e->kc.p + ((size_t)kv_layer * e->kv_layer_elems + e->kv_slot_off) * kvb : nullptr;
   void* vc = kv_layer >= 0 ? (char*)e->vc.p + ((size_t)kv_layer * e->kv_layer_elems + e->kv_slot_off) * kvb : nullptr;
   if (e->mode == VX_BF16 && !e->force_simt) {
-    launch_layernorm_image(x, nullptr, R, L.n1_g, L.n1_b, ada1, ada1 ? ada1 + kD : nullptr, 1e-5f, e->a_img.p, st);
+    // tile images are [row tile][k tile] blocks: rows [R0, ...) of a [*, K] image start R0 * K * 2 bytes in (R0 % 128 == 0)
+    char* a_img = (char*)e->a_img.p + (size_t)R0 * kD * 2;
+    char* att_img = (char*)e->att_img.p + (size_t)R0 * kD * 2;
+    char* h_img = (char*)e->h_img.p + (size_t)R0 * kFF * 2;
+    launch_layernorm_image(x, nullptr, R, L.n1_g, L.n1_b, ada1, ada1 ? ada1 + kD : nullptr, 1e-5f, a_img, st);
     // VX_ATTN_T5=3 (experimental): NAR layers (no KV scatter) write the per-head operand images straight from the QKV GEMM
     const bool heads_epi = e->attn_t5 && e->attn_t5_fuse && kv_layer < 0;
     void *q_i = e->q_img.p, *k_i = e->k_img.p, *vt_i = e->vt_img.p;
@@ -391,24 +397,28 @@ int full_layer(vx_engine* e, const LayerW& L, int64_t R, const int32_t* row0, in
       vt_i = (char*)q_i + (size_t)2 * e->full_rows * kD * 2;
     }
     if (heads_epi) {
-      launch_gemm_tc(e->a_img.p, L.qkv_i, L.qkv_b, q_i, e->full_rows, R, 3 * kD, kD, TC_EPI_QKV_HEADS, st);
+      // per-head images [full_rows, 64] (q, k) and 64-key V^T blocks: row R0 of every head sits R0 * 128 bytes into its image
+      launch_gemm_tc(a_img, L.qkv_i, L.qkv_b, (char*)q_i + (size_t)R0 * 128, e->full_rows, R, 3 * kD, kD, TC_EPI_QKV_HEADS, st);
     } else {
-      launch_gemm_tc(e->a_img.p, L.qkv_i, L.qkv_b, e->qkv16.p, 3 * kD, R, 3 * kD, kD, TC_EPI_BF16_ROW, st);
+      if (R0 != 0) return fail(VX_ERR_STATE, "full_layer: row chunks need the QKV-heads epilogue");
+      launch_gemm_tc(a_img, L.qkv_i, L.qkv_b, e->qkv16.p, 3 * kD, R, 3 * kD, kD, TC_EPI_BF16_ROW, st);
     }
     if (kv_layer >= 0) { launch_kv_scatter_bf16(bt, e->qkv16.p, kc, vc, maxlen, e->ctx_cap, st); e->launches++; }
     if (e->attn_t5) {
       if (!heads_epi) { launch_pack_qkv_heads(e->qkv16.p, e->full_rows, q_i, k_i, vt_i, st); e->launches++; }
-      launch_attn_t5(bt, q_i, k_i, vt_i, e->full_rows, row0, attn_mode, maxlen, e->att_img.p, st);
+      launch_attn_t5(bt, q_i, k_i, vt_i, e->full_rows, row0, attn_mode, maxlen, e->att_img.p, st);   // row0 is absolute: images un-offset
     } else {
+      if (R0 != 0) return fail(VX_ERR_STATE, "full_layer: row chunks need the tcgen05 attention");
       launch_attn_tc(bt, e->qkv16.p, row0, attn_mode, maxlen, e->att_img.p, st);
     }
-    launch_gemm_tc(e->att_img.p, L.out_i, L.out_b, x, kD, R, kD, kD, TC_EPI_F32_RESIDUAL, st);
-    launch_layernorm_image(x, nullptr, R, L.n2_g, L.n2_b, ada2, ada2 ? ada2 + kD : nullptr, 1e-5f, e->a_img.p, st);
-    launch_gemm_tc(e->a_img.p, L.ff1_i, L.ff1_b, e->h_img.p, kFF, R, kFF, kD, TC_EPI_BF16_IMAGE_RELU, st);
-    launch_gemm_tc(e->h_img.p, L.ff2_i, L.ff2_b, x, kD, R, kD, kFF, TC_EPI_F32_RESIDUAL, st);
+    launch_gemm_tc(att_img, L.out_i, L.out_b, x, kD, R, kD, kD, TC_EPI_F32_RESIDUAL, st);
+    launch_layernorm_image(x, nullptr, R, L.n2_g, L.n2_b, ada2, ada2 ? ada2 + kD : nullptr, 1e-5f, a_img, st);
+    launch_gemm_tc(a_img, L.ff1_i, L.ff1_b, h_img, kFF, R, kFF, kD, TC_EPI_BF16_IMAGE_RELU, st);
+    launch_gemm_tc(h_img, L.ff2_i, L.ff2_b, x, kD, R, kD, kFF, TC_EPI_F32_RESIDUAL, st);
     e->launches += 7;
     return VX_OK;
   }
+  if (R0 != 0) return fail(VX_ERR_STATE, "full_layer: row chunks exist in bf16 mode only");
   float* xn = (float*)e->xn.p; float* qkv = (float*)e->qkv.p; float* att = (float*)e->att.p; float* ffh = (float*)e->ffh.p;
   launch_layernorm(x, nullptr, R, kD, L.n1_g, L.n1_b, ada1, ada1 ? ada1 + kD : nullptr, 1e-5f, xn, st);
   launch_gemm(xn, kD, L.qkv_w, wt, L.qkv_b, qkv, 3 * kD, R, 3 * kD, kD, EPI_NONE, nullptr, st);
@@ -1273,6 +1283,20 @@ int vx_nar(vx_engine* e, const int32_t* cb0, const int32_t* t_lens, int Tmax, in
     YR += pt; TR += e->hT[b];
     maxlen = std::max(maxlen, e->hS[b] + pt); maxpt = std::max(maxpt, pt); maxT = std::max(maxT, e->hT[b]);
   }
+  // utterance chunks for the layer stack (bf16 + tcgen05 attention + QKV-heads epilogue only; otherwise one chunk)
+  std::vector<int> chunk_b{0};
+  const std::vector<int32_t> nrow0_h = nrow0;
+  {
+    const bool can_chunk = e->mode == VX_BF16 && !e->force_simt && e->attn_t5 && e->attn_t5_fuse;
+    const char* ce = getenv("VX_NAR_CHUNK_ROWS");
+    const int64_t chunk_rows = ce ? atoll(ce) : 23040;   // 180 row tiles x 4 column tiles of the N = 1024 GEMMs = 720 = 4.86 waves
+    if (can_chunk && chunk_rows > 0) {
+      int64_t start = 0;
+      for (int b = 1; b < B; ++b)
+        if ((int64_t)nrow0[b] + ((b + 1 < B ? (int64_t)nrow0[b + 1] : R) - nrow0[b]) - start > chunk_rows && nrow0[b] > start) { chunk_b.push_back(b); start = nrow0[b]; }
+    }
+    chunk_b.push_back(B);
+  }
   std::vector<int32_t> tgt((size_t)std::max<int64_t>(TR, 1));
   for (int b = 0; b < B; ++b)
     for (int t = 0; t < e->hT[b]; ++t) tgt[trow0[b] + t] = nrow0[b] + e->hS[b] + e->hP[b] + t;
@@ -1301,9 +1325,18 @@ int vx_nar(vx_engine* e, const int32_t* cb0, const int32_t* t_lens, int Tmax, in
                         vec(e, "nar_text_position.alpha"), e->pe, bt.nar_row0, x, st);
       launch_nar_build_x(bt, yemb, d_yrow0, vec(e, "nar_audio_position.alpha"), e->pe, x, maxpt, st);
       e->launches += 2;
-      for (int l = 0; l < kL; ++l) {
-        const LayerW& L = e->nar[l];
-        full_layer(e, L, R, bt.nar_row0, 0, maxlen, L.ada1 + (size_t)stage * 2 * kD, L.ada2 + (size_t)stage * 2 * kD, -1, st);
+      // The 12 layers run chunk by chunk over the utterances (independent: models/vallex.py:491 has batch 1): a chunk's residual
+      // stream and operand images stay L2-resident from kernel to kernel, which a 64-utterance pass (0.5 GB of residual stream
+      // alone) does not; chunks are sized by rows so the N = 1024 GEMMs still fill whole waves of 148 CTAs.
+      for (size_t c = 0; c + 1 < chunk_b.size(); ++c) {
+        const int cb0 = chunk_b[c], cb1 = chunk_b[c + 1];
+        const int64_t cr0 = nrow0_h[cb0], cr1 = (cb1 < B) ? nrow0_h[cb1] : R;
+        for (int l = 0; l < kL; ++l) {
+          const LayerW& L = e->nar[l];
+          const int rc = full_layer(e, L, cr1 - cr0, bt.nar_row0, 0, maxlen, L.ada1 + (size_t)stage * 2 * kD, L.ada2 + (size_t)stage * 2 * kD, -1, st,
+                                    cr0, cb0, cb1 - cb0);
+          if (rc) return rc;
+        }
       }
       const float* af = e->nar_norm_ada + (size_t)stage * 2 * kD;
       if (e->mode == VX_BF16 && !e->force_simt) {
