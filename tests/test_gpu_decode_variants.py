@@ -34,7 +34,9 @@ def _teacher_forced(m, gs, names):
         match = toks[b, :T] == w
         assert match[margin > MARGIN].all(), (names[b], margin[~match & (margin > MARGIN)][:5])
         assert match.mean() > 0.97, (names[b], match.mean())
+    kernel = eng.last_decode_kernel()
     eng.close()
+    return kernel
 
 
 @pytest.mark.parametrize("B", [8, 16, 32])
@@ -86,3 +88,16 @@ def test_nar_and_prefill_attention_kernels(monkeypatch, name, t5):
     assert nar_match.mean() > 0.90
     assert nar_match[binding & upstream_ok.all(axis=1, keepdims=True)].mean() > 0.995
     eng.close()
+
+
+
+@pytest.mark.parametrize("flag,kernel", [("0", "ar_decode_fused_kernel<1>"), ("1", "ar_decode_cluster_kernel")])
+def test_batch1_kernels(monkeypatch, flag, kernel):
+    """The batch-1 default is the cluster kernel (decode_cluster.cu: a head = a 4-CTA cluster, two grid barriers per layer);
+    VX_DECODE_CLUSTER=0 selects the 3-barrier kernel it replaced (also the fallback where 16 four-CTA clusters cannot be
+    co-resident).  Same teacher-forced bar for both, and the engine reports which kernel ran."""
+    monkeypatch.setenv("VX_DECODE_CLUSTER", flag)
+    for name in ("tiny_en", "mid_ja"):
+        g = load_golden(name)
+        m = _valle(state_dict_for(g["seed"]), "bf16", max_ctx=1024)
+        assert _teacher_forced(m, [g], [name]) == kernel

@@ -31,6 +31,8 @@ raw = eng.debug_read("decode_prof", 3 * 4096 * 2).view(np.int64).reshape(3, 2048
 mhz = 1965.0
 fused = os.environ.get("VX_DECODE_FUSED", "") != "0" and B <= (8 if os.environ.get("VX_DECODE_FUSED") == "1" else 2)
 per_layer = ("qkv", "attn", "ffn") if fused else ("qkv", "attn", "out", "ff1", "ff2")   # fused: 38 barriers per step, else 62
+if B == 1 and os.environ.get("VX_DECODE_CLUSTER", "") == "1":
+    per_layer = ("PA", "PB")   # cluster kernel: 26 barriers per step; PA stamps: 3 staged, 4 q|k|v gathered, 5 head output folded, 6 out-proj + issues done
 names = ["S0"] + [f"{n}" for l in range(12) for n in per_layer] + ["PF"]
 for c in range(3):
     ev = [(int(tag), int(clk)) for tag, clk in raw[c] if tag != 0]

@@ -26,8 +26,10 @@ __device__ __forceinline__ void fix_add(long long* p, float v) {
 __device__ __forceinline__ float fix_get(const long long* p) { return __ll2float_rn(__ldcg(p)) * (1.0f / kFixScale); }
 
 // stage_ln + write-back: the staged residual value (before normalisation) of columns [c0,c1) goes to xout
-template <int MR, typename Val>
-__device__ __forceinline__ void stage_ln_x(float* sx, int B, Val value, const LnPre& lp, float* red, float* xout, int c0, int c1) {
+// `after_loads()` runs once the activation loads have been issued (the cluster kernel requests its weight rows there: they land
+// under the two block reductions without delaying the loads the reductions wait for)
+template <int MR, typename Val, typename Mid>
+__device__ __forceinline__ void stage_ln_x(float* sx, int B, Val value, const LnPre& lp, float* red, float* xout, int c0, int c1, Mid after_loads) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int R = MR < 8 ? MR : 8;
   for (int mb = 0; mb < B; mb += R) {
@@ -38,6 +40,7 @@ __device__ __forceinline__ void stage_ln_x(float* sx, int B, Val value, const Ln
       v0[m] = (m < nb) ? value(mb + m, tid) + lp.f0 : 0.f;
       v1[m] = (m < nb) ? value(mb + m, tid + PNT) + lp.f1 : 0.f;
     }
+    if (mb == 0) after_loads();
     if (xout) {
 #pragma unroll
       for (int m = 0; m < R; ++m) {
@@ -81,6 +84,11 @@ __device__ __forceinline__ void stage_ln_x(float* sx, int B, Val value, const Ln
     }
     __syncthreads();
   }
+}
+
+template <int MR, typename Val>
+__device__ __forceinline__ void stage_ln_x(float* sx, int B, Val value, const LnPre& lp, float* red, float* xout, int c0, int c1) {
+  stage_ln_x<MR>(sx, B, value, lp, red, xout, c0, c1, [] {});
 }
 
 __device__ __forceinline__ void zero_slice(long long* acc, int B, int c0, int c1) {

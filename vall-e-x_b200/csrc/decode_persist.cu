@@ -191,6 +191,7 @@ int launch_decode_persistent(const void* params, int wt, int B, int grid, cudaSt
   if (wt == 1 && p.att_maxp > 0) {   // tensor-core batched kernel (engine.cu decides: bf16, 5 <= B <= 32)
     return (int)launch_decode_mma(p, mr < 8 ? 8 : mr, grid, st);
   }
+  if (wt == 1 && p.cluster) return (int)launch_decode_cluster(p, grid, st, nullptr);   // batch 1, head groups as clusters
   if (wt == 1 && p.fused) {  // 3-barrier variant: requires one attention unit per CTA and <= kDecodeHS hidden units per CTA
     if (mr > 8 || B * kH * p.nsplit > grid || (kFF + grid - 1) / grid > kDecodeHS) return (int)cudaErrorInvalidConfiguration;
     return (int)launch_decode_fused(p, mr, grid, st);

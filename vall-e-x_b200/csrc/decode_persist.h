@@ -33,6 +33,7 @@ struct PParams {
   long long* acc_out;         // [2][B][1024] fused variant: out-proj sums, 2^-30 fixed point, by layer parity
   long long* acc_ffn;         // [2][B][1024] fused variant: FFN2 sums
   int fused;                  // 0: 5-barrier kernel, 1: 3-barrier kernel (default for B <= 2)
+  int cluster;                // 1: batch-1 kernel with head groups as 4-CTA clusters (decode_cluster.cu; uses the fused variant's buffers)
   float* part;                // [B][16][nsplit][66]  (balanced batched attention: [B][16][att_maxp][68])
   int kv_l2_mb;               // batched kernel: MB of the next layer's KV rows prefetched into L2 during the GEMV phases (0: off)
   int att_maxp;               // balanced batched attention (decode_mma.cu): max pieces per (utterance, head); 0 = CTA-per-head units
@@ -59,6 +60,8 @@ int launch_decode_persistent(const void* params, int wt, int B, int grid, cudaSt
 // launchers of the kernel variants (one translation unit each); mr = padded batch rows
 cudaError_t launch_decode_fused(const PParams& p, int mr, int grid, cudaStream_t st);     // decode_fused.cu
 cudaError_t launch_decode_mma(const PParams& p, int mr, int grid, cudaStream_t st);       // decode_mma.cu
+cudaError_t launch_decode_cluster(const PParams& p, int num_sms, cudaStream_t st, int* grid_out);   // decode_cluster.cu (B = 1)
+int decode_cluster_grid(int num_sms);   // CTAs the cluster kernel would run with on the current device; 0: not launchable
 constexpr int kDecodeHS = 64;   // max hidden units per CTA of the fused kernels (kHS in decode_fused_common.cuh)
 
 }  // namespace vx

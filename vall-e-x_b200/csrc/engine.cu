@@ -184,6 +184,7 @@ struct vx_engine {
   Buf q_img, k_img, vt_img;                          // per-head attention operand images (tcgen05 attention)
   bool decode_fused = true;                          // 3-barrier persistent decode variant (bf16); VX_DECODE_FUSED=0 disables
   int decode_fused_maxb = 2;
+  int decode_cluster_grid = -1;                      // CTAs of the batch-1 cluster kernel on this device (0: not launchable; -1: not asked yet)
   void* ff2_t_blob = nullptr;                        // 12 x [4096][1024] bf16
   bool attn_t5 = false;
   bool attn_t5_fuse = false;                         // the QKV GEMM epilogue writes the per-head operand images (NAR layers)
@@ -1117,6 +1118,12 @@ int vx_ar_decode_ex(vx_engine* e, int max_new, int top_k, float top_p, float tem
     const bool batched = e->mode == VX_BF16 && B > 4 && e->num_sms >= 128 && e->num_sms % 4 == 0 && !(mm_env && mm_env[0] == '0');
     pp.fused = (!batched && e->decode_fused && e->mode == VX_BF16 && B <= e->decode_fused_maxb && B * kH * ns <= e->num_sms &&
                 (kFF + e->num_sms - 1) / e->num_sms <= 64 && e->ar[0].ff2_t) ? 1 : 0;
+    {   // batch 1: head groups as 4-CTA clusters, two grid barriers per layer (decode_cluster.cu; default); VX_DECODE_CLUSTER=0 keeps
+        // the 3-barrier kernel, as does a device that cannot hold the 16 head clusters at once
+      const char* ce = getenv("VX_DECODE_CLUSTER");
+      if (e->decode_cluster_grid < 0) e->decode_cluster_grid = decode_cluster_grid(e->num_sms);
+      pp.cluster = (pp.fused && B == 1 && e->decode_cluster_grid > 0 && !(ce && ce[0] == '0')) ? 1 : 0;
+    }
     if (pp.fused) {
       ENS(e->p_xb, (size_t)B * kD * 4);
       ENS(e->p_acc, (size_t)4 * B * kD * 8);
@@ -1152,6 +1159,7 @@ int vx_ar_decode_ex(vx_engine* e, int max_new, int top_k, float top_p, float tem
     {
       const int mr = B <= 1 ? 1 : B <= 2 ? 2 : B <= 4 ? 4 : B <= 8 ? 8 : B <= 16 ? 16 : 32;
       if (pp.att_maxp > 0) e->decode_kernel = "ar_decode_mma_kernel<" + std::to_string(mr < 8 ? 8 : mr) + ">";
+      else if (pp.cluster) e->decode_kernel = "ar_decode_cluster_kernel";
       else if (pp.fused) e->decode_kernel = "ar_decode_fused_kernel<" + std::to_string(mr) + ">";
       else e->decode_kernel = std::string("ar_decode_persistent_kernel<") + (e->mode == VX_BF16 ? "bf16," : "float,") + std::to_string(mr) + ">";
     }
