@@ -555,7 +555,7 @@ def main():
     traffic = None  # measured DRAM bytes per decode step from the committed ncu --set full capture of this kernel
     tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.isfile(tp) and a.dtype == "bf16":
-        traffic = json.load(open(tp)).get("ar_decode_fused_kernel<1>")
+        traffic = json.load(open(tp)).get(decode_kernel)   # keyed by the kernel name the engine reports (None: no capture of that kernel)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, a.min_warmup),
         "ms_per_step": 1e3 * elapsed / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
