@@ -1,9 +1,9 @@
-"""GPU tests of the decode kernels beyond the default batch-1 kernel: the batched tensor-core kernel (default for
+"""GPU tests of the decode kernels: both batch-1 kernels (cluster kernel = default, 3-barrier kernel = fallback), the batched tensor-core kernel (default for
 5 <= B <= 32 at bf16: mma.sync GEMV phases with the batch as N and bf16 hi/lo activations, balanced warp-level attention
 phase over the flattened key space; VX_DECODE_MMA=0 selects the CUDA-core GEMV kernel) and the tcgen05 attention paths.
-(The round-1 experiments -- two-barrier exchange, cluster/DSMEM, TMA-staged weights, trimmed variants, weight ring -- were
-measured on a B200 at the start of round 2, lost against the default kernel (profiles/r02_experiments_call1.log) and were
-deleted.)
+(The round-1 experiments -- two-barrier exchange over L2 flags, an 8-CTA-cluster variant that could not launch, TMA-staged weights,
+trimmed variants, weight ring -- were measured on a B200 at the start of round 2, lost against the then-default kernel
+(profiles/r02_experiments_call1.log) and were deleted; the 4-CTA-cluster kernel of decode_cluster.cu came later in round 2.)
 Same bar as tests/test_gpu_parity.py::test_fused_decode_variant: teacher-forced agreement with the reference's
 bf16-weight tokens wherever the reference's top-1/top-2 margin is binding."""
 import os
