@@ -15,6 +15,9 @@
 // keys are split 4 ways instead of 9 (a different but equally valid order of the softmax fold).
 #include <cooperative_groups.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "decode_fused_common.cuh"
 
 namespace vx {
@@ -462,6 +465,29 @@ cudaError_t launch_decode_cluster(const PParams& p, int num_sms, cudaStream_t st
   if (e != cudaSuccess) return e;
   cfg.stream = st;
   if (grid_out) *grid_out = kCS * n;
+  // Every CTA spins on the grid barrier, so all of them must be resident at once.  A cooperative launch makes the runtime check that
+  // (and fail instead of hanging when the GPU is shared); where the driver does not combine the cooperative attribute with cluster
+  // dimensions the occupancy query above is the guarantee (an otherwise idle device holds exactly `n` clusters of this kernel).
+  static int coop_ok = -1;   // -1 unknown, 0 rejected once, 1 accepted
+  if (coop_ok != 0) {
+    cudaLaunchAttribute a2[2];
+    a2[0] = attrs[0];
+    a2[1].id = cudaLaunchAttributeCooperative;
+    a2[1].val.cooperative = 1;
+    cudaLaunchConfig_t c2 = cfg;
+    c2.attrs = a2;
+    c2.numAttrs = 2;
+    e = cudaLaunchKernelEx(&c2, ar_decode_cluster_kernel, p);
+    if (e == cudaSuccess) {
+      if (coop_ok < 0 && getenv("VX_DECODE_PROF")) fprintf(stderr, "ar_decode_cluster_kernel: cooperative + cluster launch accepted (%d CTAs)\n", kCS * n);
+      coop_ok = 1;
+      return e;
+    }
+    if (coop_ok == 1) return e;      // it worked before: a real failure
+    if (getenv("VX_DECODE_PROF")) fprintf(stderr, "ar_decode_cluster_kernel: cooperative + cluster launch rejected (%s), plain cluster launch\n", cudaGetErrorString(e));
+    cudaGetLastError();
+    coop_ok = 0;
+  }
   return cudaLaunchKernelEx(&cfg, ar_decode_cluster_kernel, p);
 }
 
