@@ -167,7 +167,8 @@ VX_API int vx_encodec_last_timing(vx_encodec* e, float* ms, int64_t* frames, int
 VX_API int vx_last_timing(vx_engine* e, float* ms_prefill, float* ms_decode, float* ms_nar, float* ms_vocos,
                    int64_t* decode_steps, int64_t* kernel_launches);
 VX_API int vx_debug_read(vx_engine* e, const char* what, float* dst, int64_t max_elems, int64_t* out_elems);
-/* Name of the kernel the last vx_ar_decode actually launched (e.g. "ar_decode_fused_kernel<1>", "ar_decode_mma_kernel<32>"):
+/* Name of the kernel the last vx_ar_decode actually launched (e.g. "ar_decode_cluster_kernel" = batch 1, "ar_decode_fused_kernel<2>",
+ * "ar_decode_mma_kernel<32>"):
  * the engine picks the decode kernel from dtype mode, batch size and context, so bench.py reports this string instead of
  * guessing from the environment.  Valid until the next vx_ar_decode / vx_destroy. */
 VX_API const char* vx_last_decode_kernel(vx_engine* e);
