@@ -329,13 +329,26 @@ def test_large_ragged_mixed_language_batch_equals_sequential():
     m.engine.close()
 
 
-@pytest.mark.parametrize("dtype,max_batch", [("fp32", 2), ("fp32", 3), ("bf16", 2), ("bf16", 6)])
+@pytest.mark.parametrize("dtype,max_batch", [
+    ("fp32", 2), ("fp32", 3), ("bf16", 2), ("bf16", 6),
+    # Single-slot engine (found at the end of round 2, tools/repro_mb1.py): ONE bf16 engine with max_batch = 1 that served tiny_en,
+    # then noprompt_en, then the 347-row cfg1 utterance through inference_batch faulted inside vx_nar ("illegal memory access")
+    # although each utterance alone passed -- with either batch-1 decode kernel, with or without NAR chunks.  Cause: the workspaces
+    # are reallocated when the larger utterance arrives and recycled device memory is not zero (stale NaN / Inf patterns in padded
+    # operand rows that are multiplied by exact zeros); engine.cu ensure() now zero-fills a workspace when it grows, and the
+    # sequential flow (tools/repro_mb1.py seq3) passes on the B200.  The continuous single-slot flow below could not be re-run
+    # before the GPU budget ended, so it stays opt-in (VX_TEST_KNOWN_ISSUES=1): an illegal memory access is sticky for the whole
+    # process and would fail every later test.
+    pytest.param("bf16", 1, marks=pytest.mark.skipif(os.environ.get("VX_TEST_KNOWN_ISSUES") != "1",
+                                                      reason="single-slot continuous flow: fixed cause, not re-run on a GPU yet (see comment)")),
+])
 def test_continuous_batching_equals_sequential(dtype, max_batch):
     """more utterances than decode slots -> a slot is handed back the moment its utterance finishes, the next
     pending utterance is prefilled alone into it (vx_slot_prefill) and the paused batch resumes (vx_ar_decode_ex); utterances
     finish at different steps (80 / 96 tokens), so slots are refilled while their neighbours are mid-utterance.  fp32: every
     utterance's tokens equal the unmodified reference's (AR exactly; complete codes for the short cases).  bf16: the same
-    schedule through the bf16 kernels (fused B <= 2, tensor-core batched B = 6) must equal the NON-continuous bf16 run."""
+    schedule through the bf16 kernels (cluster kernel B = 1 -- one slot refilled nine times --, fused B = 2, tensor-core batched
+    B = 6) must equal the NON-continuous bf16 run."""
     names = ["tiny_en", "noprompt_en", "cfg1_short", "noprompt_en", "tiny_en", "tiny_en", "noprompt_en", "cfg1_short", "tiny_en"]
     base = {n: load_golden(n) for n in ("tiny_en", "noprompt_en")}
     g1 = load_golden("cfg1_librispeech")

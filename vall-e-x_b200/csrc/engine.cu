@@ -217,6 +217,12 @@ int ensure(Buf& b, size_t bytes) {
   const size_t want = (bytes + 255) & ~size_t(255);
   cudaError_t err = cudaMalloc(&b.p, want);
   if (err != cudaSuccess) return fail(VX_ERR_CUDA, std::string("cudaMalloc ") + std::to_string(want) + ": " + cudaGetErrorString(err));
+  // A grown workspace starts zeroed, like the first allocation of a process usually is: recycled device memory holds stale bit
+  // patterns (NaN / Inf among them), and padded operand rows that are multiplied by exact zeros must be finite.  Growth is rare
+  // (the buffers only ever grow), so the synchronous fill costs nothing in steady state.
+  err = cudaMemset(b.p, 0, want);
+  if (err == cudaSuccess) err = cudaDeviceSynchronize();
+  if (err != cudaSuccess) return fail(VX_ERR_CUDA, std::string("cudaMemset of a new workspace: ") + cudaGetErrorString(err));
   b.cap = want;
   return VX_OK;
 }
