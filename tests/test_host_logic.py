@@ -361,3 +361,64 @@ def test_inference_batch_chunks_orders_and_lengths():
     torch.manual_seed(7)
     m.inference_batch(items[:1], quiet=True)
     assert fake.seeds[1] == a
+
+
+# ---- prompt making host logic (utils/prompt_making.py:57-120, data/tokenizer.py:98-111) with a stub codec: no GPU ----
+class _StubCodec:
+    sample_rate, channels = 24000, 1
+
+    def __init__(self):
+        self.seen = None
+
+    def encode(self, wav):
+        self.seen = wav
+        T = (wav.shape[-1] + 319) // 320
+        codes = (torch.arange(8)[None, :, None] * 100 + torch.arange(T)[None, None, :]) % 1024
+        return [(codes.to(torch.int64), None)]
+
+
+def test_make_prompt_npz_layout_and_errors(tmp_path, monkeypatch):
+    from vallex_b200 import generation, prompt_making
+    stub = _StubCodec()
+    monkeypatch.setattr(prompt_making, "codec", stub)
+    stereo = torch.stack([torch.linspace(-1, 1, 4800), torch.linspace(1, -1, 4800)])      # mean = 0 everywhere
+    path = prompt_making.make_prompt("p0", (stereo, 24000), transcript=([7, 8, 9], "ja"), save_dir=str(tmp_path))
+    assert tuple(stub.seen.shape) == (1, 1, 4800) and float(stub.seen.abs().max()) < 1e-6   # stereo -> mono mean, [B,1,N]
+    d = np.load(path)
+    assert d["audio_tokens"].shape == (1, 15, 8) and d["audio_tokens"].dtype == np.int64     # [1,T,8] = codes.transpose(2,1)
+    assert d["audio_tokens"][0, 3, 2] == 203 and d["text_tokens"].tolist() == [[7, 8, 9]] and int(d["lang_code"]) == 1
+    audio_prompts, text_prompts, lang_pr = generation._load_prompt(path)                     # what generate_audio reads back
+    assert tuple(audio_prompts.shape) == (1, 15, 8) and lang_pr == "ja"
+    with pytest.raises(ValueError, match="Prompt too long"):                                 # utils/prompt_making.py:60-62
+        prompt_making.make_prompt("p1", (torch.zeros(1, 15 * 24000 + 1), 24000), transcript=([5], "en"), save_dir=str(tmp_path))
+
+
+def test_make_transcript_plumbing(monkeypatch):
+    from vallex_b200 import prompt_making
+    monkeypatch.setattr(prompt_making, "language_identifier", None)
+    monkeypatch.setattr(prompt_making, "transcriber", None)
+    wav = torch.zeros(1, 100)
+    with pytest.raises(RuntimeError, match="language identifier"):
+        prompt_making.make_transcript("n", wav, 24000, "hello there")
+    with pytest.raises(RuntimeError, match="transcriber"):
+        prompt_making.make_transcript("n", wav, 24000, None)
+    prompt_making.set_language_identifier(lambda t: "en")
+    assert prompt_making.make_transcript("n", wav, 24000, "hello there") == ("[EN]hello there[EN]", "en")
+    prompt_making.set_transcriber(lambda w, sr: ("zh", "ni hao"))
+    assert prompt_making.make_transcript("n", wav, 24000, None) == ("[ZH]ni hao.[ZH]", "zh")    # punctuation appended like :55-56
+    monkeypatch.setattr(prompt_making, "language_identifier", None)
+    monkeypatch.setattr(prompt_making, "transcriber", None)
+
+
+def test_convert_audio_and_tokenize_audio_plumbing():
+    from vallex_b200.tokenizer import AudioTokenizer, convert_audio, tokenize_audio
+    stereo = torch.stack([torch.ones(1000), -torch.ones(1000)])
+    mono = convert_audio(stereo, 24000, 24000, 1)
+    assert tuple(mono.shape) == (1, 1000) and float(mono.abs().max()) == 0.0
+    up = convert_audio(torch.zeros(1, 1200), 12000, 24000, 1)                                # resampled by torchaudio on the host
+    assert up.shape[-1] == 2400
+    stub = _StubCodec()
+    out = tokenize_audio(stub, (stereo, 24000))
+    assert tuple(stub.seen.shape) == (1, 1, 1000) and out[0][0].shape == (1, 8, 4)
+    with pytest.raises(RuntimeError, match="CUDA"):                                          # no CPU path
+        AudioTokenizer("cpu", state_dict={})
